@@ -1,0 +1,322 @@
+"""numpy/ctypes front-end of the CPU oracle (``merge_oracle.c``) -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; the product path never routes through it.
+
+Each function restates one reference function on numpy arrays; citations are relative to
+``/root/reference``.  Parity pinning: the reference ships no tests or golden vectors
+(SURVEY.md section 4), so the oracle is pinned against outputs of the unmodified reference run in
+the build container (``tests/golden/make_golden.py``) and against the live reference when
+``/root/reference`` is importable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libmergerec_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile merge_oracle.c with gcc (see oracle/Makefile)."""
+    src = os.path.join(_HERE, "merge_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_max_threads.restype = C.c_int
+    return _lib
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(C.c_int(n))
+
+
+# ----------------------------------------------------------------------------- helpers
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _ptr_array(arrs: Sequence[np.ndarray]):
+    arr = (C.c_void_p * len(arrs))()
+    for i, a in enumerate(arrs):
+        arr[i] = a.ctypes.data
+    return arr
+
+
+# ----------------------------------------------------------------------------- A0: flat layout
+def flatten_model(model: "OrderedDict[str, np.ndarray]") -> Tuple[np.ndarray, "OrderedDict[str, tuple]"]:
+    """merger/utils/model_operations.py:47-63 -- concat of reshape(-1) in dict order, ints -> fp32."""
+    shape_dict = OrderedDict((k, tuple(v.shape)) for k, v in model.items())
+    flat = np.concatenate([np.asarray(v).reshape(-1).astype(np.float32) for v in model.values()])
+    return flat, shape_dict
+
+
+def unflatten_model(flat: np.ndarray, shape_dict) -> "OrderedDict[str, np.ndarray]":
+    """merger/utils/model_operations.py:66-90."""
+    out, start = OrderedDict(), 0
+    for name, shape in shape_dict.items():
+        n = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+        out[name] = flat[start:start + n].reshape(shape)
+        start += n
+    assert start == flat.size, "Flattened tensor size does not match the expected size."
+    return out
+
+
+def segment_table(shape_dict, layer_wise: bool):
+    """Blocks and lambda groups.
+
+    task-wise (weight_learning/module/task_wise.py:36-48): one block [0, d), one group "all".
+    layer-wise (weight_learning/module/layer_wise.py:13-33): one block per tensor, group key =
+    name.split(".")[3] when "encoder.layer." is in the name, else "others"; group ids follow
+    first-appearance order (defaultdict insertion order).
+    Returns (seg_begin int64[P], seg_end int64[P], seg_group int32[P], group_keys list[str]).
+    """
+    sizes = [int(np.prod(s, dtype=np.int64)) if len(s) else 1 for s in shape_dict.values()]
+    d = int(sum(sizes))
+    if not layer_wise:
+        return (np.zeros(1, np.int64), np.full(1, d, np.int64), np.zeros(1, np.int32), ["all"])
+    keys: List[str] = []
+    begins, ends, groups = [], [], []
+    off = 0
+    for name, n in zip(shape_dict.keys(), sizes):
+        key = name.split(".")[3] if "encoder.layer." in name else "others"
+        if key not in keys:
+            keys.append(key)
+        begins.append(off)
+        ends.append(off + n)
+        groups.append(keys.index(key))
+        off += n
+    return (np.asarray(begins, np.int64), np.asarray(ends, np.int64), np.asarray(groups, np.int32), keys)
+
+
+# ----------------------------------------------------------------------------- merger
+def task_vectors(base: np.ndarray, models: Sequence[np.ndarray]) -> np.ndarray:
+    """A2 get_task_vectors, merger/algorithms/task_vector.py:8-10."""
+    base = _f32(base)
+    models = [_f32(m) for m in models]
+    K, d = len(models), base.size
+    T = np.empty((K, d), np.float32)
+    lib().orc_task_vectors(_ptr(base), _ptr_array(models), C.c_int(K), C.c_int64(d), _ptr(T))
+    return T
+
+
+def merge_task_vector(base, models, weights: Sequence[float]) -> np.ndarray:
+    """A1 merge_task_vector, merger/algorithms/task_vector.py:13-34 (weights: python floats -> fp32)."""
+    assert len(models) == len(weights), "Number of models and weights should match."
+    base = _f32(base)
+    models = [_f32(m) for m in models]
+    w = np.asarray(weights, dtype=np.float64).astype(np.float32)
+    out = np.empty_like(base)
+    lib().orc_merge_task_vector(_ptr(base), _ptr_array(models), C.c_int(len(models)),
+                                C.c_int64(base.size), _ptr(w), _ptr(out))
+    return out
+
+
+def merge_linear(models, weights: Sequence[float]) -> np.ndarray:
+    """A10 merge_linear, merger/algorithms/linear.py:8-27."""
+    assert len(models) == len(weights), "Number of models and weights should match."
+    models = [_f32(m) for m in models]
+    w = np.asarray(weights, dtype=np.float64).astype(np.float32)
+    out = np.empty_like(models[0])
+    lib().orc_merge_linear(_ptr_array(models), C.c_int(len(models)), C.c_int64(out.size), _ptr(w), _ptr(out))
+    return out
+
+
+def lambda_merge(base, T, w, seg_begin=None, seg_end=None, seg_group=None) -> np.ndarray:
+    """A3/A4 _merge_task_vectors (task_wise.py:36-48, layer_wise.py:64-83). w is (G,K) fp32."""
+    base, T = _f32(base), _f32(T)
+    K, d = T.shape
+    w = _f32(w).reshape(-1, K)
+    if seg_begin is None:
+        seg_begin, seg_end, seg_group = np.zeros(1, np.int64), np.full(1, d, np.int64), np.zeros(1, np.int32)
+    seg_begin = np.ascontiguousarray(seg_begin, np.int64)
+    seg_end = np.ascontiguousarray(seg_end, np.int64)
+    seg_group = np.ascontiguousarray(seg_group, np.int32)
+    out = np.zeros(d, np.float32)  # layer_wise.py:65 zero-initialises
+    lib().orc_lambda_merge(_ptr(base), _ptr(T), C.c_int64(d), C.c_int(K), C.c_int64(d), _ptr(w),
+                           _ptr(seg_begin), _ptr(seg_end), _ptr(seg_group), C.c_int(len(seg_begin)), _ptr(out))
+    return out
+
+
+def combine_lambda(gw, pw, gb, use_softmax: bool) -> np.ndarray:
+    """w = gw * (softmax(pw) if use_softmax else pw) + gb  (task_wise.py:37-42, layer_wise.py:67-74).
+
+    fp32 throughout; softmax follows torch.softmax's max-subtracted form.  Bits of exp() are
+    libm-dependent, so parity tests feed the kernels the same fp32 w instead of comparing this.
+    """
+    gw, pw, gb = _f32(gw), _f32(pw), _f32(gb)
+    if use_softmax:
+        m = pw.max(axis=-1, keepdims=True)
+        e = np.exp(pw - m).astype(np.float32)
+        pw = e / e.sum(axis=-1, keepdims=True, dtype=np.float32)
+    return (gw * pw + gb).astype(np.float32)
+
+
+def lambda_grad(grad, T, G: int = 1, seg_begin=None, seg_end=None, seg_group=None) -> np.ndarray:
+    """A5: dL/dw[g,k] = sum_{p in g} sum_j grad[j] T[k,j]; fp64 truth, returns (G,K) float64."""
+    grad, T = _f32(grad), _f32(T)
+    K, d = T.shape
+    if seg_begin is None:
+        seg_begin, seg_end, seg_group = np.zeros(1, np.int64), np.full(1, d, np.int64), np.zeros(1, np.int32)
+    seg_begin = np.ascontiguousarray(seg_begin, np.int64)
+    seg_end = np.ascontiguousarray(seg_end, np.int64)
+    seg_group = np.ascontiguousarray(seg_group, np.int32)
+    out = np.zeros((G, K), np.float64)
+    lib().orc_lambda_grad(_ptr(grad), _ptr(T), C.c_int64(d), C.c_int(K), _ptr(seg_begin), _ptr(seg_end),
+                          _ptr(seg_group), C.c_int(len(seg_begin)), C.c_int(G), _ptr(out))
+    return out
+
+
+def ties_topk_count(density: float, d: int) -> int:
+    """ties.py:14-15: int(density * numel) in Python double arithmetic."""
+    return int(density * d)
+
+
+def ties_select(base, models, density: float, weights: Optional[Sequence[float]] = None) -> np.ndarray:
+    """A6 selection (ties.py:8-23) under the canonical lowest-index tie rule. Returns uint64 cut[K]:
+    element j of model k survives iff ((bits(|u|) << 32) | (0xFFFFFFFF - j)) >= cut[k]."""
+    base = _f32(base)
+    models = [_f32(m) for m in models]
+    K, d = len(models), base.size
+    assert d <= 2 ** 32
+    cut = np.zeros(K, np.uint64)
+    w = None if weights is None else np.asarray(weights, np.float64).astype(np.float32)
+    lib().orc_ties_select(_ptr(base), _ptr_array(models), C.c_int(K), C.c_int64(d),
+                          None if w is None else _ptr(w), C.c_int64(ties_topk_count(density, d)), _ptr(cut))
+    return cut
+
+
+def ties_vectors(base, models, density: float, return_masks: bool = False):
+    """A6-A8 get_ties_vectors, merger/algorithms/ties.py:55-72."""
+    base = _f32(base)
+    models = [_f32(m) for m in models]
+    K, d = len(models), base.size
+    cut = ties_select(base, models, density)
+    That = np.empty((K, d), np.float32)
+    trim = np.empty((K, d), np.uint8) if return_masks else None
+    elect = np.empty((K, d), np.uint8) if return_masks else None
+    lib().orc_ties_vectors(_ptr(base), _ptr_array(models), C.c_int(K), C.c_int64(d), _ptr(cut), _ptr(That),
+                           None if trim is None else _ptr(trim), None if elect is None else _ptr(elect))
+    if return_masks:
+        return That, trim.astype(bool), elect.astype(bool), cut
+    return That
+
+
+def merge_ties(base, models, weights: Sequence[float], density: float) -> np.ndarray:
+    """A9 merge_ties, merger/algorithms/ties.py:75-83 (trim + weighted sum only)."""
+    assert len(models) == len(weights), "Number of models and weights should match."
+    base = _f32(base)
+    models = [_f32(m) for m in models]
+    cut = ties_select(base, models, density, weights)
+    w = np.asarray(weights, np.float64).astype(np.float32)
+    out = np.empty_like(base)
+    lib().orc_merge_ties(_ptr(base), _ptr_array(models), C.c_int(len(models)), C.c_int64(base.size),
+                         _ptr(w), _ptr(cut), _ptr(out))
+    return out
+
+
+# ----------------------------------------------------------------------------- evaluator
+def scores_f32(U, I) -> np.ndarray:
+    """B1: scores = U @ I.T (module/recommender/module.py:137), fp32 BLAS."""
+    return _f32(U) @ _f32(I).T
+
+
+def scores_f64(U, I) -> np.ndarray:
+    return np.asarray(U, np.float64) @ np.asarray(I, np.float64).T
+
+
+def normalize(x) -> np.ndarray:
+    """_maybe_normalize for cosine similarity (module.py:74-77): x / max(||x||_2, 1e-12)."""
+    x = _f32(x)
+    nrm = np.sqrt((x * x).sum(axis=-1, keepdims=True, dtype=np.float32)).astype(np.float32)
+    return (x / np.maximum(nrm, np.float32(1e-12))).astype(np.float32)
+
+
+def topk_rows(scores, k: int, id_base: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """B2 (evaluator/evaluator.py:43) under the canonical order (score desc, id asc)."""
+    scores = _f32(scores)
+    Q, N = scores.shape
+    assert k <= N
+    vals = np.empty((Q, k), np.float32)
+    ids = np.empty((Q, k), np.int32)
+    lib().orc_topk_rows(_ptr(scores), C.c_int64(Q), C.c_int64(N), C.c_int64(N), C.c_int(k),
+                        C.c_int32(id_base), _ptr(vals), _ptr(ids))
+    return vals, ids
+
+
+def topk_merge(vals, ids) -> Tuple[np.ndarray, np.ndarray]:
+    """Merge (G,Q,K) per-shard lists into (Q,K) under the canonical order."""
+    vals = _f32(vals)
+    ids = np.ascontiguousarray(ids, np.int32)
+    G, Q, K = vals.shape
+    ov = np.empty((Q, K), np.float32)
+    oi = np.empty((Q, K), np.int32)
+    lib().orc_topk_merge(_ptr(vals), _ptr(ids), C.c_int(G), C.c_int64(Q), C.c_int(K), _ptr(ov), _ptr(oi))
+    return ov, oi
+
+
+def label_rank(ids, labels) -> np.ndarray:
+    ids = np.ascontiguousarray(ids, np.int32)
+    labels = np.ascontiguousarray(labels, np.int64)
+    Q, K = ids.shape
+    rank = np.empty(Q, np.int32)
+    lib().orc_label_rank(_ptr(ids), C.c_int64(Q), C.c_int(K), _ptr(labels), _ptr(rank))
+    return rank
+
+
+def _log2_f32(x: int) -> float:
+    """float(torch.log2(torch.tensor(x)))  (metrics.py:84): int64 -> fp32 log2 -> python float.
+    torch's result equals the correctly rounded fp32 log2 for every x in 2..1025 (pinned by
+    tests/golden/evaluator.npz:ndcg_gain_table); numpy's own fp32 log2 is off by one ulp at 8 of them."""
+    return float(np.float32(math.log2(x)))
+
+
+def evaluate_ids(pred_ids, labels, metrics: Sequence[str], ks: Sequence[int], prefix: str = "") -> Dict[str, float]:
+    """B3/B4: Recall (metrics.py:35-59) and NDCG (metrics.py:62-88) on predicted id lists, with
+    the reference's row-order python ``sum()/len`` and its key order (evaluator.py:11-15,45-47)."""
+    pred = np.asarray(pred_ids).tolist()
+    true = np.asarray(labels).tolist()
+    out: Dict[str, float] = {}
+    for metric in metrics:
+        for k in ks:
+            vals = []
+            for p, t in zip(pred, true):
+                p = p[:k]
+                if metric == "RECALL":
+                    vals.append(1.0 if t in p else 0.0)
+                elif metric == "NDCG":
+                    vals.append(1 / _log2_f32(p.index(t) + 2) if t in p else 0.0)
+                else:
+                    raise KeyError(metric)
+            name = {"RECALL": "Recall", "NDCG": "NDCG"}[metric]
+            out[f"{prefix}{name}@{k}"] = sum(vals) / len(vals) if vals else 0.0
+    return out
+
+
+def evaluate(scores, labels, metrics: Sequence[str], ks: Sequence[int], prefix: str = "") -> Dict[str, float]:
+    """Evaluator.__call__ (evaluator/evaluator.py:31-49) with canonical top-K order."""
+    _, ids = topk_rows(scores, max(ks))
+    return evaluate_ids(ids, labels, metrics, ks, prefix)

@@ -1,0 +1,205 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference)
+on seeded synthetic inputs.  Run in the build container only (the reference does not travel):
+
+    python tests/golden/make_golden.py
+
+Inputs are regenerated in the tests from the same numpy (PCG64) seeds via mergerec_b200.synth, so
+only reference OUTPUTS are stored.  The oracle process is pinned to ATEN_CPU_CAPABILITY=avx2 so the
+bits do not depend on the host CPU.
+"""
+import os
+import sys
+
+os.environ.setdefault("ATEN_CPU_CAPABILITY", "avx2")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, "/root/reference")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from mergerec_b200 import synth  # noqa: E402
+from rec_retrieval.evaluator import Evaluator  # noqa: E402
+from rec_retrieval.evaluator.metrics import NDCG, Recall  # noqa: E402
+from rec_retrieval.merger import ModelMerger  # noqa: E402
+from rec_retrieval.merger.algorithms.linear import merge_linear  # noqa: E402
+from rec_retrieval.merger.algorithms.task_vector import get_task_vectors, merge_task_vector  # noqa: E402
+from rec_retrieval.merger.algorithms.ties import get_ties_vectors, merge_ties  # noqa: E402
+from rec_retrieval.merger.enums import LearnType, MergeType  # noqa: E402
+from rec_retrieval.merger.weight_learning import load_merging_module  # noqa: E402
+from rec_retrieval.merger.weight_learning.module.layer_wise import TaskVectorMergingModuleLayerWise  # noqa: E402
+from rec_retrieval.merger.weight_learning.module.task_wise import TaskVectorMergingModuleTaskWise  # noqa: E402
+
+import golden_cases as gc  # noqa: E402  (tests/golden_cases.py: the shared case definitions)
+
+T = torch.from_numpy
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"  {name}.npz  {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def gen_merge_flat():
+    out = {}
+    for case in gc.MERGE_FLAT_CASES:
+        base, models = synth.make_flat(case["d"], case["K"], seed=case["seed"])
+        tb, tm = T(base), [T(m) for m in models]
+        out[f"{case['name']}/task_vector"] = merge_task_vector(tb, tm, case["weights"]).numpy()
+        out[f"{case['name']}/linear"] = merge_linear(models=tm, weights=case["weights"]).numpy()
+        out[f"{case['name']}/task_vectors"] = get_task_vectors(tb, tm).numpy()
+    save("merge_flat", **out)
+
+
+def gen_model_merger():
+    out = {}
+    for case in gc.MODEL_MERGER_CASES:
+        shapes = synth.tiny_shapes(recformer=case["recformer"])
+        base, models = synth.make_state_dicts(shapes, case["K"], seed=case["seed"], sigma=1e-2)
+        tbase = {k: T(v) for k, v in base.items()}
+        tmodels = [{k: T(v) for k, v in m.items()} for m in models]
+        merger = ModelMerger(tmodels, tbase)  # align_key_order=True -> sorted keys
+        out[f"{case['name']}/keys"] = np.array(list(merger.shape_dict.keys()))
+        out[f"{case['name']}/base_flat"] = merger.base_model.numpy()
+        for mt, w, kw in case["merges"]:
+            sd = merger.merge(mt, w, **kw)
+            flat = torch.cat([v.reshape(-1) for v in sd.values()]).numpy()
+            out[f"{case['name']}/{mt}"] = flat
+    save("model_merger", **out)
+
+
+class _NoModel(torch.nn.Module):
+    def forward(self, x):
+        return x
+
+
+def gen_lambda():
+    out = {}
+    for case in gc.LAMBDA_CASES:
+        shapes = synth.tiny_shapes(recformer=case["recformer"])
+        base, models = synth.make_state_dicts(shapes, case["K"], seed=case["seed"], sigma=1e-2)
+        tbase = {k: T(v) for k, v in base.items()}
+        tmodels = [{k: T(v) for k, v in m.items()} for m in models]
+        merger = ModelMerger(tmodels, tbase, align_key_order=False)
+        tv = get_task_vectors(merger.base_model, merger.models)
+        K = case["K"]
+        rng = np.random.Generator(np.random.PCG64(case["seed"] + 100))
+        for learn in ("task", "layer"):
+            cls = TaskVectorMergingModuleTaskWise if learn == "task" else TaskVectorMergingModuleLayerWise
+            for softmax in (False, True):
+                mod = cls(merger.base_model, tv, _NoModel(), merger.shape_dict, disable_softmax=not softmax)
+                keys = list(mod.per_weights.keys())
+                with torch.no_grad():
+                    for key in keys:
+                        mod.per_weights[key].copy_(T(rng.uniform(0.1, 0.5, size=K).astype(np.float32)))
+                        mod.global_weights[key].fill_(float(rng.uniform(0.8, 1.2)))
+                        mod.global_biases[key].fill_(float(rng.uniform(-0.05, 0.05)))
+                merged = mod._merge_task_vectors()
+                g = T(rng.standard_normal(merged.numel(), dtype=np.float32))
+                (merged * g).sum().backward()
+                tag = f"{case['name']}/{learn}/softmax{int(softmax)}"
+                out[f"{tag}/keys"] = np.array(keys)
+                out[f"{tag}/per_weights"] = np.stack([mod.per_weights[k].detach().numpy() for k in keys])
+                out[f"{tag}/global_weights"] = np.stack([mod.global_weights[k].detach().numpy() for k in keys])
+                out[f"{tag}/global_biases"] = np.stack([mod.global_biases[k].detach().numpy() for k in keys])
+                # the effective (G,K) lambda exactly as torch computed it (fed verbatim to kernels)
+                ws = []
+                for key in keys:
+                    pw = mod.per_weights[key].detach()
+                    if softmax:
+                        pw = torch.softmax(pw, dim=0)
+                    ws.append((mod.global_weights[key].detach() * pw + mod.global_biases[key].detach()).numpy())
+                out[f"{tag}/w"] = np.stack(ws)
+                out[f"{tag}/merged"] = merged.detach().numpy()
+                out[f"{tag}/grad_out"] = g.numpy()
+                out[f"{tag}/grad_per_weights"] = np.stack([mod.per_weights[k].grad.numpy() for k in keys])
+                out[f"{tag}/grad_global_weights"] = np.stack([mod.global_weights[k].grad.numpy() for k in keys])
+                out[f"{tag}/grad_global_biases"] = np.stack([mod.global_biases[k].grad.numpy() for k in keys])
+    save("lambda_merge", **out)
+
+
+def gen_ties():
+    out = {}
+    for case in gc.TIES_CASES:
+        base, models = synth.make_flat(case["d"], case["K"], seed=case["seed"], tie_free=case["tie_free"],
+                                       quantize=case.get("quantize", 0.0))
+        tb, tm = T(base), [T(m) for m in models]
+        out[f"{case['name']}/ties_vectors"] = get_ties_vectors(tb, tm, case["density"]).numpy()
+        out[f"{case['name']}/merge_ties"] = merge_ties(tb, tm, case["weights"], case["density"]).numpy()
+    save("ties", **out)
+
+
+def gen_evaluator():
+    out = {}
+    table = [1 / (torch.log2(torch.tensor(r + 2)).item()) for r in range(1024)]
+    out["ndcg_gain_table"] = np.asarray(table, np.float64)
+    for case in gc.EVAL_CASES:
+        users, items, labels = synth.make_catalog(case["Q"], case["N"], case["E"], kind=case["kind"], seed=case["seed"])
+        scores = T(users) @ T(items).T
+        tl = T(labels)
+        ev = Evaluator(case["metrics"], case["ks"])
+        res = ev(scores, tl, metric_prefix=case["prefix"])
+        out[f"{case['name']}/raw_keys"] = np.array(list(res.keys()))
+        out[f"{case['name']}/raw_values"] = np.asarray(list(res.values()), np.float64)
+        out[f"{case['name']}/raw_topk"] = torch.topk(scores, max(case["ks"]), dim=1).indices.numpy()
+        # canonical ids: stable descending sort of the reference's fp32 scores (lowest id wins ties)
+        canon = torch.sort(scores, dim=1, descending=True, stable=True).indices[:, : max(case["ks"])]
+        out[f"{case['name']}/canon_topk"] = canon.numpy().astype(np.int32)
+        vals = {}
+        for m in case["metrics"]:
+            for k in case["ks"]:
+                obj = {"RECALL": Recall, "NDCG": NDCG}[m](k)
+                vals[case["prefix"] + obj.name] = obj(y_true=tl, y_pred=canon)
+        out[f"{case['name']}/canon_keys"] = np.array(list(vals.keys()))
+        out[f"{case['name']}/canon_values"] = np.asarray(list(vals.values()), np.float64)
+    save("evaluator", **out)
+
+
+def gen_module_e2e():
+    """load_merging_module on the toy encoder + 3 Adam steps on lambda (stack B of SURVEY.md section 3)."""
+    from toy_model import ToyEncoder, make_toy_state_dicts
+
+    out = {}
+    for case in gc.MODULE_CASES:
+        pre, fts = make_toy_state_dicts(case["K"], seed=case["seed"])
+        torch.manual_seed(1234)
+        model = ToyEncoder()
+        mod = load_merging_module(
+            MergeType[case["merge_type"]], LearnType[case["learn_type"]], model, pre, fts, ignore_keys=set(),
+            ties_density=case.get("density"), initial_per_weight=0.3, disable_softmax=case["disable_softmax"],
+        )
+        rng = np.random.Generator(np.random.PCG64(case["seed"] + 7))
+        ids = T(rng.integers(0, 37, size=(3, 6, 5)).astype(np.int64))
+        tgt = T(rng.standard_normal((3, 6, 24), dtype=np.float32))
+        opt = torch.optim.Adam(mod.trainable_parameters(True, True, False), lr=1e-2)
+        traj, losses = [], []
+        out[f"{case['name']}/merged0"] = mod._merge_task_vectors().detach().numpy()
+        for step in range(3):
+            opt.zero_grad()
+            rep = mod(ids[step])
+            loss = ((rep - tgt[step]) ** 2).mean()
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+            traj.append(np.stack([mod.per_weights[k].detach().numpy().copy() for k in mod.per_weights.keys()]))
+        out[f"{case['name']}/keys"] = np.array(list(mod.per_weights.keys()))
+        out[f"{case['name']}/per_weights_traj"] = np.stack(traj)
+        out[f"{case['name']}/losses"] = np.asarray(losses, np.float64)
+        sd = mod.get_state_dict()
+        out[f"{case['name']}/final_flat"] = torch.cat([v.reshape(-1) for v in sd.values()]).detach().numpy()
+        out[f"{case['name']}/sd_keys"] = np.array(list(sd.keys()))
+    save("module_e2e", **out)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
+    gen_merge_flat()
+    gen_model_merger()
+    gen_lambda()
+    gen_ties()
+    gen_evaluator()
+    gen_module_e2e()
