@@ -1,0 +1,146 @@
+"""Workloads of bench.py: each is one BASELINE.json configuration, built from synthetic inputs of the named
+shapes.  Algorithmic byte counts follow SURVEY.md section 8(d) / DESIGN.md "Measurement"."""
+from __future__ import annotations
+
+import os
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from mergerec_b200 import synth
+
+GB = 1e9
+
+
+class Workload:
+    name = ""
+    metric = ""
+    unit = ""
+    dtype = "f32"
+    scaling = "weak"
+    launches_per_step = 0
+    e2e_steps_cap = 5
+    h2d_bytes = 0
+    d2h_bytes = 0
+
+    def __init__(self, rank: int, world: int, device: Optional[torch.device]):
+        self.rank, self.world, self.device = rank, world, device
+
+    def extra(self) -> Dict:
+        return {}
+
+
+def _pinned(t: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t)
+    return out
+
+
+class LambdaMergeK8(Workload):
+    """Per-layer lambda merge of 8 BLaIR-base task vectors (the merge half of BASELINE config 2; A4).
+    Algorithmic bytes per step: (K+2) * d * 4 (read base + K task-vector rows, write merged)."""
+
+    name = "lambda_merge_k8"
+    metric = "merge GB/s (algorithmic bytes / time)"
+    unit = "GB/s"
+    K = 8
+    launches_per_step = 1
+
+    def __init__(self, rank, world, device):
+        super().__init__(rank, world, device)
+        self.shapes = synth.roberta_shapes()
+        self.d = synth.total_numel(self.shapes)
+        self.bytes_per_step = (self.K + 2) * self.d * 4
+
+    def config(self):
+        return {"workload": "BLaIR-base (RoBERTa-base, d=124,645,632, P=199) K=8 per-layer lambda merge (G=13) "
+                            "from stored task vectors; merge half of BASELINE config 2",
+                "K": self.K, "d": self.d, "G": 13, "l2": "inputs (4.5 GB) exceed L2, no flush needed",
+                "parallelism": f"replicas x{self.world}" if self.world > 1 else "1 GPU"}
+
+    # -- device-resident arm
+    def setup(self):
+        from mergerec_b200.merger.algorithms import get_task_vectors
+        from mergerec_b200.merger.layout import FlatLayout
+        g = torch.Generator(device=self.device).manual_seed(1234 + self.rank)
+        d, K = self.d, self.K
+        self.base = torch.randn(d, generator=g, device=self.device) * 0.02
+        self.models = [self.base + 1e-3 * torch.randn(d, generator=g, device=self.device) for _ in range(K)]
+        self.T = get_task_vectors(self.base, self.models)
+        self.rows = list(self.T.unbind(0))
+        self.layout = FlatLayout.from_shape_dict(self.shapes)
+        self.seg_end, self.seg_group, keys = self.layout.device_blocks(True, self.device)
+        rng = np.random.Generator(np.random.PCG64(5))
+        self.w = torch.from_numpy(rng.uniform(0.1, 0.5, size=(len(keys), K)).astype(np.float32)).to(self.device)
+        self.out = torch.empty(d, dtype=torch.float32, device=self.device)
+
+    def step(self):
+        from mergerec_b200 import _lib
+        from mergerec_b200.merger.algorithms._common import merge_axpy
+        merge_axpy(self.base, self.rows, self.w, _lib.MR_ORDER_SUM_FIRST, False, self.seg_end, self.seg_group, out=self.out)
+
+    def units_per_step_all_ranks(self):
+        return self.bytes_per_step * self.world / GB
+
+    # -- end-to-end arm: pinned host flat vectors in, merged flat vector out
+    def setup_e2e(self):
+        self.h_base = _pinned(self.base.cpu())
+        self.h_T = _pinned(self.T.cpu())
+        self.h_out = torch.empty(self.d, dtype=torch.float32, pin_memory=True)
+        self.h2d_bytes = (self.K + 1) * self.d * 4
+        self.d2h_bytes = self.d * 4
+
+    def step_e2e(self):
+        self.base.copy_(self.h_base, non_blocking=True)
+        self.T.copy_(self.h_T, non_blocking=True)
+        self.step()
+        self.h_out.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    # -- roofline of the dominant kernel (the only one here)
+    def roofline(self, peaks):
+        from bench import event_time_ms
+        ms = event_time_ms(self.step, 20)
+        achieved = self.bytes_per_step / GB / (ms * 1e-3)
+        return {"bound": "hbm", "kernel": "mr::merge_kernel<8, SUM_FIRST, segmented, vec4>", "achieved": achieved,
+                "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
+                "algorithmic_bytes_per_launch": self.bytes_per_step}
+
+    # -- CPU arms (oracle port of the reference algorithm)
+    def _cpu_inputs(self, d):
+        rng = np.random.Generator(np.random.PCG64(7))
+        base = rng.standard_normal(d, dtype=np.float32) * np.float32(0.02)
+        T = rng.standard_normal((self.K, d), dtype=np.float32) * np.float32(1e-3)
+        from oracle import oracle as orc
+        sb, se, sg, keys = orc.segment_table(self.shapes, layer_wise=True)
+        w = rng.uniform(0.1, 0.5, size=(len(keys), self.K)).astype(np.float32)
+        return base, T, w, sb, se, sg
+
+    def _cpu_time(self, reps):
+        from oracle import oracle as orc
+        base, T, w, sb, se, sg = self._cpu_inputs(self.d)
+        orc.lambda_merge(base, T, w, sb, se, sg)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            orc.lambda_merge(base, T, w, sb, se, sg)
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)), orc.max_threads()
+
+    def cpu_baseline(self):
+        t, cores = self._cpu_time(3)
+        return {"value": self.bytes_per_step / GB / t, "unit": self.unit, "cores": cores, "kind": "port",
+                "sample": f"full workload (d={self.d}, K={self.K}), median of 3 after 1 warm-up, OpenMP C oracle",
+                "seconds_per_step": t}
+
+    def reference_arm(self, steps, warmup):
+        t, cores = self._cpu_time(max(1, min(steps, 5)))
+        return {"value": self.bytes_per_step / GB / t, "ms_per_step": t * 1e3, "cores": cores,
+                "sample": f"full workload (d={self.d}, K={self.K}) per step, OpenMP C oracle port"}
+
+
+WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8}
+DEFAULT_WORKLOAD = LambdaMergeK8.name

@@ -200,9 +200,10 @@ task_vectors_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d
 extern "C" int mr_task_vectors(const float* base, const float* const* models, int K, int64_t d, float* T,
                                int64_t ldT, mr_stream_t stream) {
     using namespace mr;
-    MR_REQUIRE(base && models && T, "mr_task_vectors: null pointer");
     MR_REQUIRE(d >= 0 && ldT >= d, "mr_task_vectors: need ldT >= d >= 0");
+    MR_REQUIRE(K >= 1 && K <= MR_MAX_K, "mr_task_vectors: K=%d outside [1,%d]", K, MR_MAX_K);
     if (d == 0) return MR_OK;
+    MR_REQUIRE(base && models && T, "mr_task_vectors: null pointer");
     bool vec = host_aligned16(base) && host_aligned16(T) && (ldT % 4 == 0);
     for (int k = 0; k < K && k < MR_MAX_K; ++k) vec = vec && host_aligned16(models[k]);
     const int64_t work = vec ? (d >> 2) + 3 : d;
@@ -222,14 +223,15 @@ extern "C" int mr_merge_axpy(const float* base, const float* const* src, int K, 
                              int G, const int64_t* seg_end, const int32_t* seg_group, int P, int order,
                              int src_is_model, float* out, mr_stream_t stream) {
     using namespace mr;
+    MR_REQUIRE(d >= 0 && G >= 1 && P >= 1, "mr_merge_axpy: need d >= 0, G >= 1, P >= 1");
+    MR_REQUIRE(K >= 1 && K <= MR_MAX_K, "mr_merge_axpy: K=%d outside [1,%d]", K, MR_MAX_K);
+    if (d == 0) return MR_OK;
     MR_REQUIRE(src && w && out, "mr_merge_axpy: null pointer");
     MR_REQUIRE(order == MR_ORDER_LINEAR || base, "mr_merge_axpy: base required unless order == LINEAR");
-    MR_REQUIRE(d >= 0 && G >= 1 && P >= 1, "mr_merge_axpy: need d >= 0, G >= 1, P >= 1");
     MR_REQUIRE(P == 1 || (seg_end && seg_group), "mr_merge_axpy: P > 1 needs seg_end and seg_group");
     MR_REQUIRE(P <= kMaxSmemSegs * 8, "mr_merge_axpy: too many blocks (P=%d)", P);
     MR_REQUIRE(order >= 0 && order <= 2, "mr_merge_axpy: bad order %d", order);
     MR_REQUIRE(!(order == MR_ORDER_LINEAR && src_is_model), "mr_merge_axpy: LINEAR takes sources as they are");
-    if (d == 0) return MR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     MR_DISPATCH_K(K, {
         if (order == MR_ORDER_BASE_FIRST) {
