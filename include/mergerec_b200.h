@@ -72,6 +72,67 @@ int mr_merge_axpy(const float* base, const float* const* src, int K, int64_t d, 
                   const int64_t* seg_end, const int32_t* seg_group, int P, int order, int src_is_model,
                   float* out, mr_stream_t stream);
 
+/* The lambda-gradient reduction of collaborative merging (A5):
+ *     out[g, k] = sum_{p : seg_group[p] == g} sum_{j < seg_len[p]} grad_p[j] * T[k, seg_off[p] + j]
+ * Replaces the autograd backward of the reference's merge + P parameter views
+ *                        ref: weight_learning/module/task_wise.py:43-47, layer_wise.py:76-82,
+ *                             weight_learning/utils.py:11-15,43-51
+ *   grad_ptrs   dev array of P dev pointers: the gradient of each state_dict tensor, read in place
+ *               (NULL = no gradient = zeros).  Pointing all of them into one flat (d) gradient is fine.
+ *   seg_off     dev, P flat offsets of the tensors;  seg_len: dev, P element counts;
+ *   seg_group   dev, P group ids in [0, G) or NULL when G == 1.
+ *   T           dev, K rows of d floats with leading dimension ldT (task vectors / TIES vectors).
+ *   out         dev, (G, K) fp32.  Deterministic (fixed two-stage fp64 reduction tree, no atomics).
+ *   ws          dev scratch of at least mr_lambda_grad_workspace_bytes(d, P, K) bytes. */
+int64_t mr_lambda_grad_workspace_bytes(int64_t d, int P, int K);
+int mr_lambda_grad(const float* const* grad_ptrs, const int64_t* seg_off, const int64_t* seg_len,
+                   const int32_t* seg_group, int P, int64_t d, const float* T, int64_t ldT, int K, int G, float* out,
+                   void* ws, int64_t ws_bytes, mr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Merger: TIES (A6-A9).                                          ref: merger/algorithms/ties.py
+ * Elements of model k are ordered by the 64-bit key (bits(|u_kj|) << 32) | (0xFFFFFFFF - j), with
+ * u_kj = models[k][j] - base[j] (times w[k] when w != NULL, ties.py:20-21): larger magnitude first, lower
+ * flat index first among equal magnitudes.  Model k keeps element j iff key >= cut[k], where cut[k] is the
+ * k_cnt-th largest key, k_cnt = int(density * d) computed by the caller in double arithmetic (ties.py:14-15).
+ * The trim is global over the flat vector like the reference.  d must be < 2^32.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t mr_ties_workspace_bytes(int64_t d, int K);
+
+enum mr_ties_status {
+    MR_TIES_SEARCHING = 0, /* kernels still queued (never observed after a stream sync) */
+    MR_TIES_DONE = 1,
+    /* < 0: the sampled bracket missed or overflowed (possible on adversarial inputs, e.g. millions of equal
+     * magnitudes); call mr_ties_select_exact */
+};
+
+/* Fast path, stream-ordered: cut (dev, K x uint64) and status (dev, K x int32) are written by the queued
+ * kernels.  One pass over base + K models ((K+1)*d*4 bytes) plus a ~0.5 M-element sample per model. */
+int mr_ties_select(const float* base, const float* const* models, int K, int64_t d, const float* w, int64_t k_cnt,
+                   uint64_t* cut, int32_t* status, void* ws, int64_t ws_bytes, mr_stream_t stream);
+/* Exact path for any input; SYNCHRONOUS (reads bracket state back between passes; <= 8 passes). */
+int mr_ties_select_exact(const float* base, const float* const* models, int K, int64_t d, const float* w,
+                         int64_t k_cnt, uint64_t* cut, int32_t* status, void* ws, int64_t ws_bytes,
+                         mr_stream_t stream);
+
+enum mr_ties_mode {
+    /* out = That (K rows, leading dimension ldo): trimmed updates that agree with the elected sign, divided by
+     * their per-column count (get_ties_vectors, ties.py:55-72).  w unused. */
+    MR_TIES_VECTORS = 0,
+    /* out = base + sum_dim0_k trim_k(w[k] * (m_k - base))   (merge_ties, ties.py:75-83).  w: dev (K); cut must
+     * come from a select run with the same w. */
+    MR_TIES_TRIMSUM = 1,
+    /* out = base + sum_dim0_k w[g,k] * That[k] without materialising That: get_ties_vectors followed by the
+     * lambda merge (A3/A4) in one pass.  w: dev (G, K); seg_end / seg_group / P as in mr_merge_axpy. */
+    MR_TIES_FUSED_MERGE = 2,
+};
+
+/* trim_mask / elect_mask: optional dev (K, d) bytes: survived the magnitude trim / survived trim and sign
+ * election (That != 0).  NULL to skip. */
+int mr_ties_build(const float* base, const float* const* models, int K, int64_t d, const uint64_t* cut, int mode,
+                  const float* w, int G, const int64_t* seg_end, const int32_t* seg_group, int P, float* out,
+                  int64_t ldo, uint8_t* trim_mask, uint8_t* elect_mask, mr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmergerec_b200.so")
 
 MR_ORDER_BASE_FIRST, MR_ORDER_SUM_FIRST, MR_ORDER_LINEAR = 0, 1, 2
+MR_TIES_VECTORS, MR_TIES_TRIMSUM, MR_TIES_FUSED_MERGE = 0, 1, 2
 MR_MAX_K = 16
 
 _lib: Optional[C.CDLL] = None
@@ -27,6 +28,12 @@ SIGNATURES = {
     "mr_last_error": ([], C.c_char_p),
     "mr_task_vectors": ([_vp, _vp, _i32, _i64, _vp, _i64, _vp], C.c_int),
     "mr_merge_axpy": ([_vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp], C.c_int),
+    "mr_lambda_grad_workspace_bytes": ([_i64, _i32, _i32], _i64),
+    "mr_lambda_grad": ([_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp], C.c_int),
+    "mr_ties_workspace_bytes": ([_i64, _i32], _i64),
+    "mr_ties_select": ([_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp], C.c_int),
+    "mr_ties_select_exact": ([_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp], C.c_int),
+    "mr_ties_build": ([_vp, _vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp], C.c_int),
 }
 
 

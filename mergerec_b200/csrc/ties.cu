@@ -1,0 +1,780 @@
+// ties.cu -- TIES magnitude trim, sign election and disjoint mean (A6-A9).
+//
+// reference: rec_retrieval/merger/algorithms/ties.py
+//   _compute_sparse_updates :8-28   keep the int(density*d) largest |m_k - base| over the WHOLE flat vector
+//   _compute_final_sign     :31-52  sign vote from the fp32 sums of positive / negative survivors
+//   get_ties_vectors        :55-72  survivors that agree with the elected sign, divided by their count
+//   merge_ties              :75-83  base + sum_k trim_k(w_k * (m_k - base))   (no election, no mean)
+//
+// The trim is an exact order statistic.  Elements are ordered by the composite 64-bit key
+//     key(u, j) = (bits(|u|) << 32) | (0xFFFFFFFF - j)            (larger |u| first, then LOWER index first)
+// and model k keeps element j iff key >= cut[k], where cut[k] is the k_cnt-th largest key: the canonical
+// tie rule of SURVEY.md section 0.1-D3 (torch.topk's own order among equal magnitudes is unspecified).
+//
+// Selection = "bracket and refine" on the key space, all with one streaming pass kernel:
+//   fast path (stream-ordered, no host sync):
+//     1. two passes over a strided sample (~0.5 M elements per model) narrow [0, 2^63) to a bracket that
+//        holds the target with overwhelming probability (+-6 sigma of the sample quantile);
+//     2. ONE pass over the full data counts the keys above the bracket exactly, histograms the keys inside
+//        it (1024 linear bins) and stores them (~0.75 % of d) in per-CTA candidate lists;
+//     3. pick the bin holding rank k_cnt, compact its candidates (<= 4096) and sort them in shared memory.
+//   exact path (any input, e.g. millions of equal magnitudes; synchronous): full passes that narrow the
+//     bracket 1024x each (at most 7) until the survivors fit, then steps 2-3.
+// The full pass reads base + K models once ((K+1)*d*4 bytes, HBM-bound: a subtract, an AND and two compares
+// per element; no atomics outside the bracket).  The build kernels read them once more and write the result.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mr {
+
+typedef unsigned long long u64;
+
+constexpr int kTiesBins = 1024;
+constexpr int kTiesThreads = 256;
+constexpr int kTiesFinalCap = 4096;
+constexpr int64_t kTiesSampleQuads = 131072;  // ~0.5 M sampled elements per model
+
+struct TiesState {  // one per model
+    u64 lo, hi;      // inclusive bracket on composite keys
+    u64 above;       // keys > hi seen by the last pass (written by pick from the pass counters)
+    u64 in_bracket;  // keys inside the refined bracket
+    int shift;       // bin = (key - lo) >> shift  (< kTiesBins)
+    int status;      // 0 searching, 1 done, < 0 failed
+};
+
+enum {
+    TIES_ST_SEARCH = 0,
+    TIES_ST_DONE = 1,
+    TIES_ERR_BRACKET_LOW = -1,   // more than k_cnt - 1 keys above the bracket
+    TIES_ERR_BRACKET_HIGH = -2,  // target below the bracket
+    TIES_ERR_TOO_MANY = -3,      // refined bracket does not fit the final sort
+    TIES_ERR_CAND_OVERFLOW = -4, // a per-CTA candidate list overflowed
+    TIES_ERR_INCONSISTENT = -5,
+};
+
+__device__ __forceinline__ u64 ties_key(uint32_t mag, int64_t j) {
+    return ((u64)mag << 32) | (u64)(0xFFFFFFFFu - (uint32_t)j);
+}
+__device__ __forceinline__ int shift_for(u64 width /* hi - lo */) {
+    int s = 0;
+    while ((width >> s) >= (u64)kTiesBins) ++s;
+    return s;
+}
+
+// ---- state init -----------------------------------------------------------------------------------
+__global__ void ties_init_kernel(TiesState* st, int K, u64* cut, int32_t* status, int64_t k_cnt, int64_t d) {
+    const int k = threadIdx.x;
+    if (k >= K) return;
+    TiesState s;
+    s.lo = 0;
+    s.hi = ((u64)0x7FFFFFFFu << 32) | 0xFFFFFFFFull;
+    s.above = 0;
+    s.in_bracket = (u64)d;
+    s.shift = shift_for(s.hi - s.lo);
+    s.status = TIES_ST_SEARCH;
+    if (k_cnt <= 0) { cut[k] = ~(u64)0; s.status = TIES_ST_DONE; }       // keep nothing
+    else if (k_cnt >= d) { cut[k] = 0; s.status = TIES_ST_DONE; }        // keep everything
+    if (st) st[k] = s;
+    status[k] = s.status;
+}
+
+// ---- the pass kernel ------------------------------------------------------------------------------
+struct PassCounters {
+    uint32_t* hist;      // K * kTiesBins
+    u64* above;          // K
+    uint32_t* cand_cnt;  // K * gridDim.x   (COLLECT)
+    u64* cand_keys;      // K * gridDim.x * cand_cap
+    int cand_cap;
+};
+
+template <int K, bool VEC, bool W, bool COLLECT>
+__global__ void __launch_bounds__(kTiesThreads)
+ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const float* __restrict__ w,
+                 int64_t stride, const TiesState* __restrict__ st, PassCounters pc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);              // K * bins
+    u64* s_lo = reinterpret_cast<u64*>(s_hist + K * kTiesBins);            // K
+    u64* s_hi = s_lo + K;                                                  // K
+    int* s_shift = reinterpret_cast<int*>(s_hi + K);                       // K
+    uint32_t* s_cn = reinterpret_cast<uint32_t*>(s_shift + K);             // K (COLLECT)
+
+    for (int i = threadIdx.x; i < K * kTiesBins; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x < K) {
+        s_lo[threadIdx.x] = st[threadIdx.x].lo;
+        s_hi[threadIdx.x] = st[threadIdx.x].hi;
+        s_shift[threadIdx.x] = st[threadIdx.x].shift;
+        s_cn[threadIdx.x] = 0;
+    }
+    __syncthreads();
+
+    uint32_t lo_mag[K], hi_mag[K];
+    uint32_t above[K];  // per-thread counts fit 32 bits (d < 2^32)
+    float wreg[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        lo_mag[k] = (uint32_t)(s_lo[k] >> 32);
+        hi_mag[k] = (uint32_t)(s_hi[k] >> 32);
+        above[k] = 0;
+        wreg[k] = W ? w[k] : 1.0f;
+    }
+
+    const int64_t nq = (d + 3) >> 2;                       // quads of 4 consecutive elements
+    const int64_t nsq = (nq + stride - 1) / stride;        // sampled quads
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+
+    for (int64_t i = gtid; i < nsq; i += gsz) {
+        int64_t q = i * stride;
+        if (stride > 1) {  // jitter inside the stride window so the sample does not alias with row pitches
+            q += (int64_t)((((uint32_t)i * 2654435761u) >> 8) % (uint32_t)stride);
+            if (q >= nq) q = nq - 1;
+        }
+        const int64_t j0 = q << 2;
+        const int nvalid = (int)((d - j0) < 4 ? (d - j0) : 4);
+        float bx[4];
+        float xs[K][4];
+        if (VEC && nvalid == 4) {
+            const float4 b4 = ldg_stream4(base + j0);
+            bx[0] = b4.x; bx[1] = b4.y; bx[2] = b4.z; bx[3] = b4.w;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float4 v = ldg_stream4(models.p[k] + j0);
+                xs[k][0] = v.x; xs[k][1] = v.y; xs[k][2] = v.z; xs[k][3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool ok = c < nvalid;
+                bx[c] = ok ? base[j0 + c] : 0.0f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) xs[k][c] = ok ? models.p[k][j0 + c] : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float u = __fsub_rn(xs[k][c], bx[c]);
+                if (W) u = __fmul_rn(u, wreg[k]);
+                const uint32_t mag = __float_as_uint(u) & 0x7FFFFFFFu;
+                if (c < nvalid) {
+                    if (mag > hi_mag[k]) {
+                        ++above[k];
+                    } else if (mag >= lo_mag[k]) {  // rare: inside or at the edge of the bracket
+                        const u64 key = ties_key(mag, j0 + c);
+                        if (key > s_hi[k]) {
+                            ++above[k];
+                        } else if (key >= s_lo[k]) {
+                            const uint32_t bin = (uint32_t)((key - s_lo[k]) >> s_shift[k]);
+                            atomicAdd(&s_hist[k * kTiesBins + bin], 1u);
+                            if (COLLECT) {
+                                const uint32_t pos = atomicAdd(&s_cn[k], 1u);
+                                if (pos < (uint32_t)pc.cand_cap)
+                                    pc.cand_keys[((size_t)k * gridDim.x + blockIdx.x) * pc.cand_cap + pos] = key;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // block-reduce the above counters (warp shuffle, then one 64-bit atomic per warp and model)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        uint32_t v = above[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&pc.above[k], (u64)v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * kTiesBins; i += blockDim.x) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(&pc.hist[i], v);
+    }
+    if (COLLECT && threadIdx.x < K) pc.cand_cnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_cn[threadIdx.x];
+}
+
+// ---- pick: turn a histogram into a narrower bracket ---------------------------------------------------
+// rank_hi <= rank_lo are 1-based ranks (largest key = rank 1) in the population the pass visited.  The new
+// bracket spans the bins holding rank_hi .. rank_lo.  strict: both ranks must fall inside the old bracket
+// (exact passes, rank_hi == rank_lo == k_cnt); otherwise they are clamped to it (sample passes).
+__global__ void __launch_bounds__(kTiesBins)
+ties_pick_kernel(TiesState* st, const uint32_t* __restrict__ hist, const u64* __restrict__ above_ctr, int64_t rank_hi,
+                 int64_t rank_lo, int strict, int32_t* status) {
+    __shared__ u64 s_suffix[kTiesBins + 1];
+    __shared__ u64 s_warp[kTiesBins / 32];
+    __shared__ int s_bhi, s_blo;
+    const int k = blockIdx.x;
+    TiesState s = st[k];
+    if (s.status != TIES_ST_SEARCH) return;
+    const int t = threadIdx.x;           // thread t owns bin (bins - 1 - t): an inclusive prefix scan over t
+    const int bin = kTiesBins - 1 - t;   // is an inclusive suffix sum over bins
+    u64 v = hist[k * kTiesBins + bin];
+    // warp inclusive scan
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u64 n = __shfl_up_sync(0xffffffffu, v, off);
+        if ((t & 31) >= off) v += n;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = v;
+    if (t == 0) { s_bhi = -1; s_blo = -1; }
+    __syncthreads();
+    if (t < 32) {
+        u64 x = s_warp[t];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u64 n = __shfl_up_sync(0xffffffffu, x, off);
+            if (t >= off) x += n;
+        }
+        s_warp[t] = x;
+    }
+    __syncthreads();
+    if (t >= 32) v += s_warp[(t >> 5) - 1];
+    s_suffix[bin] = v;  // keys in bins >= bin
+    if (t == 0) s_suffix[kTiesBins] = 0;
+    __syncthreads();
+    const u64 above = above_ctr[k];
+    const u64 total_in = s_suffix[0];
+    // bin holding rank r: the largest b with above + suffix[b] >= r
+    const u64 ge = above + s_suffix[bin], gt = above + s_suffix[bin + 1];
+    if (ge >= (u64)rank_hi && gt < (u64)rank_hi) s_bhi = bin;
+    if (ge >= (u64)rank_lo && gt < (u64)rank_lo) s_blo = bin;
+    __syncthreads();
+    if (t == 0) {
+        int bhi = s_bhi, blo = s_blo;
+        int err = 0;
+        if (bhi < 0) {  // rank_hi above the bracket (<= above) or below it
+            if ((u64)rank_hi <= above) { if (strict) err = TIES_ERR_BRACKET_LOW; bhi = kTiesBins - 1; }
+            else { if (strict) err = TIES_ERR_BRACKET_HIGH; bhi = 0; }
+        }
+        if (blo < 0) {
+            if ((u64)rank_lo <= above) { if (strict) err = TIES_ERR_BRACKET_LOW; blo = kTiesBins - 1; }
+            else { if (strict) err = TIES_ERR_BRACKET_HIGH; blo = 0; }
+        }
+        if (rank_hi < 1) bhi = kTiesBins - 1;
+        if (err) {
+            s.status = err;
+        } else {
+            const u64 new_lo = s.lo + ((u64)blo << s.shift);
+            u64 new_hi = s.lo + (((u64)bhi + 1) << s.shift) - 1;
+            if (new_hi > s.hi || bhi == kTiesBins - 1) new_hi = s.hi;
+            s.above = above + s_suffix[bhi + 1];
+            s.in_bracket = s_suffix[blo] - s_suffix[bhi + 1];
+            s.lo = new_lo;
+            s.hi = new_hi;
+            s.shift = shift_for(new_hi - new_lo);
+        }
+        (void)total_in;
+        st[k] = s;
+        status[k] = s.status;
+    }
+}
+
+// ---- compact the candidates of the refined bracket ------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ties_compact_kernel(TiesState* st, const uint32_t* __restrict__ cand_cnt, const u64* __restrict__ cand_keys,
+                    int cand_cap, int n_lists, uint32_t* fin_cnt, u64* fin_keys, int32_t* status) {
+    const int k = blockIdx.y;
+    if (st[k].status != TIES_ST_SEARCH) return;
+    const u64 lo = st[k].lo, hi = st[k].hi;
+    for (int c = blockIdx.x; c < n_lists; c += gridDim.x) {
+        const uint32_t n = cand_cnt[(size_t)k * n_lists + c];
+        if (n > (uint32_t)cand_cap) {
+            if (threadIdx.x == 0) { st[k].status = TIES_ERR_CAND_OVERFLOW; status[k] = TIES_ERR_CAND_OVERFLOW; }
+            continue;
+        }
+        const u64* keys = cand_keys + ((size_t)k * n_lists + c) * cand_cap;
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+            const u64 key = keys[e];
+            if (key >= lo && key <= hi) {
+                const uint32_t pos = atomicAdd(&fin_cnt[k], 1u);
+                if (pos < (uint32_t)kTiesFinalCap) fin_keys[(size_t)k * kTiesFinalCap + pos] = key;
+            }
+        }
+    }
+}
+
+// ---- final: sort the <= 4096 survivors in shared memory and read off the cut -------------------------------
+__global__ void __launch_bounds__(1024)
+ties_final_kernel(TiesState* st, const uint32_t* __restrict__ fin_cnt, const u64* __restrict__ fin_keys, int64_t k_cnt,
+                  u64* cut, int32_t* status) {
+    __shared__ u64 s_keys[kTiesFinalCap];
+    const int k = blockIdx.x;
+    TiesState s = st[k];
+    if (s.status != TIES_ST_SEARCH) return;
+    const uint32_t n = fin_cnt[k];
+    const long long r = (long long)k_cnt - (long long)s.above;  // 1-based rank inside the bracket
+    int err = 0;
+    if (n > (uint32_t)kTiesFinalCap) err = TIES_ERR_TOO_MANY;
+    else if ((u64)n != s.in_bracket || r < 1 || r > (long long)n) err = TIES_ERR_INCONSISTENT;
+    if (err) {
+        if (threadIdx.x == 0) { st[k].status = err; status[k] = err; }
+        return;
+    }
+    for (int i = threadIdx.x; i < kTiesFinalCap; i += blockDim.x)
+        s_keys[i] = (i < (int)n) ? fin_keys[(size_t)k * kTiesFinalCap + i] : 0;  // real keys are > 0 ... or equal 0 only
+    __syncthreads();                                                              // for (mag 0, j = 2^32-1): harmless
+    for (int size = 2; size <= kTiesFinalCap; size <<= 1) {      // bitonic sort, descending
+        for (int strd = size >> 1; strd > 0; strd >>= 1) {
+            for (int i = threadIdx.x; i < kTiesFinalCap / 2; i += blockDim.x) {
+                const int a = 2 * i - (i & (strd - 1));
+                const int b = a + strd;
+                const bool desc = ((a & size) == 0);
+                const u64 x = s_keys[a], y = s_keys[b];
+                if ((x < y) == desc) { s_keys[a] = y; s_keys[b] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        cut[k] = s_keys[r - 1];
+        st[k].status = TIES_ST_DONE;
+        status[k] = TIES_ST_DONE;
+    }
+}
+
+// ---- build kernels (A6-A9) ----------------------------------------------------------------------------------
+enum { TIES_MODE_VECTORS = 0, TIES_MODE_TRIMSUM = 1, TIES_MODE_FUSED_MERGE = 2 };
+
+struct BuildArgs {
+    float* out;           // VECTORS: That (K rows, ldo).  TRIMSUM / FUSED_MERGE: merged (d)
+    int64_t ldo;
+    uint8_t* trim_mask;   // optional (K, d) bytes
+    uint8_t* elect_mask;  // optional (K, d) bytes
+    const float* w;       // TRIMSUM: (K) weights applied before the trim.  FUSED_MERGE: (G, K) lambdas
+    const int64_t* seg_end;   // FUSED_MERGE with P > 1
+    const int32_t* seg_group;
+    int P;
+};
+
+template <int K, int MODE>
+__device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_t j, bool tail, const u64 (&cut)[K],
+                                            const float* __restrict__ wk, float (&res)[K], uint32_t& trim_bits,
+                                            uint32_t& elect_bits) {
+    float s[K];
+    trim_bits = 0;
+    elect_bits = 0;
+    const uint32_t jl = 0xFFFFFFFFu - (uint32_t)j;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float u = __fsub_rn(x[k], b);
+        if (MODE == TIES_MODE_TRIMSUM) u = __fmul_rn(u, wk[k]);
+        const uint32_t mag = __float_as_uint(u) & 0x7FFFFFFFu;
+        const uint32_t cm = (uint32_t)(cut[k] >> 32), cl = (uint32_t)cut[k];
+        const bool keep = (mag > cm) || (mag == cm && jl >= cl);
+        s[k] = keep ? u : 0.0f;
+        trim_bits |= (keep ? 1u : 0u) << k;
+    }
+    if constexpr (MODE == TIES_MODE_TRIMSUM) {
+        res[0] = __fadd_rn(b, torch_sum_dim0<K>(s, tail));   // ties.py:81-83
+    } else {
+    float pp[K], nn[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        pp[k] = s[k] > 0.0f ? s[k] : 0.0f;   // ties.py:35
+        nn[k] = s[k] < 0.0f ? s[k] : 0.0f;   // ties.py:36
+    }
+    const float pos = torch_sum_dim0<K>(pp, tail);
+    const float neg = torch_sum_dim0<K>(nn, tail);
+    bool plus;
+    if (pos != 0.0f && neg != 0.0f) {
+        plus = fabsf(pos) >= fabsf(neg);      // ties.py:41-45
+    } else {
+        const float t = __fadd_rn(pos, neg);  // ties.py:47-48; sign 0 -> +1 (ties.py:50); NaN -> sign NaN -> "> 0" false
+        plus = !(t < 0.0f) && !(t != t);
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        res[k] = plus ? pp[k] : nn[k];        // ties.py:61-65
+        cnt += (res[k] != 0.0f) ? 1 : 0;
+        elect_bits |= ((res[k] != 0.0f) ? 1u : 0u) << k;
+    }
+    if (cnt > 1) {                             // ties.py:68-70 (cnt == 0: all zeros; cnt == 1: x / 1)
+        const float fc = (float)cnt;
+#pragma unroll
+        for (int k = 0; k < K; ++k) res[k] = __fdiv_rn(res[k], fc);
+    }
+    }
+}
+
+template <int K, int MODE, bool VEC, bool MASKS>
+__global__ void __launch_bounds__(kTiesThreads)
+ties_build_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const u64* __restrict__ cut_dev,
+                  BuildArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 cut[K];
+    float wk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        cut[k] = cut_dev[k];
+        wk[k] = (MODE == TIES_MODE_TRIMSUM) ? a.w[k] : 0.0f;
+    }
+    // FUSED_MERGE: lambda rows and the block table in shared memory
+    float* s_w = reinterpret_cast<float*>(smem_raw);
+    int64_t* s_end = nullptr;
+    int32_t* s_grp = nullptr;
+    int G = 1;
+    if (MODE == TIES_MODE_FUSED_MERGE) {
+        G = (int)a.ldo;  // number of lambda groups travels in ldo for this mode
+        s_end = reinterpret_cast<int64_t*>(smem_raw + ((G * K * 4 + 15) & ~15));
+        s_grp = reinterpret_cast<int32_t*>(s_end + (a.P > 1 ? a.P : 0));
+        for (int i = threadIdx.x; i < G * K; i += blockDim.x) s_w[i] = a.w[i];
+        if (a.P > 1)
+            for (int i = threadIdx.x; i < a.P; i += blockDim.x) { s_end[i] = a.seg_end[i]; s_grp[i] = a.seg_group[i]; }
+        __syncthreads();
+    }
+    const int64_t tail0 = d & ~(int64_t)31;
+    const int64_t nq = (d + 3) >> 2;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    int hint = 0;
+
+    for (int64_t q = gtid; q < nq; q += gsz) {
+        const int64_t j0 = q << 2;
+        const int nvalid = (int)((d - j0) < 4 ? (d - j0) : 4);
+        const bool full = VEC && nvalid == 4;
+        float bx[4];
+        float xs[K][4];
+        if (full) {
+            const float4 b4 = ldg_stream4(base + j0);
+            bx[0] = b4.x; bx[1] = b4.y; bx[2] = b4.z; bx[3] = b4.w;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float4 v = ldg_stream4(models.p[k] + j0);
+                xs[k][0] = v.x; xs[k][1] = v.y; xs[k][2] = v.z; xs[k][3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool ok = c < nvalid;
+                bx[c] = ok ? base[j0 + c] : 0.0f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) xs[k][c] = ok ? models.p[k][j0 + c] : 0.0f;
+            }
+        }
+        float res[4][K];
+        uint32_t tb[4], eb[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float x[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) x[k] = xs[k][c];
+            ties_column<K, MODE>(x, bx[c], j0 + c, (K >= 5) && (j0 + c >= tail0), cut, wk, res[c], tb[c], eb[c]);
+        }
+        if (MODE == TIES_MODE_VECTORS) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float* o = a.out + (int64_t)k * a.ldo + j0;
+                if (full) stg_stream4(o, make_float4(res[0][k], res[1][k], res[2][k], res[3][k]));
+                else
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (c < nvalid) o[c] = res[c][k];
+            }
+        } else if (MODE == TIES_MODE_TRIMSUM) {
+            float* o = a.out + j0;
+            if (full) stg_stream4(o, make_float4(res[0][0], res[1][0], res[2][0], res[3][0]));
+            else
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (c < nvalid) o[c] = res[c][0];
+        } else {  // FUSED_MERGE: base + sum_dim0_k(w[g,k] * That[k])  (layer_wise.py:76-82 order, blocks = tensors)
+            float r[4];
+            int p = 0;
+            if (a.P > 1) {
+                // first block with seg_end > j0
+                if (!(j0 < s_end[hint] && (hint == 0 || j0 >= s_end[hint - 1]))) {
+                    int lo = 0, hi = a.P - 1;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_end[mid] > j0) hi = mid; else lo = mid + 1; }
+                    hint = lo;
+                }
+                p = hint;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                bool tail;
+                const float* wrow = s_w;
+                if (a.P > 1) {
+                    while (c < nvalid && j0 + c >= s_end[p]) ++p;
+                    const int64_t beg = p ? s_end[p - 1] : 0;
+                    const int64_t n = s_end[p] - beg;
+                    tail = (K >= 5) && ((j0 + c - beg) >= (n & ~(int64_t)31));
+                    wrow = s_w + s_grp[p] * K;
+                } else {
+                    tail = (K >= 5) && (j0 + c >= tail0);
+                }
+                float prod[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wrow[k], res[c][k]);
+                r[c] = __fadd_rn(bx[c], torch_sum_dim0<K>(prod, tail));
+            }
+            float* o = a.out + j0;
+            if (full) stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
+            else
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (c < nvalid) o[c] = r[c];
+        }
+        if (MASKS) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nvalid) {
+                        if (a.trim_mask) a.trim_mask[(int64_t)k * d + j0 + c] = (tb[c] >> k) & 1u;
+                        if (a.elect_mask) a.elect_mask[(int64_t)k * d + j0 + c] = (eb[c] >> k) & 1u;
+                    }
+        }
+    }
+}
+
+// ---- host-side plumbing ---------------------------------------------------------------------------------------
+struct TiesWs {
+    TiesState* st;
+    uint32_t* hist;      // K * bins       } zeroed together before every pass
+    u64* above;          // K              }
+    uint32_t* fin_cnt;   // K              }
+    uint32_t* cand_cnt;  // K * n_lists
+    u64* fin_keys;       // K * final cap
+    u64* cand_keys;      // K * n_lists * cand_cap
+    size_t zero_bytes;   // bytes from hist to the end of fin_cnt
+    int n_lists, cand_cap;
+    size_t total;
+};
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int ties_pass_blocks() { return sm_count() * 4; }
+
+static int64_t ties_sample_stride(int64_t d) {
+    const int64_t nq = (d + 3) >> 2;
+    const int64_t s = nq / kTiesSampleQuads;
+    return s < 1 ? 1 : s;
+}
+
+// sampled element count for a given stride (must mirror the kernel's iteration domain; the jittered last quad may
+// be the partial one -- the error of at most 3 elements is absorbed by the margin)
+static int64_t ties_sample_count(int64_t d, int64_t stride) {
+    const int64_t nq = (d + 3) >> 2;
+    const int64_t nsq = (nq + stride - 1) / stride;
+    return stride == 1 ? d : nsq * 4;
+}
+
+static void ties_sample_ranks(int64_t d, int64_t k_cnt, int64_t n_s, int64_t* r_hi, int64_t* r_lo) {
+    const double rs = (double)k_cnt * (double)n_s / (double)d;
+    double var = rs * (1.0 - rs / (double)n_s);
+    if (var < 0) var = 0;
+    const double m = 6.0 * sqrt(var) + 8.0;
+    *r_hi = (int64_t)floor(rs - m);
+    *r_lo = (int64_t)ceil(rs + m);
+}
+
+static TiesWs ties_layout(void* ws, int64_t d, int K) {
+    TiesWs L;
+    const int n_lists = ties_pass_blocks();
+    // expected fraction of keys inside the sample bracket: the +-6 sigma rank window plus bin slack
+    const int64_t stride = ties_sample_stride(d);
+    const int64_t n_s = ties_sample_count(d, stride);
+    int64_t r_hi, r_lo;
+    ties_sample_ranks(d, d / 5, n_s, &r_hi, &r_lo);
+    double frac = (double)(r_lo - r_hi + 2) / (double)n_s + 6.0 / kTiesBins * 0.25;
+    if (frac > 1.0) frac = 1.0;
+    const double expect = (double)d * frac / n_lists;
+    int64_t cap = (int64_t)(3.0 * expect) + 512;
+    if (cap > d + 4) cap = d + 4;
+    L.n_lists = n_lists;
+    L.cand_cap = (int)cap;
+    char* p = reinterpret_cast<char*>(ws);
+    size_t off = 0;
+    L.st = reinterpret_cast<TiesState*>(p + off); off += align256((size_t)K * sizeof(TiesState));
+    const size_t z0 = off;
+    L.hist = reinterpret_cast<uint32_t*>(p + off); off += align256((size_t)K * kTiesBins * 4);
+    L.above = reinterpret_cast<u64*>(p + off); off += align256((size_t)K * 8);
+    L.fin_cnt = reinterpret_cast<uint32_t*>(p + off); off += align256((size_t)K * 4);
+    L.zero_bytes = off - z0;
+    L.cand_cnt = reinterpret_cast<uint32_t*>(p + off); off += align256((size_t)K * n_lists * 4);
+    L.fin_keys = reinterpret_cast<u64*>(p + off); off += align256((size_t)K * kTiesFinalCap * 8);
+    L.cand_keys = reinterpret_cast<u64*>(p + off); off += align256((size_t)K * n_lists * (size_t)cap * 8);
+    L.total = off;
+    return L;
+}
+
+template <int K>
+static int ties_launch_pass(const float* base, const float* const* models, int64_t d, const float* w, int64_t stride,
+                            bool collect, const TiesWs& L, cudaStream_t st) {
+    PtrPack<K> pack;
+    bool vec = host_aligned16(base);
+    for (int k = 0; k < K; ++k) { pack.p[k] = models[k]; vec = vec && host_aligned16(models[k]); }
+    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap};
+    const size_t smem = (size_t)K * kTiesBins * 4 + (size_t)K * (8 + 8 + 4 + 4) + 16;
+    const int blocks = ties_pass_blocks();
+    cudaError_t e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
+    if (e != cudaSuccess) { set_error("mr_ties_select: memset: %s", cudaGetErrorString(e)); return (int)e; }
+#define MR_PASS(VEC, W, COLLECT)                                                                               \
+    do {                                                                                                       \
+        auto kern = ties_pass_kernel<K, VEC, W, COLLECT>;                                                      \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kern<<<blocks, kTiesThreads, smem, st>>>(base, pack, d, w, stride, L.st, pc);                          \
+    } while (0)
+    if (vec) {
+        if (w) { if (collect) MR_PASS(true, true, true); else MR_PASS(true, true, false); }
+        else   { if (collect) MR_PASS(true, false, true); else MR_PASS(true, false, false); }
+    } else {
+        if (w) { if (collect) MR_PASS(false, true, true); else MR_PASS(false, true, false); }
+        else   { if (collect) MR_PASS(false, false, true); else MR_PASS(false, false, false); }
+    }
+#undef MR_PASS
+    MR_CUDA_LAUNCH_CHECK("mr_ties_select(pass)");
+    return MR_OK;
+}
+
+static int ties_finish(const TiesWs& L, int K, int64_t k_cnt, u64* cut, int32_t* status, cudaStream_t st) {
+    ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, k_cnt, k_cnt, 1, status);
+    dim3 grid((unsigned)(L.n_lists < 256 ? L.n_lists : 256), (unsigned)K);
+    ties_compact_kernel<<<grid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.fin_cnt,
+                                              L.fin_keys, status);
+    ties_final_kernel<<<K, 1024, 0, st>>>(L.st, L.fin_cnt, L.fin_keys, k_cnt, cut, status);
+    MR_CUDA_LAUNCH_CHECK("mr_ties_select(finish)");
+    return MR_OK;
+}
+
+static int ties_check_args(const float* base, const float* const* models, int K, int64_t d, const void* cut,
+                           const void* status, const void* ws, int64_t ws_bytes, const char* who) {
+    MR_REQUIRE(K >= 1 && K <= MR_MAX_K, "%s: K=%d outside [1,%d]", who, K, MR_MAX_K);
+    MR_REQUIRE(d >= 0 && d < ((int64_t)1 << 32), "%s: need 0 <= d < 2^32", who);
+    MR_REQUIRE(cut && status, "%s: null output", who);
+    if (d == 0) return MR_OK;
+    MR_REQUIRE(base && models && ws, "%s: null pointer", who);
+    if (ws_bytes < mr_ties_workspace_bytes(d, K)) {
+        set_error("%s: workspace too small (%lld < %lld bytes)", who, (long long)ws_bytes,
+                  (long long)mr_ties_workspace_bytes(d, K));
+        return MR_ERR_WORKSPACE;
+    }
+    return MR_OK;
+}
+
+}  // namespace mr
+
+extern "C" int64_t mr_ties_workspace_bytes(int64_t d, int K) {
+    if (d <= 0 || K < 1 || K > MR_MAX_K) return 256;
+    return (int64_t)mr::ties_layout(nullptr, d, K).total;
+}
+
+extern "C" int mr_ties_select(const float* base, const float* const* models, int K, int64_t d, const float* w,
+                              int64_t k_cnt, uint64_t* cut, int32_t* status, void* ws, int64_t ws_bytes,
+                              mr_stream_t stream) {
+    using namespace mr;
+    int rc = ties_check_args(base, models, K, d, cut, status, ws, ws_bytes, "mr_ties_select");
+    if (rc != MR_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d == 0) {  // nothing to keep: cut = ~0
+        ties_init_kernel<<<1, 32, 0, st>>>(nullptr, K, reinterpret_cast<u64*>(cut), status, 0, 0);
+        MR_CUDA_LAUNCH_CHECK("mr_ties_select(init)");
+        return MR_OK;
+    }
+    const TiesWs L = ties_layout(ws, d, K);
+    ties_init_kernel<<<1, 32, 0, st>>>(L.st, K, reinterpret_cast<u64*>(cut), status, k_cnt, d);
+    MR_CUDA_LAUNCH_CHECK("mr_ties_select(init)");
+    if (k_cnt <= 0 || k_cnt >= d) return MR_OK;
+    const int64_t stride = ties_sample_stride(d);
+    const int64_t n_s = ties_sample_count(d, stride);
+    int64_t r_hi, r_lo;
+    ties_sample_ranks(d, k_cnt, n_s, &r_hi, &r_lo);
+    MR_DISPATCH_K(K, {
+        for (int it = 0; it < 2; ++it) {  // two sample passes: 2^63 -> quarter-octave bins -> ~1 % bracket
+            rc = ties_launch_pass<KK>(base, models, d, w, stride, false, L, st);
+            if (rc != MR_OK) return rc;
+            ties_pick_kernel<<<KK, kTiesBins, 0, st>>>(L.st, L.hist, L.above, r_hi, r_lo, 0, status);
+        }
+        rc = ties_launch_pass<KK>(base, models, d, w, 1, true, L, st);
+        if (rc != MR_OK) return rc;
+    });
+    return ties_finish(L, K, k_cnt, reinterpret_cast<u64*>(cut), status, st);
+}
+
+// Exact path for any input (e.g. millions of equal magnitudes).  SYNCHRONOUS: reads the bracket state back after
+// every pass.  At most 7 narrowing passes + 1 collecting pass over the data.
+extern "C" int mr_ties_select_exact(const float* base, const float* const* models, int K, int64_t d, const float* w,
+                                    int64_t k_cnt, uint64_t* cut, int32_t* status, void* ws, int64_t ws_bytes,
+                                    mr_stream_t stream) {
+    using namespace mr;
+    int rc = ties_check_args(base, models, K, d, cut, status, ws, ws_bytes, "mr_ties_select_exact");
+    if (rc != MR_OK) return rc;
+    if (d == 0) return mr_ties_select(base, models, K, d, w, k_cnt, cut, status, ws, ws_bytes, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const TiesWs L = ties_layout(ws, d, K);
+    ties_init_kernel<<<1, 32, 0, st>>>(L.st, K, reinterpret_cast<u64*>(cut), status, k_cnt, d);
+    MR_CUDA_LAUNCH_CHECK("mr_ties_select_exact(init)");
+    if (k_cnt <= 0 || k_cnt >= d) return MR_OK;
+    TiesState host[MR_MAX_K];
+    for (int it = 0; it < 8; ++it) {
+        MR_DISPATCH_K(K, {
+            rc = ties_launch_pass<KK>(base, models, d, w, 1, false, L, st);
+            if (rc != MR_OK) return rc;
+            ties_pick_kernel<<<KK, kTiesBins, 0, st>>>(L.st, L.hist, L.above, k_cnt, k_cnt, 1, status);
+        });
+        cudaError_t e = cudaMemcpyAsync(host, L.st, (size_t)K * sizeof(TiesState), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("mr_ties_select_exact: %s", cudaGetErrorString(e)); return (int)e; }
+        bool fits = true;
+        for (int k = 0; k < K; ++k) {
+            if (host[k].status < 0) { set_error("mr_ties_select_exact: model %d failed with status %d", k, host[k].status); return MR_ERR_UNSUPPORTED; }
+            if (host[k].status == TIES_ST_SEARCH && host[k].in_bracket > (u64)(L.cand_cap < kTiesFinalCap ? L.cand_cap : kTiesFinalCap)) fits = false;
+        }
+        if (fits) break;
+    }
+    MR_DISPATCH_K(K, {
+        rc = ties_launch_pass<KK>(base, models, d, w, 1, true, L, st);
+        if (rc != MR_OK) return rc;
+    });
+    rc = ties_finish(L, K, k_cnt, reinterpret_cast<u64*>(cut), status, st);
+    if (rc != MR_OK) return rc;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("mr_ties_select_exact: %s", cudaGetErrorString(e)); return (int)e; }
+    return MR_OK;
+}
+
+extern "C" int mr_ties_build(const float* base, const float* const* models, int K, int64_t d, const uint64_t* cut,
+                             int mode, const float* w, int G, const int64_t* seg_end, const int32_t* seg_group, int P,
+                             float* out, int64_t ldo, uint8_t* trim_mask, uint8_t* elect_mask, mr_stream_t stream) {
+    using namespace mr;
+    MR_REQUIRE(K >= 1 && K <= MR_MAX_K, "mr_ties_build: K=%d outside [1,%d]", K, MR_MAX_K);
+    MR_REQUIRE(d >= 0 && d < ((int64_t)1 << 32), "mr_ties_build: need 0 <= d < 2^32");
+    MR_REQUIRE(mode >= 0 && mode <= 2, "mr_ties_build: bad mode %d", mode);
+    if (d == 0) return MR_OK;
+    MR_REQUIRE(base && models && cut && out, "mr_ties_build: null pointer");
+    MR_REQUIRE(mode == TIES_MODE_VECTORS || w, "mr_ties_build: this mode needs weights");
+    MR_REQUIRE(mode != TIES_MODE_VECTORS || ldo >= d, "mr_ties_build: need ldo >= d");
+    MR_REQUIRE(mode != TIES_MODE_FUSED_MERGE || (G >= 1 && P >= 1 && (P == 1 || (seg_end && seg_group))),
+               "mr_ties_build: FUSED_MERGE needs G >= 1 and a block table when P > 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool vec = host_aligned16(base) && host_aligned16(out) && (mode != TIES_MODE_VECTORS || (ldo % 4 == 0));
+    for (int k = 0; k < K; ++k) vec = vec && host_aligned16(models[k]);
+    const bool masks = trim_mask || elect_mask;
+    const int64_t nq = (d + 3) >> 2;
+    int64_t blocks = (nq + kTiesThreads - 1) / kTiesThreads;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    BuildArgs a{out, mode == TIES_MODE_FUSED_MERGE ? (int64_t)G : ldo, trim_mask, elect_mask, w, seg_end, seg_group,
+                mode == TIES_MODE_FUSED_MERGE ? P : 1};
+    size_t smem = 16;
+    if (mode == TIES_MODE_FUSED_MERGE) smem = (((size_t)G * K * 4 + 15) & ~(size_t)15) + (P > 1 ? (size_t)P * 12 : 0) + 16;
+#define MR_BUILD(MODE, VEC, MASKS) \
+    ties_build_kernel<KK, MODE, VEC, MASKS><<<(unsigned)blocks, kTiesThreads, smem, st>>>(base, pack, d, reinterpret_cast<const u64*>(cut), a)
+#define MR_BUILD_VM(MODE)                                                        \
+    do {                                                                         \
+        if (vec) { if (masks) MR_BUILD(MODE, true, true); else MR_BUILD(MODE, true, false); }   \
+        else     { if (masks) MR_BUILD(MODE, false, true); else MR_BUILD(MODE, false, false); } \
+    } while (0)
+    MR_DISPATCH_K(K, {
+        PtrPack<KK> pack;
+        for (int k = 0; k < KK; ++k) pack.p[k] = models[k];
+        if (mode == TIES_MODE_VECTORS) MR_BUILD_VM(TIES_MODE_VECTORS);
+        else if (mode == TIES_MODE_TRIMSUM) MR_BUILD_VM(TIES_MODE_TRIMSUM);
+        else MR_BUILD_VM(TIES_MODE_FUSED_MERGE);
+    });
+#undef MR_BUILD_VM
+#undef MR_BUILD
+    MR_CUDA_LAUNCH_CHECK("mr_ties_build");
+    return MR_OK;
+}

@@ -1,15 +1,112 @@
-"""TIES (A6-A9); reference: rec_retrieval/merger/algorithms/ties.py.  Filled in by csrc/ties.cu."""
+"""TIES (A6-A9 of SURVEY.md section 8(a)); reference: rec_retrieval/merger/algorithms/ties.py.
+
+The magnitude trim is global over the flat vector like the reference (``numel = base_model.numel()``,
+ties.py:14-15).  Where the reference leaves the choice among equal magnitudes at the threshold to
+``torch.topk``'s unspecified order, this implementation keeps the LOWEST flat indices (canonical tie rule);
+away from exact threshold ties the results are bit-identical to the reference.
+"""
 from __future__ import annotations
 
-from typing import List
+from typing import List, Optional, Sequence, Tuple
 
+import torch
+
+from ... import _lib
+from ..layout import alloc_rows
 from ..types import FlattenedModel, FlattenedModel2D
+from ._common import as_rows
 
 
-def get_ties_vectors(base_model: FlattenedModel, models: List[FlattenedModel], density: float, **__) -> FlattenedModel2D:
-    raise NotImplementedError("TIES kernels are not built yet")
+def ties_topk_count(density: float, numel: int) -> int:
+    """``int(density * numel)`` in Python double arithmetic (ties.py:14-15)."""
+    return int(density * numel)
+
+
+def ties_select(base_model: FlattenedModel, rows: Sequence[torch.Tensor], density: float,
+                w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-model 64-bit cut keys (int64 tensor of K, bit pattern of the uint64): model k keeps element j iff
+    ``(bits(|u_kj|) << 32 | (0xFFFFFFFF - j)) >= cut[k]``.  Runs the stream-ordered sampled-bracket select and,
+    if a model's bracket missed or overflowed (adversarial inputs), the exact multi-pass select."""
+    lib = _lib.load()
+    K, d = len(rows), base_model.numel()
+    dev = base_model.device
+    k_cnt = ties_topk_count(density, d)
+    ws_bytes = int(lib.mr_ties_workspace_bytes(d, K))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cut = torch.empty(K, dtype=torch.int64, device=dev)
+    status = torch.zeros(K, dtype=torch.int32, device=dev)
+    args = (_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(w), k_cnt, _lib.dptr(cut),
+            _lib.dptr(status), _lib.dptr(ws), ws_bytes, _lib.stream_handle())
+    _lib.check(lib.mr_ties_select(*args), "mr_ties_select")
+    st = status.cpu()
+    if bool((st != 1).any()):
+        _lib.check(lib.mr_ties_select_exact(*args), "mr_ties_select_exact")
+        st = status.cpu()
+        if bool((st != 1).any()):
+            raise _lib.MergeRecLibraryError(f"TIES select failed with status {st.tolist()}")
+    return cut
+
+
+def _build(base_model, rows, cut, mode, w=None, G=1, seg_end=None, seg_group=None, out=None, ldo=0,
+           trim_mask=None, elect_mask=None):
+    K, d = len(rows), base_model.numel()
+    P = 1 if seg_end is None else seg_end.numel()
+    rc = _lib.load().mr_ties_build(_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(cut),
+                                   mode, _lib.dptr(w), G, _lib.dptr(seg_end), _lib.dptr(seg_group), P, _lib.dptr(out),
+                                   ldo, _lib.dptr(trim_mask), _lib.dptr(elect_mask), _lib.stream_handle())
+    _lib.check(rc, "mr_ties_build")
+
+
+def get_ties_vectors(base_model: FlattenedModel, models: List[FlattenedModel], density: float,
+                     return_masks: bool = False, **__):
+    """(K, d) TIES vectors: per model the trimmed update where it agrees with the elected sign, divided by the
+    per-column count of such survivors, so that ``sum_k lambda_k * That[k]`` is the lambda-weighted TIES delta
+    (ties.py:55-72).  ``return_masks=True`` (extension) also returns the (K, d) bool trim and elect masks and
+    the cut keys."""
+    rows = as_rows(models)
+    K, d = len(rows), base_model.numel()
+    cut = ties_select(base_model, rows, density)
+    That = alloc_rows(K, d, base_model.device)
+    trim = elect = None
+    if return_masks:
+        trim = torch.empty((K, d), dtype=torch.uint8, device=base_model.device)
+        elect = torch.empty((K, d), dtype=torch.uint8, device=base_model.device)
+    _build(base_model, rows, cut, _lib.MR_TIES_VECTORS, out=That, ldo=max(That.stride(0), d),
+           trim_mask=trim, elect_mask=elect)
+    if return_masks:
+        return That, trim.bool(), elect.bool(), cut
+    return That
 
 
 def merge_ties(base_model: FlattenedModel, models: List[FlattenedModel], weights: List[float], density: float, **__
                ) -> FlattenedModel:
-    raise NotImplementedError("TIES kernels are not built yet")
+    """``base + sum_k trim_k(weights[k] * (models[k] - base))`` -- the weight is applied BEFORE the trim and there
+    is no sign election or mean, exactly like the reference function of this name (ties.py:75-83)."""
+    assert len(models) == len(weights), "Number of models and weights should match."
+    rows = as_rows(models)
+    dev = base_model.device
+    # `update *= weights[i]` only runs for a non-empty list (ties.py:20); K >= 1 here so it always does
+    w = torch.tensor([float(x) for x in weights], dtype=torch.float32, device=dev)
+    cut = ties_select(base_model, rows, density, w)
+    out = torch.empty_like(base_model)
+    _build(base_model, rows, cut, _lib.MR_TIES_TRIMSUM, w=w, out=out)
+    return out
+
+
+def merge_ties_lambda(base_model: FlattenedModel, models: List[FlattenedModel], density: float, w: torch.Tensor,
+                      seg_end: Optional[torch.Tensor] = None, seg_group: Optional[torch.Tensor] = None,
+                      cut: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> FlattenedModel:
+    """Extension: ``get_ties_vectors`` followed by the (task- or layer-wise) lambda merge in ONE pass that never
+    materialises the (K, d) TIES vectors.  Bit-identical to
+    ``base + (w[g][:, None] * get_ties_vectors(...)).sum(0)`` evaluated block by block like
+    weight_learning/module/layer_wise.py:76-82.  ``w`` is (G, K) fp32 on the device."""
+    rows = as_rows(models)
+    K = len(rows)
+    if cut is None:
+        cut = ties_select(base_model, rows, density)
+    if out is None:
+        out = torch.empty_like(base_model)
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.shape[-1] == K
+    _build(base_model, rows, cut, _lib.MR_TIES_FUSED_MERGE, w=w, G=w.numel() // K, seg_end=seg_end,
+           seg_group=seg_group, out=out)
+    return out

@@ -95,6 +95,14 @@ class FlatLayout:
                                    torch.tensor(grp, dtype=torch.int32, device=device), keys)
         return self._dev_cache[ck]
 
+    def device_segments(self, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(seg_off int64[P], seg_len int64[P]) on the device (cached)."""
+        ck = ("seg", str(device))
+        if ck not in self._dev_cache:
+            self._dev_cache[ck] = (torch.tensor(self.offsets, dtype=torch.int64, device=device),
+                                   torch.tensor(self.sizes, dtype=torch.int64, device=device))
+        return self._dev_cache[ck]
+
     def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         """Slice + reshape views of a flat vector, in layout order."""
         if flat.numel() != self.d:

@@ -1,0 +1,155 @@
+"""GPU parity for TIES (A6-A9): CUDA select + build kernels through the C ABI against the reference's golden
+vectors and the CPU oracle.  Masks, cut keys and vectors are compared bit-for-bit under the canonical
+lowest-index tie rule; against the raw reference (torch.topk's unspecified tie order) differences must be
+confined to columns holding a threshold-magnitude entry."""
+import numpy as np
+import pytest
+import torch
+
+import golden_cases as gc
+from helpers import assert_bit_equal, golden
+from mergerec_b200 import synth
+from mergerec_b200.merger.algorithms import get_ties_vectors, merge_ties
+from mergerec_b200.merger.algorithms.ties import merge_ties_lambda, ties_select, ties_topk_count
+from mergerec_b200.merger.layout import FlatLayout
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def cut_u64(t):
+    return host(t).view(np.uint64)
+
+
+def check_against_oracle(base, models, density, weights=None):
+    tb, tm = dev(base), [dev(m) for m in models]
+    That, trim, elect, cut = get_ties_vectors(tb, tm, density, return_masks=True)
+    oT, otrim, oelect, ocut = orc.ties_vectors(base, models, density, return_masks=True)
+    assert np.array_equal(cut_u64(cut), ocut), "cut keys"
+    assert np.array_equal(host(trim), otrim), "trim mask"
+    assert np.array_equal(host(elect), oelect), "elect mask"
+    assert_bit_equal(host(That), oT, "TIES vectors")
+    if weights is not None:
+        assert_bit_equal(host(merge_ties(tb, tm, weights, density)), orc.merge_ties(base, models, weights, density),
+                         "merge_ties")
+    return That, cut
+
+
+@pytest.mark.parametrize("case", gc.TIES_CASES, ids=lambda c: c["name"])
+def test_ties_vs_golden_and_oracle(case):
+    g = golden("ties")
+    base, models = synth.make_flat(case["d"], case["K"], seed=case["seed"], tie_free=case["tie_free"],
+                                   quantize=case.get("quantize", 0.0))
+    That, cut = check_against_oracle(base, models, case["density"], case["weights"])
+    ref_T = g[f"{case['name']}/ties_vectors"]
+    ref_M = g[f"{case['name']}/merge_ties"]
+    tb, tm = dev(base), [dev(m) for m in models]
+    if case["tie_free"]:
+        assert_bit_equal(host(That), ref_T, "get_ties_vectors vs raw reference")
+        assert_bit_equal(host(merge_ties(tb, tm, case["weights"], case["density"])), ref_M, "merge_ties vs raw reference")
+    else:
+        thr = (cut_u64(cut) >> np.uint64(32)).astype(np.uint32)
+        diff_cols = (host(That).view(np.uint32) != ref_T.view(np.uint32)).any(axis=0)
+        col_has_thr = np.zeros(case["d"], bool)
+        for k, m in enumerate(models):
+            col_has_thr |= np.abs(m - base).view(np.uint32) == thr[k]
+        assert not (diff_cols & ~col_has_thr).any(), "difference vs raw torch.topk outside threshold ties"
+
+
+def test_ties_edge_densities_and_all_ties():
+    base, models = synth.make_flat(1000, 3, seed=5)
+    tb, tm = dev(base), [dev(m) for m in models]
+    for density, expect in [(0.0, 0), (1.0, 1000), (0.0004, 0), (0.9999, 999), (0.001, 1)]:
+        _, trim, _, _ = get_ties_vectors(tb, tm, density, return_masks=True)
+        assert (host(trim).sum(axis=1) == expect).all(), density
+    # a model identical to the base: every |u| == 0 -> all ties -> the lowest indices survive (exact fallback path)
+    check_against_oracle(base, [base.copy(), models[0]], 0.25)
+    _, trim, _, _ = get_ties_vectors(tb, [tb.clone(), tm[0]], 0.25, return_masks=True)
+    trim = host(trim)
+    assert trim[0, :250].all() and not trim[0, 250:].any()
+
+
+@pytest.mark.parametrize("K", [1, 2, 5, 9, 16])
+def test_ties_all_k(K):
+    d = 32 * 97 + 7
+    base, models = synth.make_flat(d, K, seed=300 + K)
+    w = [0.2 + 0.05 * k for k in range(K)]
+    check_against_oracle(base, models, 0.3, w)
+
+
+@pytest.mark.parametrize("shift", [1, 2])
+def test_ties_unaligned(shift):
+    K, d = 4, 6001
+    base, models = synth.make_flat(d + 4, K, seed=88)
+    tb = dev(base)[shift:shift + d]
+    tm = [dev(m)[shift:shift + d] for m in models]
+    hb, hm = base[shift:shift + d], [m[shift:shift + d] for m in models]
+    That = get_ties_vectors(tb, tm, 0.2)
+    assert_bit_equal(host(That), orc.ties_vectors(hb, hm, 0.2), "unaligned TIES vectors")
+    w = [0.5, 0.25, 1.0, 0.75]
+    assert_bit_equal(host(merge_ties(tb, tm, w, 0.2)), orc.merge_ties(hb, hm, w, 0.2), "unaligned merge_ties")
+
+
+def test_ties_heavy_ties_quantised():
+    """Quantised updates: thousands of equal magnitudes at the threshold; the tie cut must be by lowest index."""
+    K, d = 3, 200_003
+    base, models = synth.make_flat(d, K, seed=9, quantize=5e-4)
+    check_against_oracle(base, models, 0.2, [0.3, 0.3, 0.3])
+
+
+def test_ties_sampled_path_medium():
+    """d large enough that the sample stride is > 1 (the bracket comes from a strict subsample)."""
+    K, d = 4, 3_000_017
+    base, models = synth.make_flat(d, K, seed=12)
+    tb, tm = dev(base), [dev(m) for m in models]
+    cut = ties_select(tb, tm, 0.2)
+    assert np.array_equal(cut_u64(cut), orc.ties_select(base, models, 0.2))
+    w = torch.tensor([0.3, -0.4, 0.5, 0.0], dtype=torch.float32, device="cuda")  # w = 0 -> all-zero updates -> all ties
+    cutw = ties_select(tb, tm, 0.2, w)
+    assert np.array_equal(cut_u64(cutw), orc.ties_select(base, models, 0.2, [0.3, -0.4, 0.5, 0.0]))
+
+
+@pytest.mark.parametrize("recformer", [False, True])
+@pytest.mark.parametrize("layer_wise", [False, True])
+def test_fused_ties_lambda_merge(recformer, layer_wise):
+    """merge_ties_lambda == get_ties_vectors followed by the lambda merge (bit-exact, incl. ragged blocks)."""
+    K = 6
+    shapes = synth.tiny_shapes(recformer=recformer)
+    sbase, smodels = synth.make_state_dicts(shapes, K, seed=70, sigma=1e-2)
+    base = np.concatenate([np.asarray(v).reshape(-1).astype(np.float32) for v in sbase.values()])
+    models = [np.concatenate([np.asarray(v).reshape(-1).astype(np.float32) for v in m.values()]) for m in smodels]
+    sb, se, sg, keys = orc.segment_table(shapes, layer_wise=layer_wise)
+    rng = np.random.Generator(np.random.PCG64(3))
+    w = rng.uniform(0.1, 0.6, size=(len(keys), K)).astype(np.float32)
+    want = orc.lambda_merge(base, orc.ties_vectors(base, models, 0.2), w, sb, se, sg)
+    layout = FlatLayout.from_shape_dict(shapes)
+    seg_end, seg_group, _ = layout.device_blocks(layer_wise, "cuda")
+    got = merge_ties_lambda(dev(base), [dev(m) for m in models], 0.2, dev(w),
+                            seg_end if layer_wise else None, seg_group if layer_wise else None)
+    assert_bit_equal(host(got), want, "fused TIES + lambda merge")
+
+
+def test_ties_full_size_blair_base():
+    """BASELINE config 2 size: K = 8, d = 124,645,632, density 0.2; cut keys and TIES vectors bit-exact vs the oracle."""
+    d, K = synth.total_numel(synth.roberta_shapes()), 8
+    g = torch.Generator(device="cuda").manual_seed(6)
+    base = torch.randn(d, generator=g, device="cuda") * 0.02
+    models = [base + 1e-3 * torch.randn(d, generator=g, device="cuda") for _ in range(K)]
+    That, trim, elect, cut = get_ties_vectors(base, models, 0.2, return_masks=True)
+    k_cnt = ties_topk_count(0.2, d)
+    assert k_cnt == 24_929_126
+    assert (trim.sum(dim=1) == k_cnt).all(), "every model keeps exactly int(density*d) entries"
+    assert torch.equal(elect, That != 0)
+    hb, hm = host(base), [host(m) for m in models]
+    assert np.array_equal(cut_u64(cut), orc.ties_select(hb, hm, 0.2))
+    want = orc.ties_vectors(hb, hm, 0.2)
+    got = host(That)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
