@@ -142,5 +142,132 @@ class LambdaMergeK8(Workload):
                 "sample": f"full workload (d={self.d}, K={self.K}) per step, OpenMP C oracle port"}
 
 
-WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8}
-DEFAULT_WORKLOAD = LambdaMergeK8.name
+class TiesCfg2(LambdaMergeK8):
+    """BASELINE config 2: TIES merge (trim 20 %, sign election, disjoint mean) of 8 BLaIR-base domain models with
+    per-layer lambda.  One step = the reference-shaped pipeline `get_ties_vectors(density=0.2)` (A6-A8) followed
+    by the layer-wise lambda merge (A4).  Algorithmic bytes per step: (2K+1)*d*4 + (K+2)*d*4."""
+
+    name = "ties_cfg2"
+    launches_per_step = 11  # init + 2x(memset+pass+pick) sample + pass + pick + compact + final + build + merge
+
+    def __init__(self, rank, world, device):
+        super().__init__(rank, world, device)
+        self.bytes_build = (2 * self.K + 1) * self.d * 4
+        self.bytes_merge = (self.K + 2) * self.d * 4
+        self.bytes_per_step = self.bytes_build + self.bytes_merge
+
+    def config(self):
+        return {"workload": "BASELINE config 2: TIES merge (density 0.2, global trim, sign election, disjoint mean) "
+                            "of K=8 BLaIR-base (RoBERTa-base, d=124,645,632, P=199) domain models + per-layer "
+                            "lambda merge (G=13)",
+                "K": self.K, "d": self.d, "G": 13, "density": 0.2,
+                "l2": "inputs (4.5 GB) exceed L2, no flush needed",
+                "parallelism": f"replicas x{self.world}" if self.world > 1 else "1 GPU"}
+
+    def setup(self):
+        super().setup()
+        from mergerec_b200.merger.layout import alloc_rows
+        self.That = alloc_rows(self.K, self.d, self.device)
+        self.Trows = list(self.That.unbind(0))
+        del self.T, self.rows
+
+    def step(self):
+        from mergerec_b200 import _lib
+        from mergerec_b200.merger.algorithms import ties as T
+        from mergerec_b200.merger.algorithms._common import merge_axpy
+        cut = T.ties_select(self.base, self.models, 0.2)
+        T._build(self.base, self.models, cut, _lib.MR_TIES_VECTORS, out=self.That, ldo=self.That.stride(0))
+        merge_axpy(self.base, self.Trows, self.w, _lib.MR_ORDER_SUM_FIRST, False, self.seg_end, self.seg_group, out=self.out)
+
+    def step_fused(self):
+        from mergerec_b200.merger.algorithms import ties as T
+        T.merge_ties_lambda(self.base, self.models, 0.2, self.w, self.seg_end, self.seg_group, out=self.out)
+
+    def setup_e2e(self):
+        self.h_base = _pinned(self.base.cpu())
+        self.h_models = [_pinned(m.cpu()) for m in self.models]
+        self.h_out = torch.empty(self.d, dtype=torch.float32, pin_memory=True)
+        self.h2d_bytes = (self.K + 1) * self.d * 4
+        self.d2h_bytes = self.d * 4
+
+    def step_e2e(self):
+        self.base.copy_(self.h_base, non_blocking=True)
+        for m, h in zip(self.models, self.h_models):
+            m.copy_(h, non_blocking=True)
+        self.step()
+        self.h_out.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def roofline(self, peaks):
+        from bench import event_time_ms
+        from mergerec_b200 import _lib
+        from mergerec_b200.merger.algorithms import ties as T
+        cut = T.ties_select(self.base, self.models, 0.2)
+        lib = _lib.load()
+        K, d = self.K, self.d
+        ws_bytes = int(lib.mr_ties_workspace_bytes(d, K))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        cut2 = torch.empty(K, dtype=torch.int64, device=self.device)
+        status = torch.zeros(K, dtype=torch.int32, device=self.device)
+        parr = _lib.ptr_array(self.models)
+
+        def select():
+            _lib.check(lib.mr_ties_select(_lib.dptr(self.base), parr, K, d, None, int(0.2 * d), _lib.dptr(cut2),
+                                          _lib.dptr(status), _lib.dptr(ws), ws_bytes, _lib.stream_handle()), "select")
+
+        def build():
+            T._build(self.base, self.models, cut, _lib.MR_TIES_VECTORS, out=self.That, ldo=self.That.stride(0))
+
+        ms_build = event_time_ms(build, 10)
+        ms_select = event_time_ms(select, 10)
+        ms_merge = event_time_ms(self._merge_only, 10)
+        ms_fused = event_time_ms(self.step_fused, 5)
+        ach = self.bytes_build / GB / (ms_build * 1e-3)
+        sel_bytes = (K + 1) * d * 4
+        return {"bound": "hbm", "kernel": "mr::ties_build_kernel<8, VECTORS, vec4> (get_ties_vectors build pass)",
+                "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms_build,
+                "algorithmic_bytes_per_launch": self.bytes_build,
+                "other_kernels": {
+                    "ties_select (sample + 1 full pass + finish)": {"ms": ms_select, "GB/s": sel_bytes / GB / (ms_select * 1e-3), "bytes": sel_bytes},
+                    "lambda merge (merge_kernel)": {"ms": ms_merge, "GB/s": self.bytes_merge / GB / (ms_merge * 1e-3), "bytes": self.bytes_merge},
+                    "fused select + build + merge without materialising That (merge_ties_lambda)": {"ms": ms_fused, "GB/s": self.bytes_merge / GB / (ms_fused * 1e-3), "bytes": self.bytes_merge},
+                }}
+
+    def _merge_only(self):
+        from mergerec_b200 import _lib
+        from mergerec_b200.merger.algorithms._common import merge_axpy
+        merge_axpy(self.base, self.Trows, self.w, _lib.MR_ORDER_SUM_FIRST, False, self.seg_end, self.seg_group, out=self.out)
+
+    def _cpu_time(self, reps):
+        """Oracle port on a bounded sample: the full K = 8 but a prefix of the flat vector (the select is global
+        over whatever vector it is given, so the per-element work is the same)."""
+        from oracle import oracle as orc
+        frac = 8
+        d = self.d // frac
+        rng = np.random.Generator(np.random.PCG64(7))
+        base = rng.standard_normal(d, dtype=np.float32) * np.float32(0.02)
+        models = [base + np.float32(1e-3) * rng.standard_normal(d, dtype=np.float32) for _ in range(self.K)]
+        w = rng.uniform(0.1, 0.5, size=(1, self.K)).astype(np.float32)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            That = orc.ties_vectors(base, models, 0.2)
+            orc.lambda_merge(base, That, w)
+            ts.append(time.perf_counter() - t0)
+        self._cpu_sample = f"d/{frac} = {d} flat elements of the K={self.K} workload (select is global over the sample), OpenMP C oracle port"
+        return float(np.median(ts)) * frac, orc.max_threads()
+
+    def cpu_baseline(self):
+        t, cores = self._cpu_time(2)
+        return {"value": self.bytes_per_step / GB / t, "unit": self.unit, "cores": cores, "kind": "port",
+                "sample": self._cpu_sample + "; time scaled x8 to the full vector", "seconds_per_step": t}
+
+    def reference_arm(self, steps, warmup):
+        t, cores = self._cpu_time(max(1, min(steps, 3)))
+        return {"value": self.bytes_per_step / GB / t, "ms_per_step": t * 1e3, "cores": cores,
+                "sample": self._cpu_sample + "; time scaled x8 to the full vector"}
+
+
+WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8, TiesCfg2.name: TiesCfg2}
+DEFAULT_WORKLOAD = TiesCfg2.name

@@ -133,6 +133,55 @@ int mr_ties_build(const float* base, const float* const* models, int K, int64_t 
                   const float* w, int G, const int64_t* seg_end, const int32_t* seg_group, int P, float* out,
                   int64_t ldo, uint8_t* trim_mask, uint8_t* elect_mask, mr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Evaluator (B1-B4): full-catalog scoring, per-row top-K, rank of the label.
+ * Top-K lists are ordered by score descending, then item id ascending (canonical tie rule; torch.topk's own
+ * order among equal scores is unspecified); -0.0 == +0.0 and NaN sorts first like torch.topk.
+ * ---------------------------------------------------------------------------------------------- */
+#define MR_MAX_TOPK 1024      /* mr_topk_rows / mr_topk_merge */
+#define MR_MAX_FUSED_TOPK 128 /* mr_score_topk */
+
+/* Top-K of every row of a materialised (Q, N) score matrix with row stride ld (drop-in for
+ * torch.topk(scores, K, dim=1))                                   ref: evaluator/evaluator.py:43
+ * out_val / out_id: dev (Q, K); ids are id_base + column.  Requires K <= N. */
+int mr_topk_rows(const float* scores, int64_t Q, int64_t N, int64_t ld, int K, int32_t id_base, float* out_val,
+                 int32_t* out_id, mr_stream_t stream);
+
+/* Merge L per-shard lists (vals / ids: dev (L, Q, K_in), sorted or not, id < 0 = empty slot) into one sorted
+ * (Q, K_out) list: the exchange step after the NCCL allgather of per-GPU top-K lists (no reference
+ * counterpart; the reference is single-GPU, README.md:51-53).  L * K_in <= 8192. */
+int mr_topk_merge(const float* vals, const int32_t* ids, int L, int64_t Q, int K_in, int K_out, float* out_val,
+                  int32_t* out_id, mr_stream_t stream);
+
+/* rank[q] = position of labels[q] in ids[q, :K], or -1          ref: evaluator/metrics.py:51-59, 79-84 */
+int mr_label_rank(const int32_t* ids, int64_t Q, int K, const int64_t* labels, int32_t* rank, mr_stream_t stream);
+
+/* Fused full-catalog scoring + per-row top-K: the tensor-core path (tcgen05.mma kind::tf32 fed by TMA, fp32
+ * accumulators in TMEM) that never materialises the (Q, N) score matrix
+ *                              ref: module/recommender/module.py:137 followed by evaluator/evaluator.py:43
+ *   Uhi, Ulo   dev (Q, E) row-major: the mr_split_tf32 halves of the query embeddings
+ *   Ihi, Ilo   dev (N, E) row-major: the halves of this GPU's rows of the item table (split once, reused)
+ *   id_base    global id of item row 0 (shard offset); returned ids are id_base + row
+ *   mode       MR_SCORE_TF32X3: Uhi.Ilo + Ulo.Ihi + Uhi.Ihi, fp32-faithful (default);
+ *              MR_SCORE_TF32X1: Uhi.Ihi only (Ulo / Ilo may be NULL)
+ *   out_val / out_id   dev (Q, K), sorted by (score desc, id asc); slots beyond N hold id -1, score -inf
+ *   ws         dev scratch of at least mr_score_topk_workspace_bytes(Q, N, E, K) bytes
+ * Requires E % 4 == 0, 16-byte aligned operands, 1 <= K <= MR_MAX_FUSED_TOPK.  Scores are exact (hence identical
+ * to any fp32 summation order) whenever all products and partial sums are representable, e.g. grid embeddings. */
+enum mr_score_mode { MR_SCORE_TF32X3 = 0, MR_SCORE_TF32X1 = 1 };
+int64_t mr_score_topk_workspace_bytes(int64_t Q, int64_t N, int E, int K);
+int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, const float* Ihi, const float* Ilo, int64_t N, int E,
+                  int K, int32_t id_base, int mode, float* out_val, int32_t* out_id, void* ws, int64_t ws_bytes,
+                  mr_stream_t stream);
+
+/* hi = rna_tf32(x), lo = rna_tf32(x - hi): the operand split of the fp32-faithful 3xTF32 contraction. */
+int mr_split_tf32(const float* x, int64_t n, float* hi, float* lo, mr_stream_t stream);
+
+/* out[q, n] = sum_e U[q, e] * I[n, e] in plain fp32 on CUDA cores (row-major U (Q, E), I (N, E); out row stride
+ * ldo)                                                          ref: module/recommender/module.py:137 */
+int mr_scores_fp32(const float* U, int64_t Q, const float* I, int64_t N, int E, float* out, int64_t ldo,
+                   mr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

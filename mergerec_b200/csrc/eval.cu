@@ -1,0 +1,269 @@
+// eval.cu -- evaluator kernels outside the tensor-core contraction (B2-B4):
+// per-row top-K of a materialised score matrix, merge of per-shard top-K lists, rank of the label,
+// the hi/lo TF32 operand split, and a plain fp32 scoring kernel (CUDA cores; the "fp32 mode").
+//
+// reference: rec_retrieval/evaluator/evaluator.py:31-49 (torch.topk(scores, max_k, dim=1).indices),
+//            rec_retrieval/evaluator/metrics.py:35-88 (`true in pred`, `pred.index(true)`),
+//            rec_retrieval/module/recommender/module.py:137 (scores = user @ item.T)
+//
+// Order of a top-K list: score descending, then item id ascending (canonical rule);
+// -0.0 == +0.0 and NaN sorts first, like torch.topk.  Everything is compare-only: results are bit-exact.
+#include "common.cuh"
+#include "topk_common.cuh"
+
+namespace mr {
+
+// ---- B2: per-row top-K of a (Q, N) score matrix -------------------------------------------------------------
+// One CTA per row.  Scores stream through a threshold filter into a shared-memory candidate buffer; when the
+// buffer cannot take another chunk it is sorted (bitonic, descending) and cut back to K, which also raises the
+// threshold.  After the first cut only ~K*ln(N/K) elements ever pass.
+constexpr int kTopkThreads = 256;
+constexpr int kTopkCap = 2048;               // candidate buffer (keys), power of two
+constexpr int kTopkChunk = kTopkThreads * 4; // elements examined between two buffer checks
+
+__global__ void __launch_bounds__(kTopkThreads)
+topk_rows_kernel(const float* __restrict__ scores, int64_t Q, int64_t N, int64_t ld, int K, int32_t id_base,
+                 float* __restrict__ out_val, int32_t* __restrict__ out_id) {
+    __shared__ u64 s_keys[kTopkCap];
+    __shared__ int s_cnt;
+    __shared__ u64 s_thr;
+    for (int64_t q = blockIdx.x; q < Q; q += gridDim.x) {
+        const float* row = scores + q * ld;
+        const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+        if (threadIdx.x == 0) { s_cnt = 0; s_thr = 0; }
+        __syncthreads();
+        for (int64_t c0 = 0; c0 < N; c0 += kTopkChunk) {
+            const u64 thr = s_thr;
+            int over = 0;  // did one of my appends land beyond the refill limit?
+            const int64_t c = c0 + (int64_t)threadIdx.x * 4;
+            float v[4];
+            int nv = 0;
+            if (c + 3 < N && vec) {
+                const float4 f = ldg_stream4(row + c);
+                v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                nv = 4;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (c + i < N) { v[i] = row[c + i]; nv = i + 1; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < nv) {
+                    const u64 key = topk_key(v[i], (uint32_t)(id_base + (int32_t)(c + i)));
+                    if (key > thr) {
+                        const int pos = atomicAdd(&s_cnt, 1);
+                        s_keys[pos] = key;
+                        over |= (pos >= kTopkCap - kTopkChunk);
+                    }
+                }
+            }
+            // barrier + uniform decision (s_cnt itself may already be moving again when a slow thread looks at it)
+            if (__syncthreads_or(over)) {
+                const int n = s_cnt;
+                for (int i = n + threadIdx.x; i < kTopkCap; i += blockDim.x) s_keys[i] = 0;
+                __syncthreads();
+                block_bitonic_sort_desc(s_keys, kTopkCap);
+                if (threadIdx.x == 0) {
+                    s_cnt = n < K ? n : K;
+                    if (n >= K) s_thr = s_keys[K - 1];
+                }
+                __syncthreads();
+            }
+        }
+        const int n = s_cnt;
+        for (int i = n + threadIdx.x; i < kTopkCap; i += blockDim.x) s_keys[i] = 0;
+        __syncthreads();
+        block_bitonic_sort_desc(s_keys, kTopkCap);
+        for (int i = threadIdx.x; i < K; i += blockDim.x) {
+            const u64 key = s_keys[i];
+            if (i < n && key != 0) {
+                const int32_t id = (int32_t)key_id(key);
+                out_id[q * K + i] = id;
+                out_val[q * K + i] = row[id - id_base];  // the original bits (keeps -0.0 / NaN payloads)
+            } else {
+                out_id[q * K + i] = -1;
+                out_val[q * K + i] = -INFINITY;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- merge L top-K lists per row (the multi-GPU / multi-split exchange step) -----------------------------------
+// vals / ids: (L, Q, K_in); entries with id < 0 are empty.  Output (Q, K_out) sorted by (score desc, id asc).
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ ids, int L, int64_t Q, int K_in, int K_out,
+                  int NP, float* __restrict__ out_val, int32_t* __restrict__ out_id) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* s_keys = reinterpret_cast<u64*>(smem_raw);
+    for (int64_t q = blockIdx.x; q < Q; q += gridDim.x) {
+        const int total = L * K_in;
+        for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+            u64 key = 0;
+            if (i < total) {
+                const int l = i / K_in, e = i - l * K_in;
+                const int64_t src = ((int64_t)l * Q + q) * K_in + e;
+                const int32_t id = ids[src];
+                if (id >= 0) key = topk_key(vals[src], (uint32_t)id);
+            }
+            s_keys[i] = key;
+        }
+        __syncthreads();
+        block_bitonic_sort_desc(s_keys, NP);
+        for (int i = threadIdx.x; i < K_out; i += blockDim.x) {
+            const u64 key = (i < NP) ? s_keys[i] : 0;
+            out_id[q * K_out + i] = key ? (int32_t)key_id(key) : -1;
+            out_val[q * K_out + i] = key ? key_score(key) : -INFINITY;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- B3/B4 helper: position of the label inside each row's list, -1 when absent -----------------------------
+__global__ void label_rank_kernel(const int32_t* __restrict__ ids, int64_t Q, int K, const int64_t* __restrict__ labels,
+                                  int32_t* __restrict__ rank) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const int64_t lab = labels[q];
+    int32_t r = -1;
+    for (int i = 0; i < K; ++i) {
+        if ((int64_t)ids[q * K + i] == lab) { r = i; break; }
+    }
+    rank[q] = r;
+}
+
+// ---- hi/lo split for the 3xTF32 contraction -----------------------------------------------------------------------
+// hi = rna_tf32(x), lo = rna_tf32(x - hi): x = hi + lo up to 2^-22 |x|, both exactly representable in TF32.
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gsz) {
+        const float v = x[i];
+        const float h = rna_tf32(v);
+        hi[i] = h;
+        lo[i] = rna_tf32(__fsub_rn(v, h));
+    }
+}
+
+// ---- B1 in plain fp32 on CUDA cores ("fp32 mode"; also the on-device cross-check of the tensor-core path) ------------
+// out[q, n] = sum_e U[q,e] * I[n,e], one fp32 FMA chain per score, sequential in e.
+constexpr int kSfTile = 64, kSfBk = 16;
+__global__ void __launch_bounds__(256)
+scores_fp32_kernel(const float* __restrict__ U, int64_t Q, const float* __restrict__ I, int64_t N, int E,
+                   float* __restrict__ out, int64_t ldo) {
+    __shared__ float s_u[kSfBk][kSfTile + 1];
+    __shared__ float s_i[kSfBk][kSfTile + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t q0 = (int64_t)blockIdx.y * kSfTile, n0 = (int64_t)blockIdx.x * kSfTile;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+    for (int e0 = 0; e0 < E; e0 += kSfBk) {
+        for (int i = threadIdx.x; i < kSfTile * kSfBk; i += 256) {
+            const int r = i / kSfBk, e = i % kSfBk;
+            const bool eok = e0 + e < E;
+            s_u[e][r] = (eok && q0 + r < Q) ? U[(q0 + r) * E + e0 + e] : 0.0f;
+            s_i[e][r] = (eok && n0 + r < N) ? I[(n0 + r) * E + e0 + e] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < kSfBk; ++e) {
+            float a[4], b[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { a[x] = s_u[e][ty * 4 + x]; b[x] = s_i[e][tx * 4 + x]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int64_t q = q0 + ty * 4 + x, n = n0 + tx * 4 + y;
+            if (q < Q && n < N) out[q * ldo + n] = acc[x][y];
+        }
+}
+
+}  // namespace mr
+
+extern "C" int mr_topk_rows(const float* scores, int64_t Q, int64_t N, int64_t ld, int K, int32_t id_base,
+                            float* out_val, int32_t* out_id, mr_stream_t stream) {
+    using namespace mr;
+    MR_REQUIRE(Q >= 0 && N >= 0 && ld >= N, "mr_topk_rows: need Q >= 0 and ld >= N >= 0");
+    MR_REQUIRE(K >= 1 && K <= MR_MAX_TOPK, "mr_topk_rows: K=%d outside [1,%d]", K, MR_MAX_TOPK);
+    MR_REQUIRE((int64_t)K <= N || Q == 0, "mr_topk_rows: K=%d exceeds the number of items %lld", K, (long long)N);
+    if (Q == 0) return MR_OK;
+    MR_REQUIRE(scores && out_val && out_id, "mr_topk_rows: null pointer");
+    const int64_t cap = (int64_t)sm_count() * 8;
+    const unsigned blocks = (unsigned)(Q < cap ? Q : cap);
+    // rows whose start is not 16-byte aligned (ld % 4 != 0) simply take the scalar loads
+    topk_rows_kernel<<<blocks, kTopkThreads, 0, (cudaStream_t)stream>>>(scores, Q, N, ld, K, id_base, out_val, out_id);
+    MR_CUDA_LAUNCH_CHECK("mr_topk_rows");
+    return MR_OK;
+}
+
+extern "C" int mr_topk_merge(const float* vals, const int32_t* ids, int L, int64_t Q, int K_in, int K_out,
+                             float* out_val, int32_t* out_id, mr_stream_t stream) {
+    using namespace mr;
+    MR_REQUIRE(L >= 1 && Q >= 0 && K_in >= 1 && K_out >= 1, "mr_topk_merge: need L, K_in, K_out >= 1 and Q >= 0");
+    MR_REQUIRE(K_out <= MR_MAX_TOPK, "mr_topk_merge: K_out=%d exceeds %d", K_out, MR_MAX_TOPK);
+    int NP = 1;
+    while (NP < L * K_in) NP <<= 1;
+    MR_REQUIRE(NP <= 8192, "mr_topk_merge: L*K_in=%d candidates per row exceed 8192", L * K_in);
+    if (Q == 0) return MR_OK;
+    MR_REQUIRE(vals && ids && out_val && out_id, "mr_topk_merge: null pointer");
+    const size_t smem = (size_t)NP * 8;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    const unsigned blocks = (unsigned)(Q < cap ? Q : cap);
+    topk_merge_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(vals, ids, L, Q, K_in, K_out, NP, out_val, out_id);
+    MR_CUDA_LAUNCH_CHECK("mr_topk_merge");
+    return MR_OK;
+}
+
+extern "C" int mr_label_rank(const int32_t* ids, int64_t Q, int K, const int64_t* labels, int32_t* rank,
+                             mr_stream_t stream) {
+    using namespace mr;
+    MR_REQUIRE(Q >= 0 && K >= 1, "mr_label_rank: need Q >= 0, K >= 1");
+    if (Q == 0) return MR_OK;
+    MR_REQUIRE(ids && labels && rank, "mr_label_rank: null pointer");
+    label_rank_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, Q, K, labels, rank);
+    MR_CUDA_LAUNCH_CHECK("mr_label_rank");
+    return MR_OK;
+}
+
+extern "C" int mr_split_tf32(const float* x, int64_t n, float* hi, float* lo, mr_stream_t stream) {
+    using namespace mr;
+    MR_REQUIRE(n >= 0, "mr_split_tf32: n < 0");
+    if (n == 0) return MR_OK;
+    MR_REQUIRE(x && hi && lo, "mr_split_tf32: null pointer");
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, hi, lo);
+    MR_CUDA_LAUNCH_CHECK("mr_split_tf32");
+    return MR_OK;
+}
+
+extern "C" int mr_scores_fp32(const float* U, int64_t Q, const float* I, int64_t N, int E, float* out, int64_t ldo,
+                              mr_stream_t stream) {
+    using namespace mr;
+    MR_REQUIRE(Q >= 0 && N >= 0 && E >= 1 && ldo >= N, "mr_scores_fp32: need Q, N >= 0, E >= 1, ldo >= N");
+    if (Q == 0 || N == 0) return MR_OK;
+    MR_REQUIRE(U && I && out, "mr_scores_fp32: null pointer");
+    MR_REQUIRE((Q + kSfTile - 1) / kSfTile <= 65535, "mr_scores_fp32: Q too large for this kernel (use mr_score_topk)");
+    dim3 grid((unsigned)((N + kSfTile - 1) / kSfTile), (unsigned)((Q + kSfTile - 1) / kSfTile));
+    scores_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(U, Q, I, N, E, out, ldo);
+    MR_CUDA_LAUNCH_CHECK("mr_scores_fp32");
+    return MR_OK;
+}

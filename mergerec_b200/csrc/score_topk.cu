@@ -1,0 +1,594 @@
+// score_topk.cu -- evaluator hot path B1+B2 fused: full-catalog scoring
+//     scores[q, n] = sum_e U[q, e] * I[n, e]                (ref: module/recommender/module.py:137)
+// followed by the per-row top-K                              (ref: evaluator/evaluator.py:43)
+// without ever materialising the (Q, N) score matrix.
+//
+// Tensor-core contraction on sm_100a: tcgen05.mma kind::tf32, operands staged in shared memory by TMA
+// (128-byte swizzle, K-major), fp32 accumulators in TMEM, read back with tcgen05.ld by the epilogue warps.
+// fp32-faithful mode (default) is 3xTF32 on pre-split operands (hi = rna_tf32(x), lo = rna_tf32(x - hi)):
+//     U.I ~= Uhi.Ilo + Ulo.Ihi + Uhi.Ihi      (error ~2^-22 per product, like an fp32 product's own rounding)
+//
+// Work decomposition.  A "unit" is (query block, item split): BLOCK_M * CG query rows against a contiguous
+// range of 256-item tiles.  A persistent grid of CTAs (CG = 1) or CTA pairs (CG = 2, cta_group::2: 256-row
+// tiles, each CTA stages its own 128 query rows and half of the item tile) walks a static unit list ordered so
+// that concurrently running units share item tiles through L2 while their query blocks stay L2-resident.
+// Warp roles per CTA: 0 = TMA producer, 1 = MMA issuer (leader CTA of a pair only), 2 = TMEM allocator,
+// 4..7 = epilogue: thread t owns accumulator lane (= query row) t, filters the 256 scores of a tile against the
+// row's running threshold (score of its K-th best so far) and appends survivors to a per-row candidate buffer in
+// global memory (L2-resident); when a buffer fills, the warp sorts it cooperatively in shared memory (bitonic,
+// 64-bit keys = (score desc, id asc)) and keeps the best K.  After its last tile a unit writes one sorted list
+// per row; lists of different splits are merged by mr_topk_merge.
+//
+// Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i + 1.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "topk_common.cuh"
+
+namespace mr {
+namespace st {
+
+constexpr int kBlockM = 128;   // query rows per CTA (TMEM lanes)
+constexpr int kBlockN = 256;   // items per tile (TMEM columns per accumulator stage)
+constexpr int kBlockK = 32;    // fp32 elements per k-block: 128 bytes = one SWIZZLE_128B atom
+constexpr int kUmmaK = 8;      // tf32: 32 bytes of K per tcgen05.mma
+constexpr int kThreads = 256;
+constexpr int kCap = 256;      // per-row candidate buffer (keys); power of two, >= 2 * MR_MAX_FUSED_TOPK
+constexpr int kChunk = 32;     // accumulator columns per tcgen05.ld
+constexpr int kAccStages = 2;
+constexpr int kABytes = kBlockM * kBlockK * 4;   // 16 KB: one of (hi, lo) of the query tile
+
+template <int CG> struct Cfg {
+    static constexpr int kBRows = kBlockN / CG;              // item rows staged by one CTA
+    static constexpr int kBBytes = kBRows * kBlockK * 4;     // 32 KB (CG 1) / 16 KB (CG 2)
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    static constexpr int kStages = CG == 1 ? 2 : 3;
+    static constexpr int kSortBytes = 4 * kCap * 8;          // one sort scratch per epilogue warp
+    static constexpr int kBarBytes = 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kSortBytes + kBarBytes + 1024 /* alignment slack */;
+};
+
+struct Params {
+    int64_t Q, N;
+    int E, K, mode;
+    int32_t id_base;
+    int KB;       // k-blocks per tile = ceil(E / 32)
+    int T;        // item tiles = ceil(N / 256)
+    int QB;       // query blocks = ceil(Q / (128 * CG))
+    int S;        // item splits
+    int QG;       // query blocks per L2 group
+    u64* cand;    // grid * 128 * kCap keys
+    float* out_val;     // (S, Q, K)
+    int32_t* out_id;    // (S, Q, K)
+};
+
+// ---- PTX helpers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must end in a trap (launch failure), never in a hung GPU.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int what) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("mr_score_topk: barrier wait timed out (what=%d block=%d thread=%d parity=%u)\n", what, blockIdx.x,
+                   threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int what) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, what);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    if (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+    } else {
+        // both CTAs of the pair issue their own loads; the transaction bytes land on the leader's barrier
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    }
+}
+// tcgen05.commit: the barrier is arrived on when every previously issued MMA of this thread has completed
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+            ::"r"(bar), "h"((uint16_t)3) : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4)   // start address, 16-byte units
+           | ((uint64_t)(1024 >> 4) << 32)       // stride byte offset between 8-row groups
+           | (1ull << 46)                        // descriptor version (sm_100)
+           | (2ull << 61);                       // SWIZZLE_128B
+}
+// kind::tf32 instruction descriptor: fp32 accumulate, tf32 x tf32, both operands K-major, N = 256, M = 128 * CG
+template <int CG>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)((kBlockM * CG) >> 4) << 24);
+}
+
+// ---- static unit schedule (identical in every role) ---------------------------------------------------------------
+struct Unit {
+    int qb, split, t0, t1;
+};
+__device__ __forceinline__ bool get_unit(const Params& p, int u, Unit& out) {
+    if (u >= p.QB * p.S) return false;
+    const int per_group = p.QG * p.S;
+    const int g = u / per_group, r = u - g * per_group;
+    const int qg0 = g * p.QG;
+    const int qgn = (p.QB - qg0) < p.QG ? (p.QB - qg0) : p.QG;
+    out.split = r / qgn;
+    out.qb = qg0 + (r - out.split * qgn);
+    out.t0 = (int)(((int64_t)out.split * p.T) / p.S);
+    out.t1 = (int)(((int64_t)(out.split + 1) * p.T) / p.S);
+    return true;
+}
+
+// ---- warp-cooperative compaction of one row's candidate buffer ----------------------------------------------------
+__device__ __forceinline__ void warp_sort_desc(u64* s, int n, int lane) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = lane; i < (n >> 1); i += 32) {
+                const int a = 2 * i - (i & (stride - 1));
+                const int b = a + stride;
+                const bool desc = ((a & size) == 0);
+                const u64 x = s[a], y = s[b];
+                if ((x < y) == desc) { s[a] = y; s[b] = x; }
+            }
+            __syncwarp();
+        }
+    }
+}
+// Loads `n` keys of a row into the warp's scratch, sorts them descending; returns with s[] sorted (zero padded).
+__device__ __forceinline__ void warp_load_sort(u64* s, const u64* gbuf, int n, int lane) {
+    int np = 32;
+    while (np < n) np <<= 1;
+    for (int i = lane; i < np; i += 32) s[i] = (i < n) ? gbuf[i] : 0ull;
+    __syncwarp();
+    warp_sort_desc(s, np, lane);
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_constant__ CUtensorMap map_ulo,
+                  const __grid_constant__ CUtensorMap map_ihi, const __grid_constant__ CUtensorMap map_ilo,
+                  const Params p) {
+    using C = Cfg<CG>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* stages = smem;
+    u64* sort_scratch = reinterpret_cast<u64*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kSortBytes);
+    // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * C::kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * C::kStages;
+    const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 2 * kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x / CG;
+    const int num_clusters = gridDim.x / CG;
+    const bool x3 = p.mode == 0;
+
+    if (CG > 1) cluster_sync_all();  // both CTAs resident before the paired TMEM allocation
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_uhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ihi) : "memory");
+        if (x3) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ulo) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ilo) : "memory");
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::kStages; ++i) {
+            mbar_init(bar_full + 8 * i, CG);   // producer arrivals (leader's barrier collects both CTAs)
+            mbar_init(bar_empty + 8 * i, 1);   // one tcgen05.commit
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);        // one tcgen05.commit
+            mbar_init(bar_tempty + 8 * i, 4 * CG);  // one arrival per epilogue warp of every CTA in the pair
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    if (CG > 1) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (one lane) =====
+        if (lane == 0) {
+            uint32_t kiter = 0;
+            Unit u;
+            for (int ui = cluster_id; get_unit(p, ui, u); ui += num_clusters) {
+                const int qrow = (u.qb * CG + (int)rank) * kBlockM;
+                for (int t = u.t0; t < u.t1; ++t) {
+                    const int nrow = t * kBlockN + (int)rank * C::kBRows;
+                    for (int kb = 0; kb < p.KB; ++kb, ++kiter) {
+                        const int s = kiter % C::kStages;
+                        mbar_wait(bar_empty + 8 * s, ((kiter / C::kStages) & 1) ^ 1, 1);
+                        const uint32_t full = bar_full + 8 * s;
+                        const uint32_t sbase = smem_u32(stages + (size_t)s * C::kStageBytes);
+                        const uint32_t bytes = (x3 ? 2u : 1u) * (uint32_t)(kABytes + C::kBBytes);
+                        if (leader) mbar_arrive_expect_tx(full, bytes * CG);
+                        const int kc = kb * kBlockK;
+                        tma_load_2d<CG>(sbase, &map_uhi, full, kc, qrow);
+                        tma_load_2d<CG>(sbase + 2 * kABytes, &map_ihi, full, kc, nrow);
+                        if (x3) {
+                            tma_load_2d<CG>(sbase + kABytes, &map_ulo, full, kc, qrow);
+                            tma_load_2d<CG>(sbase + 2 * kABytes + C::kBBytes, &map_ilo, full, kc, nrow);
+                        }
+                        if (!leader) mbar_arrive_remote(full, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA; one lane issues) =====
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc<CG>();
+            uint32_t kiter = 0, it = 0;
+            Unit u;
+            for (int ui = cluster_id; get_unit(p, ui, u); ui += num_clusters) {
+                for (int t = u.t0; t < u.t1; ++t, ++it) {
+                    const uint32_t acc = it & 1;
+                    mbar_wait(bar_tempty + 8 * acc, ((it >> 1) & 1) ^ 1, 2);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * kBlockN;
+                    for (int kb = 0; kb < p.KB; ++kb, ++kiter) {
+                        const int s = kiter % C::kStages;
+                        mbar_wait(bar_full + 8 * s, (kiter / C::kStages) & 1, 3);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t sbase = smem_u32(stages + (size_t)s * C::kStageBytes);
+                            const uint64_t a_hi = make_smem_desc(sbase);
+                            const uint64_t a_lo = make_smem_desc(sbase + kABytes);
+                            const uint64_t b_hi = make_smem_desc(sbase + 2 * kABytes);
+                            const uint64_t b_lo = make_smem_desc(sbase + 2 * kABytes + C::kBBytes);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                const uint64_t off = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 bytes of K per step
+                                if (x3) {
+                                    umma_tf32<CG>(d_tmem, a_hi + off, b_lo + off, idesc, (kb | k) != 0);
+                                    umma_tf32<CG>(d_tmem, a_lo + off, b_hi + off, idesc, 1u);
+                                    umma_tf32<CG>(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+                                } else {
+                                    umma_tf32<CG>(d_tmem, a_hi + off, b_hi + off, idesc, (kb | k) != 0);
+                                }
+                            }
+                            umma_commit<CG>(bar_empty + 8 * s);                      // stage consumed
+                            if (kb == p.KB - 1) umma_commit<CG>(bar_tfull + 8 * acc);  // accumulator complete
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> threshold filter -> per-row candidate buffers -> sorted top-K =====
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        u64* s_sort = sort_scratch + ew * kCap;
+        u64* my_buf = p.cand + ((size_t)blockIdx.x * kBlockM + row) * kCap;
+        const u64* warp_buf = p.cand + ((size_t)blockIdx.x * kBlockM + ew * 32) * kCap;
+        const int K = p.K;
+        uint32_t it = 0;
+        Unit u;
+        for (int ui = cluster_id; get_unit(p, ui, u); ui += num_clusters) {
+            const int64_t q = ((int64_t)u.qb * CG + rank) * kBlockM + row;
+            const bool active = q < p.Q;
+            int cnt = 0;
+            uint32_t thr = 0;  // score key of the row's K-th best so far (0: list not full, everything passes)
+            for (int t = u.t0; t < u.t1; ++t, ++it) {
+                const uint32_t acc = it & 1;
+                mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1, 4);
+                tc_fence_after();
+                const int64_t n0 = (int64_t)t * kBlockN;
+                const int nvalid = (int)((p.N - n0) < kBlockN ? (p.N - n0) : kBlockN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kBlockN;
+                for (int c = 0; c < nvalid; c += kChunk) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c, r);
+                    tmem_ld_wait();
+                    if (active) {
+                        const uint32_t id0 = (uint32_t)(p.id_base + (int32_t)(n0 + c));
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j) {
+                            const uint32_t key = score_key(__uint_as_float(r[j]));
+                            if (key > thr && c + j < nvalid) my_buf[cnt++] = ((u64)key << 32) | (u64)(0xFFFFFFFFu - (id0 + j));
+                        }
+                    }
+                    // rows that could overflow on the next chunk are cut back to their best K
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - kChunk);
+                    while (need) {
+                        const int L = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int n = __shfl_sync(0xffffffffu, cnt, L);
+                        u64* gbuf = const_cast<u64*>(warp_buf) + (size_t)L * kCap;
+                        __syncwarp();
+                        warp_load_sort(s_sort, gbuf, n, lane);
+                        const int keep = n < K ? n : K;
+                        for (int i = lane; i < keep; i += 32) gbuf[i] = s_sort[i];
+                        const uint32_t nthr = n >= K ? (uint32_t)(s_sort[K - 1] >> 32) : 0u;
+                        __syncwarp();
+                        if (lane == L) { cnt = keep; thr = nthr; }
+                    }
+                }
+                // accumulator stage drained: hand it back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 1 || leader) mbar_arrive_local(bar_tempty + 8 * acc);
+                    else mbar_arrive_remote(bar_tempty + 8 * acc, 0);
+                }
+            }
+            // unit done: final sort of every row, one (val, id) list per (split, q)
+            for (int L = 0; L < 32; ++L) {
+                const int n = __shfl_sync(0xffffffffu, cnt, L);
+                const int64_t qL = ((int64_t)u.qb * CG + rank) * kBlockM + ew * 32 + L;
+                if (qL >= p.Q) break;  // warp-uniform: rows are ascending
+                u64* gbuf = const_cast<u64*>(warp_buf) + (size_t)L * kCap;
+                __syncwarp();
+                warp_load_sort(s_sort, gbuf, n, lane);
+                const size_t o = ((size_t)u.split * p.Q + qL) * K;
+                for (int i = lane; i < K; i += 32) {
+                    const u64 key = (i < n) ? s_sort[i] : 0ull;
+                    p.out_id[o + i] = key ? (int32_t)key_id(key) : -1;
+                    p.out_val[o + i] = key ? key_score(key) : -INFINITY;
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    // teardown: everyone (both CTAs of a pair) is done with TMEM and the barriers before they go away
+    tc_fence_before();
+    if (CG > 1) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+// (rows, E) fp32 row-major -> boxes of (32 floats, box_rows rows), 128-byte swizzle, zero fill out of bounds
+static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int E, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)E, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)E * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Plan {
+    int cg, QB, T, S, QG, grid;
+    int64_t cand_bytes, part_bytes;
+};
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+static Plan make_plan(int64_t Q, int64_t N, int K) {
+    Plan pl;
+    pl.cg = env_int("MR_SCORE_CTA_GROUP", 2) == 1 ? 1 : 2;
+    const int sms = sm_count();
+    const int clusters = sms / pl.cg;
+    pl.QB = (int)((Q + (int64_t)kBlockM * pl.cg - 1) / ((int64_t)kBlockM * pl.cg));
+    pl.T = (int)((N + kBlockN - 1) / kBlockN);
+    pl.QG = env_int("MR_SCORE_QGROUP", 16);
+    if (pl.QG < 1) pl.QG = 1;
+    // item splits: enough units to fill the machine evenly, few enough that a unit amortises its top-K warm-up
+    int smax = 8192 / (K > 0 ? K : 1);        // mr_topk_merge takes at most 8192 candidates per row
+    if (smax > pl.T) smax = pl.T;
+    if (smax < 1) smax = 1;
+    int s = env_int("MR_SCORE_SPLITS", 0);
+    if (s <= 0) {
+        int smin = pl.T / 16;                  // keep >= 16 tiles per unit when the catalog allows
+        if (smin > 8) smin = 8;
+        if (smin < 1) smin = 1;
+        double best = -1.0;
+        s = smin;
+        for (int c = smin; c <= smax; ++c) {
+            const int64_t units = (int64_t)pl.QB * c;
+            const int64_t waves = (units + clusters - 1) / clusters;
+            const double eff = (double)units / (double)(waves * clusters);
+            if (eff > best + 1e-9) { best = eff; s = c; }
+            if (eff >= 0.97) { s = c; break; }
+        }
+    }
+    if (s > smax) s = smax;
+    pl.S = s;
+    const int64_t units = (int64_t)pl.QB * pl.S;
+    pl.grid = (int)((units < clusters ? units : clusters) * pl.cg);
+    if (pl.grid < pl.cg) pl.grid = pl.cg;
+    pl.cand_bytes = (int64_t)sms * kBlockM * kCap * 8;
+    pl.part_bytes = pl.S > 1 ? (int64_t)pl.S * Q * K * 8 : 0;
+    return pl;
+}
+
+template <int CG>
+static int launch(const Plan& pl, const CUtensorMap& muh, const CUtensorMap& mul, const CUtensorMap& mih, const CUtensorMap& mil,
+                  const Params& p, cudaStream_t stream) {
+    using C = Cfg<CG>;
+    cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { set_error("mr_score_topk: shared memory attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pl.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, score_topk_kernel<CG>, muh, mul, mih, mil, p);
+    if (e != cudaSuccess) { set_error("mr_score_topk: launch: %s", cudaGetErrorString(e)); return (int)e; }
+    return MR_OK;
+}
+
+}  // namespace st
+}  // namespace mr
+
+extern "C" int64_t mr_score_topk_workspace_bytes(int64_t Q, int64_t N, int E, int K) {
+    using namespace mr;
+    if (Q < 0 || N < 0 || E < 1 || K < 1 || K > MR_MAX_FUSED_TOPK) {
+        set_error("mr_score_topk_workspace_bytes: need Q, N >= 0, E >= 1, 1 <= K <= %d", MR_MAX_FUSED_TOPK);
+        return MR_ERR_INVALID_ARG;
+    }
+    if (Q == 0) return 0;
+    const st::Plan pl = st::make_plan(Q, N, K);
+    return pl.cand_bytes + pl.part_bytes + 256;
+}
+
+extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, const float* Ihi, const float* Ilo, int64_t N,
+                             int E, int K, int32_t id_base, int mode, float* out_val, int32_t* out_id, void* ws,
+                             int64_t ws_bytes, mr_stream_t stream) {
+    using namespace mr;
+    MR_REQUIRE(Q >= 0 && N >= 0 && E >= 1, "mr_score_topk: need Q, N >= 0 and E >= 1");
+    MR_REQUIRE(K >= 1 && K <= MR_MAX_FUSED_TOPK, "mr_score_topk: K=%d outside [1,%d]", K, MR_MAX_FUSED_TOPK);
+    MR_REQUIRE(mode == MR_SCORE_TF32X3 || mode == MR_SCORE_TF32X1, "mr_score_topk: unknown mode %d", mode);
+    MR_REQUIRE(E % 4 == 0, "mr_score_topk: E=%d must be a multiple of 4 (16-byte rows for TMA)", E);
+    MR_REQUIRE(Q < (1ll << 31) - 512 && N < (1ll << 31) - 512 && (int64_t)id_base + N < (1ll << 31),
+               "mr_score_topk: Q, N and id_base + N must fit 31 bits");
+    if (Q == 0) return MR_OK;
+    MR_REQUIRE(Uhi && Ihi && out_val && out_id, "mr_score_topk: null pointer");
+    MR_REQUIRE(mode == MR_SCORE_TF32X1 || (Ulo && Ilo), "mr_score_topk: the 3xTF32 mode needs the lo operands");
+    MR_REQUIRE(host_aligned16(Uhi) && host_aligned16(Ihi) && host_aligned16(Ulo) && host_aligned16(Ilo),
+               "mr_score_topk: operands must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (N == 0) {  // nothing to score: every list is empty
+        cudaError_t e = cudaMemsetAsync(out_id, 0xFF, (size_t)Q * K * 4, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(out_val, 0xFF, (size_t)Q * K * 4, s);  // NaN payload; ids say "empty"
+        if (e != cudaSuccess) { set_error("mr_score_topk: memset: %s", cudaGetErrorString(e)); return (int)e; }
+        return MR_OK;
+    }
+    const st::Plan pl = st::make_plan(Q, N, K);
+    const int64_t need = pl.cand_bytes + pl.part_bytes + 256;
+    if (!ws || ws_bytes < need) {
+        set_error("mr_score_topk: workspace of %lld bytes needed, %lld given", (long long)need, (long long)ws_bytes);
+        return MR_ERR_WORKSPACE;
+    }
+    unsigned char* w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    st::Params p;
+    p.Q = Q; p.N = N; p.E = E; p.K = K; p.mode = mode; p.id_base = id_base;
+    p.KB = (E + st::kBlockK - 1) / st::kBlockK;
+    p.T = pl.T; p.QB = pl.QB; p.S = pl.S; p.QG = pl.QG;
+    p.cand = reinterpret_cast<mr::u64*>(w);
+    float* part_val = reinterpret_cast<float*>(w + pl.cand_bytes);
+    int32_t* part_id = reinterpret_cast<int32_t*>(w + pl.cand_bytes + pl.part_bytes / 2);
+    p.out_val = pl.S > 1 ? part_val : out_val;
+    p.out_id = pl.S > 1 ? part_id : out_id;
+
+    CUtensorMap muh, mul, mih, mil;
+    const int brows = st::kBlockN / pl.cg;
+    bool ok = st::make_map(&muh, Uhi, Q, E, st::kBlockM) && st::make_map(&mih, Ihi, N, E, brows);
+    if (ok && mode == MR_SCORE_TF32X3) ok = st::make_map(&mul, Ulo, Q, E, st::kBlockM) && st::make_map(&mil, Ilo, N, E, brows);
+    else if (ok) { mul = muh; mil = mih; }
+    if (!ok) { set_error("mr_score_topk: cuTensorMapEncodeTiled failed (driver without TMA support?)"); return MR_ERR_UNSUPPORTED; }
+
+    int rc = pl.cg == 1 ? st::launch<1>(pl, muh, mul, mih, mil, p, s) : st::launch<2>(pl, muh, mul, mih, mil, p, s);
+    if (rc != MR_OK) return rc;
+    if (pl.S > 1) return mr_topk_merge(part_val, part_id, pl.S, Q, K, K, out_val, out_id, stream);
+    return MR_OK;
+}

@@ -88,41 +88,89 @@ struct PassCounters {
     int cand_cap;
 };
 
+// Shared-memory layout of the pass kernel (dynamic): hist[K][bins] u32 | lo[K] hi[K] u64 | shift[K] i32 |
+// lom[K] span[K] i32 | cn[K] notabove[K] ge[K] u32
+template <int K>
+struct PassSmem {
+    uint32_t* hist; u64* lo; u64* hi; int* shift; int* lom; int* span; uint32_t* cn; uint32_t* notabove; uint32_t* ge;
+    __device__ __forceinline__ explicit PassSmem(unsigned char* raw) {
+        hist = reinterpret_cast<uint32_t*>(raw);
+        lo = reinterpret_cast<u64*>(hist + K * kTiesBins);
+        hi = lo + K;
+        shift = reinterpret_cast<int*>(hi + K);
+        lom = shift + K;
+        span = lom + K;
+        cn = reinterpret_cast<uint32_t*>(span + K);
+        notabove = cn + K;
+        ge = notabove + K;
+    }
+    static constexpr size_t bytes() { return (size_t)K * kTiesBins * 4 + (size_t)K * (8 + 8 + 4 * 6) + 16; }
+};
+
+// Rare path (the magnitude lies inside [lo_mag, hi_mag]): exact 64-bit classification against the bracket.
+template <int K, bool COLLECT>
+__device__ __noinline__ void ties_pass_edge(unsigned char* raw, uint32_t mag, int64_t j, int k, u64* cand_keys,
+                                            int cand_cap) {
+    PassSmem<K> sm(raw);
+    const u64 key = ties_key(mag, j);
+    if (key > sm.hi[k]) return;                 // above the bracket after all (already counted by the caller)
+    atomicAdd(&sm.notabove[k], 1u);
+    if (key < sm.lo[k]) return;                 // below it
+    const uint32_t bin = (uint32_t)((key - sm.lo[k]) >> sm.shift[k]);
+    atomicAdd(&sm.hist[k * kTiesBins + bin], 1u);
+    if (COLLECT) {
+        const uint32_t pos = atomicAdd(&sm.cn[k], 1u);
+        if (pos < (uint32_t)cand_cap) cand_keys[((size_t)k * gridDim.x + blockIdx.x) * cand_cap + pos] = key;
+    }
+}
+
+// One streaming pass: per model, count the keys above the bracket, histogram (and optionally store) the keys inside.
+// Per element and model the common path is FSUB, AND, ISUB, compare+count, compare+branch; everything 64-bit lives
+// in ties_pass_edge.  VEC: all pointers 16-byte aligned (128-bit loads); otherwise scalar loads.
 template <int K, bool VEC, bool W, bool COLLECT>
-__global__ void __launch_bounds__(kTiesThreads)
+__global__ void __launch_bounds__(kTiesThreads, K <= 8 ? 3 : 2)
 ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const float* __restrict__ w,
                  int64_t stride, const TiesState* __restrict__ st, PassCounters pc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);              // K * bins
-    u64* s_lo = reinterpret_cast<u64*>(s_hist + K * kTiesBins);            // K
-    u64* s_hi = s_lo + K;                                                  // K
-    int* s_shift = reinterpret_cast<int*>(s_hi + K);                       // K
-    uint32_t* s_cn = reinterpret_cast<uint32_t*>(s_shift + K);             // K (COLLECT)
-
-    for (int i = threadIdx.x; i < K * kTiesBins; i += blockDim.x) s_hist[i] = 0;
+    PassSmem<K> sm(smem_raw);
+    for (int i = threadIdx.x; i < K * kTiesBins; i += blockDim.x) sm.hist[i] = 0;
     if (threadIdx.x < K) {
-        s_lo[threadIdx.x] = st[threadIdx.x].lo;
-        s_hi[threadIdx.x] = st[threadIdx.x].hi;
-        s_shift[threadIdx.x] = st[threadIdx.x].shift;
-        s_cn[threadIdx.x] = 0;
+        const TiesState s = st[threadIdx.x];
+        sm.lo[threadIdx.x] = s.lo;
+        sm.hi[threadIdx.x] = s.hi;
+        sm.shift[threadIdx.x] = s.shift;
+        sm.lom[threadIdx.x] = (int)(uint32_t)(s.lo >> 32);
+        sm.span[threadIdx.x] = (int)((uint32_t)(s.hi >> 32) - (uint32_t)(s.lo >> 32));
+        sm.cn[threadIdx.x] = 0;
+        sm.notabove[threadIdx.x] = 0;
+        sm.ge[threadIdx.x] = 0;
     }
     __syncthreads();
 
-    uint32_t lo_mag[K], hi_mag[K];
-    uint32_t above[K];  // per-thread counts fit 32 bits (d < 2^32)
+    uint32_t ge[K];  // per-thread count of magnitudes >= lo_mag (fits 32 bits: d < 2^32)
     float wreg[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        lo_mag[k] = (uint32_t)(s_lo[k] >> 32);
-        hi_mag[k] = (uint32_t)(s_hi[k] >> 32);
-        above[k] = 0;
+        ge[k] = 0;
         wreg[k] = W ? w[k] : 1.0f;
     }
 
-    const int64_t nq = (d + 3) >> 2;                       // quads of 4 consecutive elements
+    const int64_t nq_full = d >> 2;                        // quads of 4 consecutive elements
+    const int64_t nq = (d + 3) >> 2;                       // ... including a partial last one
     const int64_t nsq = (nq + stride - 1) / stride;        // sampled quads
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+
+#define MR_TIES_ELEMENT(K_, X_, B_, J_)                                                        \
+    do {                                                                                       \
+        float u_ = __fsub_rn((X_), (B_));                                                      \
+        if (W) u_ = __fmul_rn(u_, wreg[K_]);                                                   \
+        const uint32_t mag_ = __float_as_uint(u_) & 0x7FFFFFFFu;                               \
+        const int t_ = (int)mag_ - sm.lom[K_];                                                 \
+        ge[K_] += (t_ >= 0) ? 1u : 0u;                                                         \
+        if ((uint32_t)t_ <= (uint32_t)sm.span[K_])                                             \
+            ties_pass_edge<K, COLLECT>(smem_raw, mag_, (J_), (K_), pc.cand_keys, pc.cand_cap); \
+    } while (0)
 
     for (int64_t i = gtid; i < nsq; i += gsz) {
         int64_t q = i * stride;
@@ -131,69 +179,47 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
             if (q >= nq) q = nq - 1;
         }
         const int64_t j0 = q << 2;
-        const int nvalid = (int)((d - j0) < 4 ? (d - j0) : 4);
-        float bx[4];
-        float xs[K][4];
-        if (VEC && nvalid == 4) {
+        if (VEC && q < nq_full) {
             const float4 b4 = ldg_stream4(base + j0);
-            bx[0] = b4.x; bx[1] = b4.y; bx[2] = b4.z; bx[3] = b4.w;
+            float4 xs[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) xs[k] = ldg_stream4(models.p[k] + j0);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const float4 v = ldg_stream4(models.p[k] + j0);
-                xs[k][0] = v.x; xs[k][1] = v.y; xs[k][2] = v.z; xs[k][3] = v.w;
+                MR_TIES_ELEMENT(k, xs[k].x, b4.x, j0);
+                MR_TIES_ELEMENT(k, xs[k].y, b4.y, j0 + 1);
+                MR_TIES_ELEMENT(k, xs[k].z, b4.z, j0 + 2);
+                MR_TIES_ELEMENT(k, xs[k].w, b4.w, j0 + 3);
             }
         } else {
+            const int nvalid = (int)((d - j0) < 4 ? (d - j0) : 4);
+            for (int c = 0; c < nvalid; ++c) {
+                const float b = base[j0 + c];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const bool ok = c < nvalid;
-                bx[c] = ok ? base[j0 + c] : 0.0f;
-#pragma unroll
-                for (int k = 0; k < K; ++k) xs[k][c] = ok ? models.p[k][j0 + c] : 0.0f;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float u = __fsub_rn(xs[k][c], bx[c]);
-                if (W) u = __fmul_rn(u, wreg[k]);
-                const uint32_t mag = __float_as_uint(u) & 0x7FFFFFFFu;
-                if (c < nvalid) {
-                    if (mag > hi_mag[k]) {
-                        ++above[k];
-                    } else if (mag >= lo_mag[k]) {  // rare: inside or at the edge of the bracket
-                        const u64 key = ties_key(mag, j0 + c);
-                        if (key > s_hi[k]) {
-                            ++above[k];
-                        } else if (key >= s_lo[k]) {
-                            const uint32_t bin = (uint32_t)((key - s_lo[k]) >> s_shift[k]);
-                            atomicAdd(&s_hist[k * kTiesBins + bin], 1u);
-                            if (COLLECT) {
-                                const uint32_t pos = atomicAdd(&s_cn[k], 1u);
-                                if (pos < (uint32_t)pc.cand_cap)
-                                    pc.cand_keys[((size_t)k * gridDim.x + blockIdx.x) * pc.cand_cap + pos] = key;
-                            }
-                        }
-                    }
-                }
+                for (int k = 0; k < K; ++k) MR_TIES_ELEMENT(k, models.p[k][j0 + c], b, j0 + c);
             }
         }
     }
+#undef MR_TIES_ELEMENT
 
-    // block-reduce the above counters (warp shuffle, then one 64-bit atomic per warp and model)
+    // above = (#magnitudes >= lo_mag) - (#of those that turned out not to be above the bracket)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        uint32_t v = above[k];
+        uint32_t v = ge[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&pc.above[k], (u64)v);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sm.ge[k], v);
     }
     __syncthreads();
+    if (threadIdx.x < K) {
+        const uint32_t v = sm.ge[threadIdx.x] - sm.notabove[threadIdx.x];
+        if (v) atomicAdd(&pc.above[threadIdx.x], (u64)v);
+        if (COLLECT) pc.cand_cnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = sm.cn[threadIdx.x];
+    }
     for (int i = threadIdx.x; i < K * kTiesBins; i += blockDim.x) {
-        const uint32_t v = s_hist[i];
+        const uint32_t v = sm.hist[i];
         if (v) atomicAdd(&pc.hist[i], v);
     }
-    if (COLLECT && threadIdx.x < K) pc.cand_cnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_cn[threadIdx.x];
 }
 
 // ---- pick: turn a histogram into a narrower bracket ---------------------------------------------------
@@ -606,7 +632,7 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
     bool vec = host_aligned16(base);
     for (int k = 0; k < K; ++k) { pack.p[k] = models[k]; vec = vec && host_aligned16(models[k]); }
     PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap};
-    const size_t smem = (size_t)K * kTiesBins * 4 + (size_t)K * (8 + 8 + 4 + 4) + 16;
+    const size_t smem = PassSmem<K>::bytes();
     const int blocks = ties_pass_blocks();
     cudaError_t e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
     if (e != cudaSuccess) { set_error("mr_ties_select: memset: %s", cudaGetErrorString(e)); return (int)e; }

@@ -1,0 +1,7 @@
+"""Evaluator hot path (reference: rec_retrieval/evaluator/__init__.py)."""
+from .enums import MetricType
+from .evaluator import Evaluator
+from .metrics import NDCG, BaseMetric, Recall
+from .sharded import ShardedItemTable, shard_bounds
+
+__all__ = ["Evaluator", "MetricType", "Recall", "NDCG", "BaseMetric", "ShardedItemTable", "shard_bounds"]

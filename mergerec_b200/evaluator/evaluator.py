@@ -1,0 +1,123 @@
+"""``Evaluator`` -- full-catalog top-K evaluation (reference: rec_retrieval/evaluator/evaluator.py:6-49).
+
+``Evaluator(metrics, ks)(scores, labels, metric_prefix)`` keeps the reference contract (a materialised (Q, N)
+score matrix in, ``{prefix}{Recall|NDCG}@{k}`` python floats out, same key order).  Because that contract forces
+the caller to build the score matrix (module/recommender/module.py:137, :344-352), two additions take the
+embeddings instead and never materialise it: ``topk_embeddings`` and ``evaluate_embeddings`` run the fused
+tensor-core scoring + per-row top-K kernel (``mr_score_topk``), shard-aware through ``ShardedItemTable``.
+
+Top-K order is (score desc, item id asc): ``torch.topk``'s order among equal scores is unspecified (SURVEY.md
+0.1-D3), so ids can differ from the raw reference only inside groups of exactly equal scores.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+
+from .. import _lib
+from .enums import MetricType
+from .metrics import label_rank
+from .sharded import MAX_FUSED_TOPK, MR_SCORE_TF32X3, ShardedItemTable, exchange_topk, split_tf32
+
+MAX_TOPK = 1024
+
+
+def topk_rows(scores: torch.Tensor, k: int, id_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(values (Q, k) fp32, ids (Q, k) int32) of a (Q, N) score matrix: `mr_topk_rows`, the drop-in for
+    ``torch.topk(scores, k, dim=1)`` (evaluator.py:43).  CPU inputs are copied to the GPU in row chunks."""
+    dev = _lib.require_cuda()
+    lib = _lib.load()
+    if scores.dim() != 2:
+        raise ValueError("scores must be (Q, N)")
+    Q, N = scores.shape
+    if k > N:
+        raise RuntimeError(f"selected index k out of range (k={k}, N={N})")  # torch.topk's error class
+    out_v = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    rows_per_chunk = Q if scores.is_cuda else max(1, min(Q, (1 << 30) // max(4 * N, 1)))
+    for q0 in range(0, Q, max(rows_per_chunk, 1)):
+        q1 = min(Q, q0 + rows_per_chunk)
+        chunk = scores[q0:q1].to(device=dev, dtype=torch.float32, non_blocking=True)
+        if chunk.stride(1) != 1:
+            chunk = chunk.contiguous()
+        _lib.check(lib.mr_topk_rows(_lib.dptr(chunk), q1 - q0, N, chunk.stride(0), k, id_base,
+                                    _lib.dptr(out_v[q0:q1]), _lib.dptr(out_i[q0:q1]), _lib.stream_handle()),
+                   "mr_topk_rows")
+    return out_v, out_i
+
+
+def score_topk(user_hi: torch.Tensor, user_lo: Optional[torch.Tensor], table: ShardedItemTable, k: int,
+               mode: int = MR_SCORE_TF32X3) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Local fused scoring + top-k of pre-split queries against this rank's shard (`mr_score_topk`)."""
+    dev = _lib.require_cuda()
+    lib = _lib.load()
+    Q, E = user_hi.shape
+    if E != table.dim:
+        raise ValueError(f"embedding dims differ: queries {E}, items {table.dim}")
+    out_v = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.mr_score_topk_workspace_bytes(Q, table.n_local, E, k))
+    if ws_bytes < 0:
+        _lib.check(ws_bytes, "mr_score_topk_workspace_bytes")
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    _lib.check(lib.mr_score_topk(_lib.dptr(user_hi), _lib.dptr(user_lo), Q, _lib.dptr(table.hi), _lib.dptr(table.lo),
+                                 table.n_local, E, k, table.id_base, mode, _lib.dptr(out_v), _lib.dptr(out_i),
+                                 _lib.dptr(ws), ws_bytes, _lib.stream_handle()), "mr_score_topk")
+    return out_v, out_i
+
+
+class Evaluator:
+    def __init__(self, metrics: List[str], ks: List[int]):
+        self.metric_names = metrics
+        self.ks = ks
+        self._max_k = max(ks)
+        self._metrics = []
+        for metric in metrics:
+            for k in ks:
+                self._metrics.append(MetricType[metric].metric_cls(k))
+
+    # ------------------------------------------------------------------ reference contract
+    def evaluate(self, scores: torch.Tensor, labels: torch.Tensor, metric_prefix: str = "") -> Dict[str, float]:
+        return self(scores, labels, metric_prefix)
+
+    def __call__(self, scores: torch.Tensor, labels: torch.Tensor, metric_prefix: str = "") -> Dict[str, float]:
+        _, ids = topk_rows(scores, self._max_k)
+        return self.metrics_from_ids(ids, labels, metric_prefix)
+
+    # ------------------------------------------------------------------ fused additions
+    def topk_embeddings(self, user_emb: torch.Tensor, item_emb: Union[torch.Tensor, ShardedItemTable],
+                        k: Optional[int] = None, normalize: bool = False,
+                        mode: int = MR_SCORE_TF32X3) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Top-k (values fp32, global ids int32), both (Q, k), of ``user_emb @ item_emb.T`` without the matrix.
+
+        ``item_emb`` is an (N, E) tensor (single GPU) or a ``ShardedItemTable`` (reusable, possibly one shard of
+        a multi-GPU catalog -- then every rank passes the same queries and receives the same merged lists).
+        ``normalize`` applies the reference's cosine normalisation to the queries (and to a raw item tensor)."""
+        k = self._max_k if k is None else k
+        if k > MAX_FUSED_TOPK:
+            raise ValueError(f"fused top-k supports k <= {MAX_FUSED_TOPK}")
+        dev = _lib.require_cuda()
+        table = item_emb if isinstance(item_emb, ShardedItemTable) else ShardedItemTable(item_emb, normalize=normalize)
+        if k > table.n_total:
+            raise RuntimeError(f"selected index k out of range (k={k}, N={table.n_total})")
+        users = user_emb.to(device=dev, dtype=torch.float32)
+        if normalize:
+            users = torch.nn.functional.normalize(users, p=2, dim=-1)
+        u_hi, u_lo = split_tf32(users)
+        vals, ids = score_topk(u_hi, u_lo, table, k, mode)
+        if table.group is not None:
+            vals, ids = exchange_topk(vals, ids, k, table.group)
+        return vals, ids
+
+    def evaluate_embeddings(self, user_emb: torch.Tensor, item_emb: Union[torch.Tensor, ShardedItemTable],
+                            labels: torch.Tensor, metric_prefix: str = "", normalize: bool = False,
+                            mode: int = MR_SCORE_TF32X3) -> Dict[str, float]:
+        _, ids = self.topk_embeddings(user_emb, item_emb, self._max_k, normalize, mode)
+        return self.metrics_from_ids(ids, labels, metric_prefix)
+
+    # ------------------------------------------------------------------ shared tail
+    def metrics_from_ids(self, ids: torch.Tensor, labels: torch.Tensor, metric_prefix: str = "") -> Dict[str, float]:
+        """One rank lookup on the GPU (Q int32 back to the host), then every (metric, k) from the same ranks."""
+        ranks = label_rank(ids, labels).cpu().numpy()
+        return {metric_prefix + m.name: m.from_ranks(ranks) for m in self._metrics}

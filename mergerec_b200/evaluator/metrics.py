@@ -1,0 +1,87 @@
+"""Recall@k / NDCG@k (reference: rec_retrieval/evaluator/metrics.py:4-88).
+
+The per-row search (`true in pred`, `pred.index(true)`) runs on the GPU as one `mr_label_rank` launch that
+returns the position of the label inside each row's predicted list (-1 = absent).  The final reduction is the
+reference's own arithmetic, kept on the host so the Python floats come out bit-identical:
+`sum(list_of_row_values) / len(list)` in row order, with the NDCG gain `1 / log2_fp32(rank + 2)` taken from a
+table built with the very expression the reference evaluates per hit row (metrics.py:84).
+"""
+from __future__ import annotations
+
+from functools import lru_cache
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+@lru_cache(maxsize=None)
+def _gain_table(n: int) -> np.ndarray:
+    """gain[r] = 1 / (torch.log2(torch.tensor(r + 2)).item())  -- int64 -> fp32 log2 -> python float."""
+    return np.asarray([1 / (torch.log2(torch.tensor(r + 2)).item()) for r in range(n)], dtype=np.float64)
+
+
+def label_rank(ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """rank[q] = index of labels[q] in ids[q, :], or -1 (int32, on the GPU)."""
+    dev = _lib.require_cuda()
+    lib = _lib.load()
+    ids = ids.to(device=dev, dtype=torch.int32).contiguous()
+    labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+    if ids.dim() != 2 or labels.dim() != 1 or labels.numel() != ids.shape[0]:
+        raise ValueError("expected y_pred (Q, C) and y_true (Q,)")
+    Q, K = ids.shape
+    rank = torch.empty(Q, dtype=torch.int32, device=dev)
+    if Q and K:
+        _lib.check(lib.mr_label_rank(_lib.dptr(ids), Q, K, _lib.dptr(labels), _lib.dptr(rank), _lib.stream_handle()),
+                   "mr_label_rank")
+    elif Q:
+        rank.fill_(-1)
+    return rank
+
+
+def recall_from_ranks(ranks: np.ndarray, k: int) -> float:
+    vals: List[float] = np.where((ranks >= 0) & (ranks < k), 1.0, 0.0).tolist()
+    return sum(vals) / len(vals) if vals else 0.0
+
+
+def ndcg_from_ranks(ranks: np.ndarray, k: int) -> float:
+    hit = (ranks >= 0) & (ranks < k)
+    table = _gain_table(max(int(k), 1))
+    vals: List[float] = np.where(hit, table[np.where(hit, ranks, 0)], 0.0).tolist()
+    return sum(vals) / len(vals) if vals else 0.0
+
+
+class BaseMetric:
+    METRIC_NAME: Optional[str] = None
+
+    def __init__(self, k: int):
+        super().__init__()
+        self.k = k
+
+    def __call__(self, y_true: torch.Tensor, y_pred: torch.Tensor) -> float:
+        """y_true (Q,) labels, y_pred (Q, C) predicted ids -> metric@k over the first k columns."""
+        ranks = label_rank(y_pred[:, : self.k], y_true).cpu().numpy()
+        return self.from_ranks(ranks)
+
+    def from_ranks(self, ranks: np.ndarray) -> float:
+        raise NotImplementedError("Subclasses must implement this method.")
+
+    @property
+    def name(self) -> str:
+        return f"{self.METRIC_NAME}@{self.k}"
+
+
+class Recall(BaseMetric):
+    METRIC_NAME = "Recall"
+
+    def from_ranks(self, ranks: np.ndarray) -> float:
+        return recall_from_ranks(ranks, self.k)
+
+
+class NDCG(BaseMetric):
+    METRIC_NAME = "NDCG"
+
+    def from_ranks(self, ranks: np.ndarray) -> float:
+        return ndcg_from_ranks(ranks, self.k)

@@ -1,0 +1,111 @@
+"""Item-table handles for the fused scoring path: the pre-split (hi, lo) TF32 operands of one GPU's shard of the
+catalog, and the exchange step that merges per-GPU top-K lists (NCCL allgather over NVLink + `mr_topk_merge`).
+
+The reference is single-GPU and evaluates one domain catalog at a time (README.md:51-53, utils.py:108-119); the
+sharding is this package's multi-GPU extension: rows [lo, hi) of the item table live on
+rank r, global item id = id_base + local row, queries are replicated, and the merged answer is bit-identical to
+the single-GPU one because every (query, item) score is computed by the same instruction sequence on any rank.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from .. import _lib
+
+MR_SCORE_TF32X3, MR_SCORE_TF32X1 = 0, 1
+MAX_FUSED_TOPK = 128
+
+
+def shard_bounds(n_items: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of the item table owned by `rank`: contiguous, sizes differ by at most one, earlier ranks
+    take the remainder (so global ids stay ascending with the rank -- the tie rule needs nothing else)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def split_tf32(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """hi = rna_tf32(x), lo = rna_tf32(x - hi) on the GPU (`mr_split_tf32`)."""
+    dev = _lib.require_cuda()
+    lib = _lib.load()
+    x = x.to(device=dev, dtype=torch.float32).contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    if x.numel():
+        _lib.check(lib.mr_split_tf32(_lib.dptr(x), x.numel(), _lib.dptr(hi), _lib.dptr(lo), _lib.stream_handle()),
+                   "mr_split_tf32")
+    return hi, lo
+
+
+def topk_merge(vals: torch.Tensor, ids: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge (L, Q, K_in) per-shard lists into (Q, k_out) under (score desc, id asc) (`mr_topk_merge`)."""
+    dev = _lib.require_cuda()
+    lib = _lib.load()
+    vals = vals.to(device=dev, dtype=torch.float32).contiguous()
+    ids = ids.to(device=dev, dtype=torch.int32).contiguous()
+    L, Q, K_in = vals.shape
+    out_v = torch.empty((Q, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((Q, k_out), dtype=torch.int32, device=dev)
+    _lib.check(lib.mr_topk_merge(_lib.dptr(vals), _lib.dptr(ids), L, Q, K_in, k_out, _lib.dptr(out_v), _lib.dptr(out_i),
+                                 _lib.stream_handle()), "mr_topk_merge")
+    return out_v, out_i
+
+
+class ShardedItemTable:
+    """One rank's rows of the item-embedding table, stored as the (hi, lo) operand pair of the 3xTF32 contraction.
+
+    items      (n_local, E) fp32 rows owned by this rank (any device; moved to the current GPU).
+    id_base    global id of local row 0.
+    n_total    catalog size over all ranks (defaults to n_local: a single-GPU table).
+    group      torch.distributed process group holding the other shards (None = no exchange).
+    """
+
+    def __init__(self, items: torch.Tensor, id_base: int = 0, n_total: Optional[int] = None, group=None,
+                 normalize: bool = False):
+        dev = _lib.require_cuda()
+        items = items.to(device=dev, dtype=torch.float32)
+        if items.dim() != 2:
+            raise ValueError("item table must be (N, E)")
+        if normalize:
+            items = torch.nn.functional.normalize(items, p=2, dim=-1)  # module/recommender/module.py:74-77
+        self.hi, self.lo = split_tf32(items)
+        self.n_local, self.dim = items.shape
+        self.id_base = int(id_base)
+        self.n_total = int(n_total if n_total is not None else self.n_local)
+        self.group = group
+
+    @classmethod
+    def from_full(cls, items: torch.Tensor, group=None, normalize: bool = False) -> "ShardedItemTable":
+        """Keep this rank's slice of a table every rank can see (host tensor or replicated)."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        lo, hi = shard_bounds(items.shape[0], world, rank)
+        return cls(items[lo:hi], id_base=lo, n_total=items.shape[0], group=group if world > 1 else None,
+                   normalize=normalize)
+
+    @property
+    def world(self) -> int:
+        if self.group is None:
+            return 1
+        import torch.distributed as dist
+        return dist.get_world_size(self.group)
+
+
+def exchange_topk(local_vals: torch.Tensor, local_ids: torch.Tensor, k: int, group,
+                  merge: Callable = topk_merge) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The exchange step: allgather every rank's (Q, k) list and merge.  `merge` is injectable so the host logic
+    can be exercised with the gloo backend on CPU tensors (tests); the product path uses `mr_topk_merge`."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local_vals, local_ids
+    Q = local_vals.shape[0]
+    all_v = torch.empty((world, Q, k), dtype=local_vals.dtype, device=local_vals.device)
+    all_i = torch.empty((world, Q, k), dtype=local_ids.dtype, device=local_ids.device)
+    dist.all_gather_into_tensor(all_v, local_vals.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, local_ids.contiguous(), group=group)
+    return merge(all_v, all_i, k)
