@@ -185,6 +185,8 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         line.update(wl.extra())
+        if hasattr(wl, "Q"):
+            line["eval_seqs_per_s"] = wl.Q / (ms_per_step * 1e-3)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

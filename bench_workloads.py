@@ -269,5 +269,124 @@ class TiesCfg2(LambdaMergeK8):
                 "sample": self._cpu_sample + "; time scaled x8 to the full vector"}
 
 
-WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8, TiesCfg2.name: TiesCfg2}
+class EvalCatalog(Workload):
+    """BASELINE config 5 (evaluator): full-catalog scoring of Q query embeddings against an N-item table (E = 768),
+    fused per-row top-100, label rank and Recall/NDCG.  The item table is sharded over the ranks (N / world rows
+    each, strong scaling); every rank scores all queries against its shard, the per-rank top-K lists are
+    allgathered over NCCL and merged.  One step = one pass of all Q queries over the whole catalog.
+
+    The default sizes are a slice of config 5 (N = 1,000,000 x Q = 65,536 would take minutes per step on one GPU):
+    MR_BENCH_EVAL_Q / MR_BENCH_EVAL_N / MR_BENCH_EVAL_K / MR_BENCH_EVAL_E override them."""
+
+    name = "eval_cfg5"
+    metric = "catalog scores/sec (Q*N / time, fused scoring + top-K + Recall/NDCG)"
+    unit = "scores/s"
+    dtype = "tf32x3 (fp32-faithful split, fp32 accumulate)"
+    scaling = "strong"
+    e2e_steps_cap = 3
+
+    def __init__(self, rank, world, device):
+        super().__init__(rank, world, device)
+        self.Q = int(os.environ.get("MR_BENCH_EVAL_Q", 2048))
+        self.N = int(os.environ.get("MR_BENCH_EVAL_N", 500_000))
+        self.E = int(os.environ.get("MR_BENCH_EVAL_E", 768))
+        self.K = int(os.environ.get("MR_BENCH_EVAL_K", 100))
+        self.mode = int(os.environ.get("MR_BENCH_EVAL_MODE", 0))
+        self.flops = 2.0 * self.Q * self.N * self.E
+        self.launches_per_step = 5 if world == 1 else 6  # split(users), score_topk, [split merge], [shard merge], label_rank
+
+    def config(self):
+        return {"workload": f"BASELINE config 5 slice: {self.Q} query seqs x {self.N}-item catalog, E={self.E}, "
+                            f"top-{self.K}, Recall/NDCG@{{10,{self.K}}}; item table sharded over {self.world} GPU(s), "
+                            "NCCL allgather of per-GPU top-K + merge",
+                "Q": self.Q, "N": self.N, "E": self.E, "K": self.K, "mode": "tf32x3" if self.mode == 0 else "tf32x1",
+                "l2": "item table (3.1 GB x2 hi/lo at N=1M) exceeds L2, no flush needed",
+                "parallelism": f"item-sharded x{self.world}" if self.world > 1 else "1 GPU"}
+
+    def setup(self):
+        import torch.distributed as dist
+        from mergerec_b200.evaluator import Evaluator, ShardedItemTable, shard_bounds
+        g = torch.Generator(device=self.device).manual_seed(99)       # same queries on every rank
+        self.users = torch.nn.functional.normalize(torch.randn(self.Q, self.E, generator=g, device=self.device), dim=-1)
+        self.labels = torch.randint(0, self.N, (self.Q,), generator=g, device=self.device)
+        lo, hi = shard_bounds(self.N, self.world, self.rank)
+        gi = torch.Generator(device=self.device).manual_seed(1000 + self.rank)
+        self.items = torch.nn.functional.normalize(torch.randn(hi - lo, self.E, generator=gi, device=self.device), dim=-1)
+        self.lo = lo
+        self.group = dist.group.WORLD if self.world > 1 else None
+        self.table = ShardedItemTable(self.items, id_base=lo, n_total=self.N, group=self.group)
+        self.ev = Evaluator(["RECALL", "NDCG"], [10, self.K])
+        self.last = None
+
+    def step(self):
+        self.last = self.ev.evaluate_embeddings(self.users, self.table, self.labels, mode=self.mode)
+
+    def units_per_step_all_ranks(self):
+        return float(self.Q) * float(self.N)
+
+    def setup_e2e(self):
+        self.h_users = _pinned(self.users.cpu())
+        self.h_items = _pinned(self.items.cpu())
+        self.h_labels = _pinned(self.labels.cpu())
+        self.h2d_bytes = self.h_users.numel() * 4 + self.h_items.numel() * 4 + self.h_labels.numel() * 8
+        self.d2h_bytes = self.Q * 4          # the rank of each label; the metric floats are finished on the host
+
+    def step_e2e(self):
+        from mergerec_b200.evaluator import ShardedItemTable
+        users = self.h_users.to(self.device, non_blocking=True)
+        items = self.h_items.to(self.device, non_blocking=True)
+        labels = self.h_labels.to(self.device, non_blocking=True)
+        table = ShardedItemTable(items, id_base=self.lo, n_total=self.N, group=self.group)
+        self.last = self.ev.evaluate_embeddings(users, table, labels, mode=self.mode)
+
+    def roofline(self, peaks):
+        from bench import event_time_ms
+        from mergerec_b200.evaluator.evaluator import score_topk
+        from mergerec_b200.evaluator.sharded import split_tf32
+        u_hi, u_lo = split_tf32(self.users)
+        ms = event_time_ms(lambda: score_topk(u_hi, u_lo, self.table, self.K, self.mode), 2)
+        passes = 3 if self.mode == 0 else 1
+        local_flops = 2.0 * self.Q * self.table.n_local * self.E
+        ach = passes * local_flops / (ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"] / 2
+        return {"bound": "tensor", "kernel": "mr::st::score_topk_kernel<2> (tcgen05.mma kind::tf32, cta_group::2) + list merge",
+                "achieved": ach, "peak": peak, "peak_source": peaks["source"] + ": sustained bf16 cuBLAS / 2 (tf32 runs at half the bf16 rate)",
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms_per_launch": ms,
+                "tensor_passes": passes, "logical_tflops": local_flops / (ms * 1e-3) / 1e12,
+                "algorithmic_flops_per_launch": passes * local_flops,
+                "peak_burst": peaks["bf16_tflops"] / 2, "frac_of_burst": ach / (peaks["bf16_tflops"] / 2)}
+
+    def extra(self):
+        return {"metrics": self.last}
+
+    # -- CPU arms: fp32 sgemm + canonical top-K + metrics (oracle port of module.py:137 + evaluator.py:31-49)
+    def _cpu_time(self, reps):
+        from oracle import oracle as orc
+        Qs, Ns = min(self.Q, 256), min(self.N, 100_000)
+        rng = np.random.Generator(np.random.PCG64(7))
+        users = rng.standard_normal((Qs, self.E), dtype=np.float32)
+        items = rng.standard_normal((Ns, self.E), dtype=np.float32)
+        labels = rng.integers(0, Ns, size=Qs)
+        ts = []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            scores = orc.scores_f32(users, items)
+            orc.evaluate(scores, labels, ["RECALL", "NDCG"], [10, min(self.K, Ns)])
+            ts.append(time.perf_counter() - t0)
+        t = float(np.median(ts[1:]))
+        self._cpu_sample = (f"{Qs} queries x {Ns} items (E={self.E}) of the workload: numpy/BLAS sgemm + OpenMP C top-K + "
+                            "python metric loops (oracle port); rate scaled linearly")
+        return t, Qs * Ns, max(orc.max_threads(), os.cpu_count() or 1)
+
+    def cpu_baseline(self):
+        t, n, cores = self._cpu_time(2)
+        return {"value": n / t, "unit": self.unit, "cores": cores, "kind": "port", "sample": self._cpu_sample,
+                "seconds_per_sample": t}
+
+    def reference_arm(self, steps, warmup):
+        t, n, cores = self._cpu_time(max(1, min(steps, 3)))
+        return {"value": n / t, "ms_per_step": t * 1e3, "cores": cores, "sample": self._cpu_sample}
+
+
+WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8, TiesCfg2.name: TiesCfg2, EvalCatalog.name: EvalCatalog}
 DEFAULT_WORKLOAD = TiesCfg2.name

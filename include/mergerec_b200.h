@@ -174,6 +174,10 @@ int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, const float* Ih
                   int K, int32_t id_base, int mode, float* out_val, int32_t* out_id, void* ws, int64_t ws_bytes,
                   mr_stream_t stream);
 
+/* Diagnostics: when dev_buf != NULL, later mr_score_topk launches of this thread make block 0 record clock64()
+ * stamps per tile (3 roles x 64 tiles x 4 slots of int64: tools/score_sweep.py prints them).  NULL switches it off. */
+int mr_score_topk_debug_buffer(void* dev_buf, int64_t bytes);
+
 /* hi = rna_tf32(x), lo = rna_tf32(x - hi): the operand split of the fp32-faithful 3xTF32 contraction. */
 int mr_split_tf32(const float* x, int64_t n, float* hi, float* lo, mr_stream_t stream);
 

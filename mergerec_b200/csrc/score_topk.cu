@@ -32,9 +32,10 @@ constexpr int kBlockM = 128;   // query rows per CTA (TMEM lanes)
 constexpr int kBlockN = 256;   // items per tile (TMEM columns per accumulator stage)
 constexpr int kBlockK = 32;    // fp32 elements per k-block: 128 bytes = one SWIZZLE_128B atom
 constexpr int kUmmaK = 8;      // tf32: 32 bytes of K per tcgen05.mma
-constexpr int kThreads = 256;
+constexpr int kEpiGroups = 1;  // epilogue warp groups (4 warps each); group g drains accumulator stage g
+constexpr int kThreads = 128 + 128 * kEpiGroups;
 constexpr int kCap = 256;      // per-row candidate buffer (keys); power of two, >= 2 * MR_MAX_FUSED_TOPK
-constexpr int kChunk = 32;     // accumulator columns per tcgen05.ld
+constexpr int kChunk = 16;     // accumulator columns per tcgen05.ld
 constexpr int kAccStages = 2;
 constexpr int kABytes = kBlockM * kBlockK * 4;   // 16 KB: one of (hi, lo) of the query tile
 
@@ -43,9 +44,8 @@ template <int CG> struct Cfg {
     static constexpr int kBBytes = kBRows * kBlockK * 4;     // 32 KB (CG 1) / 16 KB (CG 2)
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr int kStages = CG == 1 ? 2 : 3;
-    static constexpr int kSortBytes = 4 * kCap * 8;          // one sort scratch per epilogue warp
     static constexpr int kBarBytes = 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kSortBytes + kBarBytes + 1024 /* alignment slack */;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024 /* alignment slack */;
 };
 
 struct Params {
@@ -57,9 +57,10 @@ struct Params {
     int QB;       // query blocks = ceil(Q / (128 * CG))
     int S;        // item splits
     int QG;       // query blocks per L2 group
-    u64* cand;    // grid * 128 * kCap keys
-    float* out_val;     // (S, Q, K)
-    int32_t* out_id;    // (S, Q, K)
+    u64* cand;    // grid * kEpiGroups * 128 * kCap keys
+    float* out_val;     // (S * kEpiGroups, Q, K)
+    int32_t* out_id;    // (S * kEpiGroups, Q, K)
+    long long* dbg;     // optional timestamps of block 0 (mr_score_topk_debug_buffer), else NULL
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------------
@@ -148,15 +149,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
             ::"r"(bar), "h"((uint16_t)3) : "memory");
     }
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -172,6 +170,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 template <int CG>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)((kBlockM * CG) >> 4) << 24);
+}
+
+// diagnostics: block 0 stamps clock64() per tile into dbg[role][tile][slot] (role 0 producer, 1 mma, 2 epilogue)
+constexpr int kDbgTiles = 64, kDbgSlots = 4;
+__device__ __forceinline__ void dbg_stamp(const Params& p, int role, uint32_t tile, int slot) {
+    if (p.dbg && blockIdx.x == 0 && tile < (uint32_t)kDbgTiles) p.dbg[(role * kDbgTiles + tile) * kDbgSlots + slot] = clock64();
 }
 
 // ---- static unit schedule (identical in every role) ---------------------------------------------------------------
@@ -192,27 +196,82 @@ __device__ __forceinline__ bool get_unit(const Params& p, int u, Unit& out) {
 }
 
 // ---- warp-cooperative compaction of one row's candidate buffer ----------------------------------------------------
-__device__ __forceinline__ void warp_sort_desc(u64* s, int n, int lane) {
-    for (int size = 2; size <= n; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = lane; i < (n >> 1); i += 32) {
-                const int a = 2 * i - (i & (stride - 1));
-                const int b = a + stride;
-                const bool desc = ((a & size) == 0);
-                const u64 x = s[a], y = s[b];
-                if ((x < y) == desc) { s[a] = y; s[b] = x; }
+// Bitonic sort (descending) of kCap = 256 keys held in registers, 8 per lane: element e = lane * 8 + r.
+// Strides 1, 2, 4 are register-to-register; strides >= 8 exchange with lane ^ (stride / 8) through shuffles.
+// Register indices are compile-time constants, but the stage loops are NOT unrolled: `size` and the lane stride
+// are run-time values, which keeps the routine at ~250 instructions instead of ~1500 (the epilogue has to stay
+// inside the instruction cache; a fully unrolled network plus an unrolled filter made every tile fetch its code
+// from L2 again and ran 3x slower).
+__device__ __forceinline__ void cmpx(u64& a, u64& b, bool desc) {
+    const bool gt = a > b;
+    const u64 hi = gt ? a : b, lo = gt ? b : a;
+    a = desc ? hi : lo;
+    b = desc ? lo : hi;
+}
+__device__ __forceinline__ void warp_sort256(u64 (&v)[8], int lane) {
+#pragma unroll 1
+    for (int size = 2; size <= kCap; size <<= 1) {
+        const bool desc_lane = ((lane * 8) & size) == 0;     // valid for size >= 8 (direction depends on the lane only)
+#pragma unroll 1
+        for (int lstride = size >> 4; lstride > 0; lstride >>= 1) {   // strides size/2 .. 8, in lanes
+            const bool take_max = ((lane & lstride) == 0) == desc_lane;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const u64 other = __shfl_xor_sync(0xffffffffu, v[r], lstride);
+                v[r] = ((v[r] > other) == take_max) ? v[r] : other;
             }
-            __syncwarp();
+        }
+#pragma unroll
+        for (int stride = 4; stride >= 1; stride >>= 1) {
+            if (stride < size) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if ((r & stride) == 0) cmpx(v[r], v[r | stride], (((lane * 8) + r) & size) == 0);
+            }
         }
     }
 }
-// Loads `n` keys of a row into the warp's scratch, sorts them descending; returns with s[] sorted (zero padded).
-__device__ __forceinline__ void warp_load_sort(u64* s, const u64* gbuf, int n, int lane) {
-    int np = 32;
-    while (np < n) np <<= 1;
-    for (int i = lane; i < np; i += 32) s[i] = (i < n) ? gbuf[i] : 0ull;
-    __syncwarp();
-    warp_sort_desc(s, np, lane);
+// Row buffer (n <= kCap keys in global memory) -> registers (zero padded), element e = lane * 8 + r, sorted.
+__device__ __forceinline__ void warp_load_sort(u64 (&v)[8], const u64* gbuf, int n, int lane) {
+    const uint4* g4 = reinterpret_cast<const uint4*>(gbuf + lane * 8);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        uint4 t = make_uint4(0, 0, 0, 0);
+        if (lane * 8 + 2 * h < n) t = g4[h];
+        v[2 * h] = ((u64)t.y << 32) | t.x;
+        v[2 * h + 1] = (lane * 8 + 2 * h + 1 < n) ? (((u64)t.w << 32) | t.z) : 0ull;
+    }
+    warp_sort256(v, lane);
+}
+// the first `keep` sorted keys back to the row buffer
+__device__ __forceinline__ void warp_store_keys(u64* gbuf, const u64 (&v)[8], int keep, int lane) {
+    uint4* o4 = reinterpret_cast<uint4*>(gbuf + lane * 8);
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+        if (lane * 8 + 2 * h < keep)
+            o4[h] = make_uint4((uint32_t)v[2 * h], (uint32_t)(v[2 * h] >> 32), (uint32_t)v[2 * h + 1],
+                               (uint32_t)(v[2 * h + 1] >> 32));
+}
+// sorted element e (warp-uniform index) broadcast to every lane
+__device__ __forceinline__ u64 warp_pick(const u64 (&v)[8], int e) {
+    u64 x = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if (r == (e & 7)) x = v[r];
+    return __shfl_sync(0xffffffffu, x, e >> 3);
+}
+
+// sorted registers -> one (val, id) list of K entries; keys are zero beyond the row's candidates
+__device__ __forceinline__ void warp_write_list(const Params& p, size_t o, const u64 (&v)[8], int K, int lane) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = lane * 8 + r;
+        if (i < K) {
+            const u64 key = v[r];
+            p.out_id[o + i] = key ? (int32_t)key_id(key) : -1;
+            p.out_val[o + i] = key ? key_score(key) : -INFINITY;
+        }
+    }
 }
 
 template <int CG>
@@ -224,8 +283,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* stages = smem;
-    u64* sort_scratch = reinterpret_cast<u64*>(smem + C::kStages * C::kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kSortBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
     // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * C::kStages;
@@ -283,9 +341,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                 const int qrow = (u.qb * CG + (int)rank) * kBlockM;
                 for (int t = u.t0; t < u.t1; ++t) {
                     const int nrow = t * kBlockN + (int)rank * C::kBRows;
+                    dbg_stamp(p, 0, (uint32_t)(t - u.t0), 0);
+#pragma unroll 1
                     for (int kb = 0; kb < p.KB; ++kb, ++kiter) {
                         const int s = kiter % C::kStages;
                         mbar_wait(bar_empty + 8 * s, ((kiter / C::kStages) & 1) ^ 1, 1);
+                        if (kb == 0) dbg_stamp(p, 0, (uint32_t)(t - u.t0), 1);
+                        if (kb == p.KB - 1) dbg_stamp(p, 0, (uint32_t)(t - u.t0), 2);
                         const uint32_t full = bar_full + 8 * s;
                         const uint32_t sbase = smem_u32(stages + (size_t)s * C::kStageBytes);
                         const uint32_t bytes = (x3 ? 2u : 1u) * (uint32_t)(kABytes + C::kBBytes);
@@ -311,9 +373,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
             for (int ui = cluster_id; get_unit(p, ui, u); ui += num_clusters) {
                 for (int t = u.t0; t < u.t1; ++t, ++it) {
                     const uint32_t acc = it & 1;
+                    if (lane == 0) dbg_stamp(p, 1, it, 0);
                     mbar_wait(bar_tempty + 8 * acc, ((it >> 1) & 1) ^ 1, 2);
                     tc_fence_after();
+                    if (lane == 0) dbg_stamp(p, 1, it, 1);
                     const uint32_t d_tmem = tmem_base + acc * kBlockN;
+#pragma unroll 1
                     for (int kb = 0; kb < p.KB; ++kb, ++kiter) {
                         const int s = kiter % C::kStages;
                         mbar_wait(bar_full + 8 * s, (kiter / C::kStages) & 1, 3);
@@ -337,6 +402,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                             }
                             umma_commit<CG>(bar_empty + 8 * s);                      // stage consumed
                             if (kb == p.KB - 1) umma_commit<CG>(bar_tfull + 8 * acc);  // accumulator complete
+                            if (kb == 0) dbg_stamp(p, 1, it, 2);
+                            if (kb == p.KB - 1) dbg_stamp(p, 1, it, 3);
                         }
                         __syncwarp();
                     }
@@ -345,11 +412,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> threshold filter -> per-row candidate buffers -> sorted top-K =====
-        const int ew = warp - 4;
+        // Group g = (warp - 4) / 4 owns accumulator stage g, i.e. every second tile; warp ew of a group reads TMEM
+        // lanes [32 ew, 32 ew + 32).  Each (group, row) keeps its own candidate buffer and threshold; the lists of
+        // the two groups are merged with those of the other splits by mr_topk_merge.
+        const int grp = (warp - 4) >> 2;
+        const int ew = (warp - 4) & 3;
         const int row = ew * 32 + lane;
-        u64* s_sort = sort_scratch + ew * kCap;
-        u64* my_buf = p.cand + ((size_t)blockIdx.x * kBlockM + row) * kCap;
-        const u64* warp_buf = p.cand + ((size_t)blockIdx.x * kBlockM + ew * 32) * kCap;
+        u64* warp_buf = p.cand + (((size_t)blockIdx.x * kEpiGroups + grp) * kBlockM + ew * 32) * kCap;
+        u64* my_buf = warp_buf + (size_t)lane * kCap;
         const int K = p.K;
         uint32_t it = 0;
         Unit u;
@@ -357,43 +427,60 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
             const int64_t q = ((int64_t)u.qb * CG + rank) * kBlockM + row;
             const bool active = q < p.Q;
             int cnt = 0;
-            uint32_t thr = 0;  // score key of the row's K-th best so far (0: list not full, everything passes)
+            uint32_t thr = 0;                        // score key of the row's K-th best so far (0: list not full)
+            float thr_f = __int_as_float(0x7FC00000);  // same threshold as a float; NaN = "everything passes"
             for (int t = u.t0; t < u.t1; ++t, ++it) {
+                if (kEpiGroups > 1 && (int)(it & 1) != grp) continue;   // two groups: group g drains stage g
                 const uint32_t acc = it & 1;
+                if (threadIdx.x == 128) dbg_stamp(p, 2, it, 0);
                 mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1, 4);
                 tc_fence_after();
+                if (threadIdx.x == 128) dbg_stamp(p, 2, it, 1);
                 const int64_t n0 = (int64_t)t * kBlockN;
                 const int nvalid = (int)((p.N - n0) < kBlockN ? (p.N - n0) : kBlockN);
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kBlockN;
+#pragma unroll 1
                 for (int c = 0; c < nvalid; c += kChunk) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c, r);
+                    uint32_t v[kChunk];
+                    tmem_ld16(taddr + c, v);
                     tmem_ld_wait();
                     if (active) {
                         const uint32_t id0 = (uint32_t)(p.id_base + (int32_t)(n0 + c));
 #pragma unroll
                         for (int j = 0; j < kChunk; ++j) {
-                            const uint32_t key = score_key(__uint_as_float(r[j]));
-                            if (key > thr && c + j < nvalid) my_buf[cnt++] = ((u64)key << 32) | (u64)(0xFFFFFFFFu - (id0 + j));
+                            const float f = __uint_as_float(v[j]);
+                            // cheap superset test first: key(f) > thr implies f > thr_f or f is NaN
+                            if (!(f <= thr_f)) {
+                                const uint32_t key = score_key(f);
+                                if (key > thr && c + j < nvalid)
+                                    my_buf[cnt++] = ((u64)key << 32) | (u64)(0xFFFFFFFFu - (id0 + j));
+                            }
                         }
                     }
                     // rows that could overflow on the next chunk are cut back to their best K
                     unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - kChunk);
+#pragma unroll 1
                     while (need) {
                         const int L = __ffs(need) - 1;
                         need &= need - 1;
                         const int n = __shfl_sync(0xffffffffu, cnt, L);
-                        u64* gbuf = const_cast<u64*>(warp_buf) + (size_t)L * kCap;
-                        __syncwarp();
-                        warp_load_sort(s_sort, gbuf, n, lane);
+                        u64* gbuf = warp_buf + (size_t)L * kCap;
+                        __syncwarp();   // lane L's appends are visible to the whole warp
+                        u64 keys[8];
+                        warp_load_sort(keys, gbuf, n, lane);
                         const int keep = n < K ? n : K;
-                        for (int i = lane; i < keep; i += 32) gbuf[i] = s_sort[i];
-                        const uint32_t nthr = n >= K ? (uint32_t)(s_sort[K - 1] >> 32) : 0u;
+                        warp_store_keys(gbuf, keys, keep, lane);
+                        const uint32_t nthr = n >= K ? (uint32_t)(warp_pick(keys, K - 1) >> 32) : 0u;
                         __syncwarp();
-                        if (lane == L) { cnt = keep; thr = nthr; }
+                        if (lane == L) {
+                            cnt = keep;
+                            thr = nthr;
+                            thr_f = nthr ? key_score((u64)nthr << 32) : __int_as_float(0x7FC00000);
+                        }
                     }
                 }
                 // accumulator stage drained: hand it back to the MMA issuer
+                if (threadIdx.x == 128) dbg_stamp(p, 2, it, 2);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -401,20 +488,17 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                     else mbar_arrive_remote(bar_tempty + 8 * acc, 0);
                 }
             }
-            // unit done: final sort of every row, one (val, id) list per (split, q)
+            // unit done: final sort of every row, one (val, id) list per (split, group, q)
+#pragma unroll 1
             for (int L = 0; L < 32; ++L) {
-                const int n = __shfl_sync(0xffffffffu, cnt, L);
                 const int64_t qL = ((int64_t)u.qb * CG + rank) * kBlockM + ew * 32 + L;
                 if (qL >= p.Q) break;  // warp-uniform: rows are ascending
-                u64* gbuf = const_cast<u64*>(warp_buf) + (size_t)L * kCap;
+                const int n = __shfl_sync(0xffffffffu, cnt, L);
                 __syncwarp();
-                warp_load_sort(s_sort, gbuf, n, lane);
-                const size_t o = ((size_t)u.split * p.Q + qL) * K;
-                for (int i = lane; i < K; i += 32) {
-                    const u64 key = (i < n) ? s_sort[i] : 0ull;
-                    p.out_id[o + i] = key ? (int32_t)key_id(key) : -1;
-                    p.out_val[o + i] = key ? key_score(key) : -INFINITY;
-                }
+                u64 keys[8];
+                warp_load_sort(keys, warp_buf + (size_t)L * kCap, n, lane);
+                const size_t list = (size_t)u.split * kEpiGroups + grp;
+                warp_write_list(p, (list * p.Q + qL) * K, keys, K, lane);
                 __syncwarp();
             }
         }
@@ -476,7 +560,7 @@ static Plan make_plan(int64_t Q, int64_t N, int K) {
     pl.QG = env_int("MR_SCORE_QGROUP", 16);
     if (pl.QG < 1) pl.QG = 1;
     // item splits: enough units to fill the machine evenly, few enough that a unit amortises its top-K warm-up
-    int smax = 8192 / (K > 0 ? K : 1);        // mr_topk_merge takes at most 8192 candidates per row
+    int smax = 8192 / (kEpiGroups * (K > 0 ? K : 1));  // mr_topk_merge takes at most 8192 candidates per row
     if (smax > pl.T) smax = pl.T;
     if (smax < 1) smax = 1;
     int s = env_int("MR_SCORE_SPLITS", 0);
@@ -499,8 +583,8 @@ static Plan make_plan(int64_t Q, int64_t N, int K) {
     const int64_t units = (int64_t)pl.QB * pl.S;
     pl.grid = (int)((units < clusters ? units : clusters) * pl.cg);
     if (pl.grid < pl.cg) pl.grid = pl.cg;
-    pl.cand_bytes = (int64_t)sms * kBlockM * kCap * 8;
-    pl.part_bytes = pl.S > 1 ? (int64_t)pl.S * Q * K * 8 : 0;
+    pl.cand_bytes = (int64_t)sms * kEpiGroups * kBlockM * kCap * 8;
+    pl.part_bytes = (int64_t)pl.S * kEpiGroups * Q * K * 8;
     return pl;
 }
 
@@ -529,6 +613,15 @@ static int launch(const Plan& pl, const CUtensorMap& muh, const CUtensorMap& mul
 
 }  // namespace st
 }  // namespace mr
+
+static thread_local long long* g_score_dbg = nullptr;
+extern "C" int mr_score_topk_debug_buffer(void* dev_buf, int64_t bytes) {
+    using namespace mr;
+    MR_REQUIRE(dev_buf == nullptr || bytes >= (int64_t)(3 * st::kDbgTiles * st::kDbgSlots * 8),
+               "mr_score_topk_debug_buffer: need %d bytes", 3 * st::kDbgTiles * st::kDbgSlots * 8);
+    g_score_dbg = reinterpret_cast<long long*>(dev_buf);
+    return MR_OK;
+}
 
 extern "C" int64_t mr_score_topk_workspace_bytes(int64_t Q, int64_t N, int E, int K) {
     using namespace mr;
@@ -575,10 +668,11 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     p.KB = (E + st::kBlockK - 1) / st::kBlockK;
     p.T = pl.T; p.QB = pl.QB; p.S = pl.S; p.QG = pl.QG;
     p.cand = reinterpret_cast<mr::u64*>(w);
+    p.dbg = g_score_dbg;
     float* part_val = reinterpret_cast<float*>(w + pl.cand_bytes);
     int32_t* part_id = reinterpret_cast<int32_t*>(w + pl.cand_bytes + pl.part_bytes / 2);
-    p.out_val = pl.S > 1 ? part_val : out_val;
-    p.out_id = pl.S > 1 ? part_id : out_id;
+    p.out_val = part_val;
+    p.out_id = part_id;
 
     CUtensorMap muh, mul, mih, mil;
     const int brows = st::kBlockN / pl.cg;
@@ -589,6 +683,5 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
 
     int rc = pl.cg == 1 ? st::launch<1>(pl, muh, mul, mih, mil, p, s) : st::launch<2>(pl, muh, mul, mih, mil, p, s);
     if (rc != MR_OK) return rc;
-    if (pl.S > 1) return mr_topk_merge(part_val, part_id, pl.S, Q, K, K, out_val, out_id, stream);
-    return MR_OK;
+    return mr_topk_merge(part_val, part_id, pl.S * st::kEpiGroups, Q, K, K, out_val, out_id, stream);
 }

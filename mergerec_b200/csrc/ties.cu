@@ -149,10 +149,14 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 
     uint32_t ge[K];  // per-thread count of magnitudes >= lo_mag (fits 32 bits: d < 2^32)
     float wreg[K];
+    int lom[K];      // bracket bounds in registers: the edge call may touch shared memory, so values read through
+    uint32_t span[K];  // `sm` would be reloaded from shared memory for every element
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         ge[k] = 0;
         wreg[k] = W ? w[k] : 1.0f;
+        lom[k] = sm.lom[k];
+        span[k] = (uint32_t)sm.span[k];
     }
 
     const int64_t nq_full = d >> 2;                        // quads of 4 consecutive elements
@@ -166,9 +170,9 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
         float u_ = __fsub_rn((X_), (B_));                                                      \
         if (W) u_ = __fmul_rn(u_, wreg[K_]);                                                   \
         const uint32_t mag_ = __float_as_uint(u_) & 0x7FFFFFFFu;                               \
-        const int t_ = (int)mag_ - sm.lom[K_];                                                 \
+        const int t_ = (int)mag_ - lom[K_];                                                    \
         ge[K_] += (t_ >= 0) ? 1u : 0u;                                                         \
-        if ((uint32_t)t_ <= (uint32_t)sm.span[K_])                                             \
+        if ((uint32_t)t_ <= span[K_])                                                          \
             ties_pass_edge<K, COLLECT>(smem_raw, mag_, (J_), (K_), pc.cand_keys, pc.cand_cap); \
     } while (0)
 
@@ -375,10 +379,33 @@ struct BuildArgs {
     int P;
 };
 
-template <int K, int MODE>
-__device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_t j, bool tail, const u64 (&cut)[K],
-                                            const float* __restrict__ wk, float (&res)[K], uint32_t& trim_bits,
-                                            uint32_t& elect_bits) {
+// x / c for an integer count c in [2, 16], bit-identical to IEEE division (ties.py:68, `div_`): one reciprocal
+// multiply plus a Markstein FMA correction.  Exhaustively checked against x / c for every fp32 mantissa and
+// c = 2..16 (.scratch/divfast.c in the build log; DESIGN.md "TIES build").  The correction needs the quotient and
+// the residual to stay normal, so magnitudes outside [2^-100, 2^100] (never produced by real task vectors)
+// take the IEEE divide.
+__device__ __forceinline__ float div_by_count_fast(float x, float fc, float inv) {
+    const float q0 = __fmul_rn(x, inv);
+    const float r = __fmaf_rn(-q0, fc, x);
+    return __fmaf_rn(r, inv, q0);
+}
+// non-zero and exponent outside [27, 227]
+__device__ __forceinline__ bool div_needs_ieee(float x) {
+    const uint32_t e = (__float_as_uint(x) >> 23) & 0xFFu;
+    return x != 0.0f && (e - 27u) > 200u;
+}
+template <int K>
+__device__ __noinline__ void div_column_ieee(float (&res)[K], float fc) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) res[k] = __fdiv_rn(res[k], fc);
+}
+
+// One flat column: trim, sign election, disjoint mean (or the trimmed sum for merge_ties).
+// TAIL = false: the column lies in the sequential part of torch.sum(dim=0) (every column when K <= 4).
+template <int K, int MODE, bool TAIL>
+__device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_t j, const uint32_t (&cut_mag)[K],
+                                            const uint32_t (&cut_lo)[K], const float* __restrict__ wk, float (&res)[K],
+                                            uint32_t& trim_bits, uint32_t& elect_bits) {
     float s[K];
     trim_bits = 0;
     elect_bits = 0;
@@ -388,41 +415,49 @@ __device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_
         float u = __fsub_rn(x[k], b);
         if (MODE == TIES_MODE_TRIMSUM) u = __fmul_rn(u, wk[k]);
         const uint32_t mag = __float_as_uint(u) & 0x7FFFFFFFu;
-        const uint32_t cm = (uint32_t)(cut[k] >> 32), cl = (uint32_t)cut[k];
-        const bool keep = (mag > cm) || (mag == cm && jl >= cl);
+        const bool keep = (mag > cut_mag[k]) || (mag == cut_mag[k] && jl >= cut_lo[k]);
         s[k] = keep ? u : 0.0f;
         trim_bits |= (keep ? 1u : 0u) << k;
     }
     if constexpr (MODE == TIES_MODE_TRIMSUM) {
-        res[0] = __fadd_rn(b, torch_sum_dim0<K>(s, tail));   // ties.py:81-83
+        res[0] = __fadd_rn(b, torch_sum_dim0<K>(s, TAIL));   // ties.py:81-83
     } else {
-    float pp[K], nn[K];
+        float pp[K], nn[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        pp[k] = s[k] > 0.0f ? s[k] : 0.0f;   // ties.py:35
-        nn[k] = s[k] < 0.0f ? s[k] : 0.0f;   // ties.py:36
-    }
-    const float pos = torch_sum_dim0<K>(pp, tail);
-    const float neg = torch_sum_dim0<K>(nn, tail);
-    bool plus;
-    if (pos != 0.0f && neg != 0.0f) {
-        plus = fabsf(pos) >= fabsf(neg);      // ties.py:41-45
-    } else {
-        const float t = __fadd_rn(pos, neg);  // ties.py:47-48; sign 0 -> +1 (ties.py:50); NaN -> sign NaN -> "> 0" false
-        plus = !(t < 0.0f) && !(t != t);
-    }
-    int cnt = 0;
+        for (int k = 0; k < K; ++k) {
+            pp[k] = s[k] > 0.0f ? s[k] : 0.0f;   // ties.py:35 (torch.where: -0.0 and NaN become +0.0)
+            nn[k] = s[k] < 0.0f ? s[k] : 0.0f;   // ties.py:36
+        }
+        const float pos = torch_sum_dim0<K>(pp, TAIL);
+        const float neg = torch_sum_dim0<K>(nn, TAIL);
+        bool plus;
+        if (pos != 0.0f && neg != 0.0f) {
+            plus = fabsf(pos) >= fabsf(neg);      // ties.py:41-45
+        } else {
+            const float t = __fadd_rn(pos, neg);  // ties.py:47-48; sign 0 -> +1 (ties.py:50)
+            plus = !(t < 0.0f) && !(t != t);
+        }
+        int cnt = 0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        res[k] = plus ? pp[k] : nn[k];        // ties.py:61-65
-        cnt += (res[k] != 0.0f) ? 1 : 0;
-        elect_bits |= ((res[k] != 0.0f) ? 1u : 0u) << k;
-    }
-    if (cnt > 1) {                             // ties.py:68-70 (cnt == 0: all zeros; cnt == 1: x / 1)
-        const float fc = (float)cnt;
+        for (int k = 0; k < K; ++k) {
+            res[k] = plus ? pp[k] : nn[k];        // ties.py:61-65
+            const bool nz = res[k] != 0.0f;
+            cnt += nz ? 1 : 0;
+            elect_bits |= (nz ? 1u : 0u) << k;
+        }
+        if (cnt > 1) {                             // ties.py:68-70 (cnt == 0: all zeros; cnt == 1: x / 1)
+            const float fc = (float)cnt;
+            const float inv = __frcp_rn(fc);
+            bool odd = false;
 #pragma unroll
-        for (int k = 0; k < K; ++k) res[k] = __fdiv_rn(res[k], fc);
-    }
+            for (int k = 0; k < K; ++k) odd |= div_needs_ieee(res[k]);
+            if (odd) {
+                div_column_ieee<K>(res, fc);
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) res[k] = div_by_count_fast(res[k], fc, inv);
+            }
+        }
     }
 }
 
@@ -431,11 +466,13 @@ __global__ void __launch_bounds__(kTiesThreads)
 ties_build_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const u64* __restrict__ cut_dev,
                   BuildArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 cut[K];
+    uint32_t cut_mag[K], cut_lo[K];
     float wk[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        cut[k] = cut_dev[k];
+        const u64 c = cut_dev[k];
+        cut_mag[k] = (uint32_t)(c >> 32);
+        cut_lo[k] = (uint32_t)c;
         wk[k] = (MODE == TIES_MODE_TRIMSUM) ? a.w[k] : 0.0f;
     }
     // FUSED_MERGE: lambda rows and the block table in shared memory
@@ -483,12 +520,17 @@ ties_build_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, 
         }
         float res[4][K];
         uint32_t tb[4], eb[4];
+        // the interleaved torch.sum order only exists for K >= 5 and only on the last d mod 32 columns
+        const bool tail_quad = (K >= 5) && (j0 + 3 >= tail0);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             float x[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) x[k] = xs[k][c];
-            ties_column<K, MODE>(x, bx[c], j0 + c, (K >= 5) && (j0 + c >= tail0), cut, wk, res[c], tb[c], eb[c]);
+            if (tail_quad && j0 + c >= tail0)
+                ties_column<K, MODE, true>(x, bx[c], j0 + c, cut_mag, cut_lo, wk, res[c], tb[c], eb[c]);
+            else
+                ties_column<K, MODE, false>(x, bx[c], j0 + c, cut_mag, cut_lo, wk, res[c], tb[c], eb[c]);
         }
         if (MODE == TIES_MODE_VECTORS) {
 #pragma unroll

@@ -106,6 +106,7 @@ def exchange_topk(local_vals: torch.Tensor, local_ids: torch.Tensor, k: int, gro
     Q = local_vals.shape[0]
     all_v = torch.empty((world, Q, k), dtype=local_vals.dtype, device=local_vals.device)
     all_i = torch.empty((world, Q, k), dtype=local_ids.dtype, device=local_ids.device)
-    dist.all_gather_into_tensor(all_v, local_vals.contiguous(), group=group)
-    dist.all_gather_into_tensor(all_i, local_ids.contiguous(), group=group)
+    # concatenated form (world * Q, k): accepted by both the nccl and the gloo backends
+    dist.all_gather_into_tensor(all_v.view(world * Q, k), local_vals.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i.view(world * Q, k), local_ids.contiguous(), group=group)
     return merge(all_v, all_i, k)

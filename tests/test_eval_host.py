@@ -91,6 +91,8 @@ def _exchange_worker(rank, world, port, q):
         res = {m.name: m.from_ranks(ranks) for m in ev._metrics}
         ok = ok and res == orc.evaluate_ids(fi, labels, ["NDCG", "RECALL"], [5, 25])
         q.put((rank, bool(ok)))
+    except Exception as e:  # noqa: BLE001 -- report instead of leaving the parent to time out
+        q.put((rank, repr(e)))
     finally:
         dist.destroy_process_group()
 
