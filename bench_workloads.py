@@ -218,6 +218,17 @@ class TiesCfg2(LambdaMergeK8):
         def build():
             T._build(self.base, self.models, cut, _lib.MR_TIES_VECTORS, out=self.That, ldo=self.That.stride(0))
 
+        # lambda-gradient reduction (A5; the backward kernel of BASELINE config 3) against the same K x d rows
+        from mergerec_b200.merger.weight_learning.module._base import _lambda_grad
+        grad = torch.randn(self.d, device=self.device)
+        seg_off, seg_len = self.layout.device_segments(self.device)
+        grads = [grad[o:o + n] for o, n in zip(seg_off.tolist(), seg_len.tolist())]
+        lgrad = lambda: _lambda_grad(grads, self.layout, self.That, self.seg_group, int(self.w.shape[0]))  # noqa: E731
+        lgrad()
+        ms_lgrad = event_time_ms(lgrad, 5)
+        lgrad_bytes = (K + 1) * d * 4
+        del grad, grads
+
         ms_build = event_time_ms(build, 10)
         ms_select = event_time_ms(select, 10)
         ms_merge = event_time_ms(self._merge_only, 10)
@@ -230,6 +241,7 @@ class TiesCfg2(LambdaMergeK8):
                 "algorithmic_bytes_per_launch": self.bytes_build,
                 "other_kernels": {
                     "ties_select (sample + 1 full pass + finish)": {"ms": ms_select, "GB/s": sel_bytes / GB / (ms_select * 1e-3), "bytes": sel_bytes},
+                    "lambda-gradient reduction (lambda_grad_kernel, incl. host pointer-table upload)": {"ms": ms_lgrad, "GB/s": lgrad_bytes / GB / (ms_lgrad * 1e-3), "bytes": lgrad_bytes},
                     "lambda merge (merge_kernel)": {"ms": ms_merge, "GB/s": self.bytes_merge / GB / (ms_merge * 1e-3), "bytes": self.bytes_merge},
                     "fused select + build + merge without materialising That (merge_ties_lambda)": {"ms": ms_fused, "GB/s": self.bytes_merge / GB / (ms_fused * 1e-3), "bytes": self.bytes_merge},
                 }}

@@ -208,7 +208,9 @@ __device__ __forceinline__ void cmpx(u64& a, u64& b, bool desc) {
     a = desc ? hi : lo;
     b = desc ? lo : hi;
 }
-__device__ __forceinline__ void warp_sort256(u64 (&v)[8], int lane) {
+// Two rows per call: the two networks are independent, which doubles the instruction-level parallelism of what is
+// otherwise a chain of dependent compare-exchanges run by one warp alone on its scheduler.
+__device__ __forceinline__ void warp_sort256x2(u64 (&a)[8], u64 (&b)[8], int lane) {
 #pragma unroll 1
     for (int size = 2; size <= kCap; size <<= 1) {
         const bool desc_lane = ((lane * 8) & size) == 0;     // valid for size >= 8 (direction depends on the lane only)
@@ -217,8 +219,10 @@ __device__ __forceinline__ void warp_sort256(u64 (&v)[8], int lane) {
             const bool take_max = ((lane & lstride) == 0) == desc_lane;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const u64 other = __shfl_xor_sync(0xffffffffu, v[r], lstride);
-                v[r] = ((v[r] > other) == take_max) ? v[r] : other;
+                const u64 oa = __shfl_xor_sync(0xffffffffu, a[r], lstride);
+                const u64 ob = __shfl_xor_sync(0xffffffffu, b[r], lstride);
+                a[r] = ((a[r] > oa) == take_max) ? a[r] : oa;
+                b[r] = ((b[r] > ob) == take_max) ? b[r] : ob;
             }
         }
 #pragma unroll
@@ -226,13 +230,17 @@ __device__ __forceinline__ void warp_sort256(u64 (&v)[8], int lane) {
             if (stride < size) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
-                    if ((r & stride) == 0) cmpx(v[r], v[r | stride], (((lane * 8) + r) & size) == 0);
+                    if ((r & stride) == 0) {
+                        const bool desc = (((lane * 8) + r) & size) == 0;
+                        cmpx(a[r], a[r | stride], desc);
+                        cmpx(b[r], b[r | stride], desc);
+                    }
             }
         }
     }
 }
-// Row buffer (n <= kCap keys in global memory) -> registers (zero padded), element e = lane * 8 + r, sorted.
-__device__ __forceinline__ void warp_load_sort(u64 (&v)[8], const u64* gbuf, int n, int lane) {
+// Row buffer (n <= kCap keys in global memory) -> registers (zero padded), element e = lane * 8 + r.
+__device__ __forceinline__ void warp_load_keys(u64 (&v)[8], const u64* gbuf, int n, int lane) {
     const uint4* g4 = reinterpret_cast<const uint4*>(gbuf + lane * 8);
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
@@ -241,7 +249,6 @@ __device__ __forceinline__ void warp_load_sort(u64 (&v)[8], const u64* gbuf, int
         v[2 * h] = ((u64)t.y << 32) | t.x;
         v[2 * h + 1] = (lane * 8 + 2 * h + 1 < n) ? (((u64)t.w << 32) | t.z) : 0ull;
     }
-    warp_sort256(v, lane);
 }
 // the first `keep` sorted keys back to the row buffer
 __device__ __forceinline__ void warp_store_keys(u64* gbuf, const u64 (&v)[8], int keep, int lane) {
@@ -439,45 +446,74 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                 const int64_t n0 = (int64_t)t * kBlockN;
                 const int nvalid = (int)((p.N - n0) < kBlockN ? (p.N - n0) : kBlockN);
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kBlockN;
+                long long t_ld = 0, t_flt = 0, t_cmp = 0;
+                int n_cmp = 0;
 #pragma unroll 1
                 for (int c = 0; c < nvalid; c += kChunk) {
                     uint32_t v[kChunk];
+                    const long long c0 = p.dbg ? clock64() : 0;
                     tmem_ld16(taddr + c, v);
                     tmem_ld_wait();
-                    if (active) {
-                        const uint32_t id0 = (uint32_t)(p.id_base + (int32_t)(n0 + c));
+                    const long long c1 = p.dbg ? clock64() : 0;
+                    // Phase 1, branch-free: bit j of m = "column c + j may enter the row's list" (cheap superset test:
+                    // key(f) > thr implies f > thr_f or f is NaN).  No per-element branches, so the 16 tests overlap.
+                    uint32_t m = 0;
 #pragma unroll
-                        for (int j = 0; j < kChunk; ++j) {
-                            const float f = __uint_as_float(v[j]);
-                            // cheap superset test first: key(f) > thr implies f > thr_f or f is NaN
-                            if (!(f <= thr_f)) {
-                                const uint32_t key = score_key(f);
-                                if (key > thr && c + j < nvalid)
-                                    my_buf[cnt++] = ((u64)key << 32) | (u64)(0xFFFFFFFFu - (id0 + j));
-                            }
-                        }
+                    for (int j = 0; j < kChunk; ++j) m |= (!(__uint_as_float(v[j]) <= thr_f)) ? (1u << j) : 0u;
+                    if (nvalid - c < kChunk) m &= (1u << (nvalid - c)) - 1u;
+                    if (!active) m = 0;
+                    // Phase 2: each lane walks its own set bits (usually none), exact key test, append.
+                    const uint32_t id0 = (uint32_t)(p.id_base + (int32_t)(n0 + c));
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        uint32_t bits = v[0];
+#pragma unroll
+                        for (int jj = 1; jj < kChunk; ++jj) bits = (j == jj) ? v[jj] : bits;
+                        const uint32_t key = score_key(__uint_as_float(bits));
+                        if (key > thr) my_buf[cnt++] = ((u64)key << 32) | (u64)(0xFFFFFFFFu - (id0 + (uint32_t)j));
                     }
-                    // rows that could overflow on the next chunk are cut back to their best K
+                    // rows that could overflow on the next chunk are cut back to their best K, two rows per sort
                     unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - kChunk);
+                    const long long c2 = p.dbg ? clock64() : 0;
+                    n_cmp += __popc(need);
 #pragma unroll 1
                     while (need) {
-                        const int L = __ffs(need) - 1;
+                        const int L0 = __ffs(need) - 1;
                         need &= need - 1;
-                        const int n = __shfl_sync(0xffffffffu, cnt, L);
-                        u64* gbuf = warp_buf + (size_t)L * kCap;
-                        __syncwarp();   // lane L's appends are visible to the whole warp
-                        u64 keys[8];
-                        warp_load_sort(keys, gbuf, n, lane);
-                        const int keep = n < K ? n : K;
-                        warp_store_keys(gbuf, keys, keep, lane);
-                        const uint32_t nthr = n >= K ? (uint32_t)(warp_pick(keys, K - 1) >> 32) : 0u;
+                        const int L1 = need ? __ffs(need) - 1 : L0;
+                        if (need) need &= need - 1;
+                        const int na = __shfl_sync(0xffffffffu, cnt, L0), nb = __shfl_sync(0xffffffffu, cnt, L1);
+                        u64* ga = warp_buf + (size_t)L0 * kCap;
+                        u64* gb = warp_buf + (size_t)L1 * kCap;
+                        __syncwarp();   // the appends of lanes L0 / L1 are visible to the whole warp
+                        u64 ka[8], kb[8];
+                        warp_load_keys(ka, ga, na, lane);
+                        warp_load_keys(kb, gb, nb, lane);
+                        warp_sort256x2(ka, kb, lane);
+                        const int keepa = na < K ? na : K, keepb = nb < K ? nb : K;
+                        warp_store_keys(ga, ka, keepa, lane);
+                        if (L1 != L0) warp_store_keys(gb, kb, keepb, lane);
+                        const uint32_t ta = na >= K ? (uint32_t)(warp_pick(ka, K - 1) >> 32) : 0u;
+                        const uint32_t tb = nb >= K ? (uint32_t)(warp_pick(kb, K - 1) >> 32) : 0u;
                         __syncwarp();
-                        if (lane == L) {
-                            cnt = keep;
-                            thr = nthr;
-                            thr_f = nthr ? key_score((u64)nthr << 32) : __int_as_float(0x7FC00000);
+                        if (lane == L0 || lane == L1) {
+                            const bool first = lane == L0;
+                            cnt = first ? keepa : keepb;
+                            thr = first ? ta : tb;
+                            thr_f = thr ? key_score((u64)thr << 32) : __int_as_float(0x7FC00000);
                         }
                     }
+                    if (p.dbg) {
+                        const long long c3 = clock64();
+                        t_ld += c1 - c0; t_flt += c2 - c1; t_cmp += c3 - c2;
+                    }
+                }
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128 && it < (uint32_t)kDbgTiles) {
+                    p.dbg[(3 * kDbgTiles + it) * kDbgSlots + 0] = t_ld;
+                    p.dbg[(3 * kDbgTiles + it) * kDbgSlots + 1] = t_flt;
+                    p.dbg[(3 * kDbgTiles + it) * kDbgSlots + 2] = t_cmp;
+                    p.dbg[(3 * kDbgTiles + it) * kDbgSlots + 3] = n_cmp;
                 }
                 // accumulator stage drained: hand it back to the MMA issuer
                 if (threadIdx.x == 128) dbg_stamp(p, 2, it, 2);
@@ -488,17 +524,20 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                     else mbar_arrive_remote(bar_tempty + 8 * acc, 0);
                 }
             }
-            // unit done: final sort of every row, one (val, id) list per (split, group, q)
+            // unit done: final sort of every row (two per call), one (val, id) list per (split, group, q)
 #pragma unroll 1
-            for (int L = 0; L < 32; ++L) {
+            for (int L = 0; L < 32; L += 2) {
                 const int64_t qL = ((int64_t)u.qb * CG + rank) * kBlockM + ew * 32 + L;
                 if (qL >= p.Q) break;  // warp-uniform: rows are ascending
-                const int n = __shfl_sync(0xffffffffu, cnt, L);
+                const int na = __shfl_sync(0xffffffffu, cnt, L), nb = __shfl_sync(0xffffffffu, cnt, L + 1);
                 __syncwarp();
-                u64 keys[8];
-                warp_load_sort(keys, warp_buf + (size_t)L * kCap, n, lane);
+                u64 ka[8], kb[8];
+                warp_load_keys(ka, warp_buf + (size_t)L * kCap, na, lane);
+                warp_load_keys(kb, warp_buf + (size_t)(L + 1) * kCap, nb, lane);
+                warp_sort256x2(ka, kb, lane);
                 const size_t list = (size_t)u.split * kEpiGroups + grp;
-                warp_write_list(p, (list * p.Q + qL) * K, keys, K, lane);
+                warp_write_list(p, (list * p.Q + qL) * K, ka, K, lane);
+                if (qL + 1 < p.Q) warp_write_list(p, (list * p.Q + qL + 1) * K, kb, K, lane);
                 __syncwarp();
             }
         }
@@ -617,8 +656,8 @@ static int launch(const Plan& pl, const CUtensorMap& muh, const CUtensorMap& mul
 static thread_local long long* g_score_dbg = nullptr;
 extern "C" int mr_score_topk_debug_buffer(void* dev_buf, int64_t bytes) {
     using namespace mr;
-    MR_REQUIRE(dev_buf == nullptr || bytes >= (int64_t)(3 * st::kDbgTiles * st::kDbgSlots * 8),
-               "mr_score_topk_debug_buffer: need %d bytes", 3 * st::kDbgTiles * st::kDbgSlots * 8);
+    MR_REQUIRE(dev_buf == nullptr || bytes >= (int64_t)(4 * st::kDbgTiles * st::kDbgSlots * 8),
+               "mr_score_topk_debug_buffer: need %d bytes", 4 * st::kDbgTiles * st::kDbgSlots * 8);
     g_score_dbg = reinterpret_cast<long long*>(dev_buf);
     return MR_OK;
 }

@@ -147,13 +147,16 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
     }
     __syncthreads();
 
-    uint32_t ge[K];  // per-thread count of magnitudes >= lo_mag (fits 32 bits: d < 2^32)
+    uint32_t below[K];  // per-thread count of magnitudes < lo_mag (fits 32 bits: d < 2^32)
+    uint32_t visited = 0;  // elements this thread looked at
+    uint32_t nab[K];       // COLLECT: keys at or below the bracket's upper end among those >= lo_mag
     float wreg[K];
     int lom[K];      // bracket bounds in registers: the edge call may touch shared memory, so values read through
     uint32_t span[K];  // `sm` would be reloaded from shared memory for every element
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        ge[k] = 0;
+        below[k] = 0;
+        nab[k] = 0;
         wreg[k] = W ? w[k] : 1.0f;
         lom[k] = sm.lom[k];
         span[k] = (uint32_t)sm.span[k];
@@ -165,15 +168,38 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
 
-#define MR_TIES_ELEMENT(K_, X_, B_, J_)                                                        \
-    do {                                                                                       \
-        float u_ = __fsub_rn((X_), (B_));                                                      \
-        if (W) u_ = __fmul_rn(u_, wreg[K_]);                                                   \
-        const uint32_t mag_ = __float_as_uint(u_) & 0x7FFFFFFFu;                               \
-        const int t_ = (int)mag_ - lom[K_];                                                    \
-        ge[K_] += (t_ >= 0) ? 1u : 0u;                                                         \
-        if ((uint32_t)t_ <= span[K_])                                                          \
-            ties_pass_edge<K, COLLECT>(smem_raw, mag_, (J_), (K_), pc.cand_keys, pc.cand_cap); \
+// Common path per element and model: FSUB, AND, ISUB, one add of the sign bit, one compare OR-ed into a predicate.
+// `below[k]` counts magnitudes < lo_mag; `hit` collects "some element of this quad lies inside [lo_mag, hi_mag]".
+#define MR_TIES_MAG(K_, X_, B_, MAG_)                                           \
+    do {                                                                        \
+        float u_ = __fsub_rn((X_), (B_));                                       \
+        if (W) u_ = __fmul_rn(u_, wreg[K_]);                                    \
+        (MAG_) = __float_as_uint(u_) & 0x7FFFFFFFu;                             \
+        const uint32_t t_ = (MAG_) - (uint32_t)lom[K_];                         \
+        below[K_] += t_ >> 31; /* lo_mag, mag < 2^31: the sign bit is mag < lo_mag */ \
+        hit |= t_ <= span[K_];                                                  \
+    } while (0)
+// Rare path.  COLLECT (the one full pass of the fast path): classify against the 64-bit bracket inline, count
+// "not above" in a register and store the key -- one shared-memory atomic (the slot), no histogram; the histogram of
+// the ~0.7 % collected keys is built afterwards by ties_cand_hist_kernel.  Otherwise (sample / exact passes, which
+// need the histogram and store nothing): the out-of-line ties_pass_edge.
+#define MR_TIES_EDGE(K_, MAG_, J_)                                              \
+    do {                                                                        \
+        if ((MAG_) - (uint32_t)lom[K_] <= span[K_]) {                           \
+            if (COLLECT) {                                                      \
+                const u64 key_ = ties_key((MAG_), (J_));                        \
+                if (key_ <= sm.hi[K_]) {                                        \
+                    ++nab[K_];                                                  \
+                    if (key_ >= sm.lo[K_]) {                                    \
+                        const uint32_t pos_ = atomicAdd(&sm.cn[K_], 1u);        \
+                        if (pos_ < (uint32_t)pc.cand_cap)                       \
+                            pc.cand_keys[((size_t)(K_) * gridDim.x + blockIdx.x) * pc.cand_cap + pos_] = key_; \
+                    }                                                           \
+                }                                                               \
+            } else {                                                            \
+                ties_pass_edge<K, false>(smem_raw, (MAG_), (J_), (K_), pc.cand_keys, pc.cand_cap); \
+            }                                                                   \
+        }                                                                       \
     } while (0)
 
     for (int64_t i = gtid; i < nsq; i += gsz) {
@@ -190,26 +216,42 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
             for (int k = 0; k < K; ++k) xs[k] = ldg_stream4(models.p[k] + j0);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                MR_TIES_ELEMENT(k, xs[k].x, b4.x, j0);
-                MR_TIES_ELEMENT(k, xs[k].y, b4.y, j0 + 1);
-                MR_TIES_ELEMENT(k, xs[k].z, b4.z, j0 + 2);
-                MR_TIES_ELEMENT(k, xs[k].w, b4.w, j0 + 3);
+                uint32_t m0, m1, m2, m3;
+                bool hit = false;
+                MR_TIES_MAG(k, xs[k].x, b4.x, m0);
+                MR_TIES_MAG(k, xs[k].y, b4.y, m1);
+                MR_TIES_MAG(k, xs[k].z, b4.z, m2);
+                MR_TIES_MAG(k, xs[k].w, b4.w, m3);
+                if (hit) {  // rare: one branch per model and quad instead of one per element
+                    MR_TIES_EDGE(k, m0, j0);
+                    MR_TIES_EDGE(k, m1, j0 + 1);
+                    MR_TIES_EDGE(k, m2, j0 + 2);
+                    MR_TIES_EDGE(k, m3, j0 + 3);
+                }
             }
+            visited += 4;
         } else {
             const int nvalid = (int)((d - j0) < 4 ? (d - j0) : 4);
             for (int c = 0; c < nvalid; ++c) {
                 const float b = base[j0 + c];
 #pragma unroll
-                for (int k = 0; k < K; ++k) MR_TIES_ELEMENT(k, models.p[k][j0 + c], b, j0 + c);
+                for (int k = 0; k < K; ++k) {
+                    uint32_t m0;
+                    bool hit = false;
+                    MR_TIES_MAG(k, models.p[k][j0 + c], b, m0);
+                    if (hit) MR_TIES_EDGE(k, m0, j0 + c);
+                }
             }
+            visited += (uint32_t)nvalid;
         }
     }
-#undef MR_TIES_ELEMENT
+#undef MR_TIES_MAG
+#undef MR_TIES_EDGE
 
     // above = (#magnitudes >= lo_mag) - (#of those that turned out not to be above the bracket)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        uint32_t v = ge[k];
+        uint32_t v = visited - below[k] - nab[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sm.ge[k], v);
@@ -223,6 +265,32 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
     for (int i = threadIdx.x; i < K * kTiesBins; i += blockDim.x) {
         const uint32_t v = sm.hist[i];
         if (v) atomicAdd(&pc.hist[i], v);
+    }
+}
+
+// ---- histogram of the keys collected by the full pass (replaces per-element histogram atomics in that pass) ----------
+__global__ void __launch_bounds__(256)
+ties_cand_hist_kernel(const TiesState* __restrict__ st, const uint32_t* __restrict__ cand_cnt,
+                      const u64* __restrict__ cand_keys, int cand_cap, int n_lists, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[kTiesBins];
+    const int k = blockIdx.y;
+    const TiesState s = st[k];
+    if (s.status != TIES_ST_SEARCH) return;
+    for (int i = threadIdx.x; i < kTiesBins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int c = blockIdx.x; c < n_lists; c += gridDim.x) {
+        uint32_t n = cand_cnt[(size_t)k * n_lists + c];
+        if (n > (uint32_t)cand_cap) n = (uint32_t)cand_cap;   // overflow is reported by ties_compact_kernel
+        const u64* keys = cand_keys + ((size_t)k * n_lists + c) * cand_cap;
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+            const u64 key = keys[e];                            // every stored key lies inside [lo, hi]
+            atomicAdd(&s_hist[(uint32_t)((key - s.lo) >> s.shift)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTiesBins; i += blockDim.x) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(&hist[k * kTiesBins + i], v);
     }
 }
 
@@ -697,6 +765,10 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
 }
 
 static int ties_finish(const TiesWs& L, int K, int64_t k_cnt, u64* cut, int32_t* status, cudaStream_t st) {
+    {
+        dim3 hgrid((unsigned)(L.n_lists < 128 ? L.n_lists : 128), (unsigned)K);
+        ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.hist);
+    }
     ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, k_cnt, k_cnt, 1, status);
     dim3 grid((unsigned)(L.n_lists < 256 ? L.n_lists : 256), (unsigned)K);
     ties_compact_kernel<<<grid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.fin_cnt,

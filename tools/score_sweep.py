@@ -45,15 +45,15 @@ def stamps(Q, N, E, K, mode=0):
     """Per-tile clock64 stamps of block 0 (producer / mma / epilogue)."""
     from mergerec_b200 import _lib
     lib = _lib.load()
-    buf = torch.zeros(3 * 64 * 4, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(4 * 64 * 4, dtype=torch.int64, device="cuda")
     (uh, ul), table = make(Q, N, E)
     score_topk(uh, ul, table, K, mode)
     lib.mr_score_topk_debug_buffer(_lib.dptr(buf), buf.numel() * 8)
     score_topk(uh, ul, table, K, mode)
     torch.cuda.synchronize()
     lib.mr_score_topk_debug_buffer(None, 0)
-    b = buf.cpu().numpy().reshape(3, 64, 4)
-    t0 = b[b > 0].min()
+    b = buf.cpu().numpy().reshape(4, 64, 4)
+    t0 = b[:3][b[:3] > 0].min()
     print(f"--- stamps Q={Q} N={N} E={E} K={K} mode={mode} (cycles since first stamp)")
     print("tile | prod: start emptyok lastkb | mma: start temptyok kb0 last | epi: start tfullok drained")
     for t in range(0, 40):
@@ -61,7 +61,7 @@ def stamps(Q, N, E, K, mode=0):
             break
         r = lambda x: int(x - t0) if x > 0 else -1  # noqa: E731
         print(f"{t:3d} | {r(b[0,t,0]):8d} {r(b[0,t,1]):8d} {r(b[0,t,2]):8d} | {r(b[1,t,0]):8d} {r(b[1,t,1]):8d} {r(b[1,t,2]):8d} "
-              f"{r(b[1,t,3]):8d} | {r(b[2,t,0]):8d} {r(b[2,t,1]):8d} {r(b[2,t,2]):8d}")
+              f"{r(b[1,t,3]):8d} | {r(b[2,t,0]):8d} {r(b[2,t,1]):8d} {r(b[2,t,2]):8d} | ld {b[3,t,0]:6d} flt {b[3,t,1]:6d} cmp {b[3,t,2]:7d} n {b[3,t,3]:3d}")
 
 
 if __name__ == "__main__":
@@ -74,9 +74,8 @@ if __name__ == "__main__":
         torch.cuda.synchronize()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "stamps":
-        stamps(2048, 65536, 128, 10)
-        stamps(2048, 65536, 768, 10)
-        stamps(2048, 65536, 768, 100)
+        stamps(2048, 65536, 128, 100)
+        stamps(2048, 262144, 768, 100)
         sys.exit(0)
     timed(2048, 262144, 768, 100)
     timed(2048, 262144, 768, 100, mode=1)
