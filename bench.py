@@ -28,8 +28,20 @@ import torch  # noqa: E402
 
 
 # ------------------------------------------------------------------------------------------------ utilities
+_JSON_FD = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def measured_peaks():
@@ -187,7 +199,7 @@ def run_ours(args):
         line.update(wl.extra())
         if hasattr(wl, "Q"):
             line["eval_seqs_per_s"] = wl.Q / (ms_per_step * 1e-3)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -209,10 +221,16 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # Only the JSON line may reach stdout: libraries (NCCL with NCCL_DEBUG set, ...) print there from C code, so
+    # file descriptor 1 is pointed at stderr for the whole run and the line is written to the saved descriptor.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

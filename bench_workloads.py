@@ -318,12 +318,29 @@ class EvalCatalog(Workload):
     def setup(self):
         import torch.distributed as dist
         from mergerec_b200.evaluator import Evaluator, ShardedItemTable, shard_bounds
-        g = torch.Generator(device=self.device).manual_seed(99)       # same queries on every rank
-        self.users = torch.nn.functional.normalize(torch.randn(self.Q, self.E, generator=g, device=self.device), dim=-1)
+        # every rank generates the same full table chunk by chunk (seeded), keeps its own rows and the rows of the
+        # labels: half of the queries are planted near their label item so Recall / NDCG are non-trivial
+        g = torch.Generator(device=self.device).manual_seed(99)       # same queries and labels on every rank
+        users = torch.randn(self.Q, self.E, generator=g, device=self.device)
         self.labels = torch.randint(0, self.N, (self.Q,), generator=g, device=self.device)
+        planted = torch.rand(self.Q, generator=g, device=self.device) < 0.5
         lo, hi = shard_bounds(self.N, self.world, self.rank)
-        gi = torch.Generator(device=self.device).manual_seed(1000 + self.rank)
-        self.items = torch.nn.functional.normalize(torch.randn(hi - lo, self.E, generator=gi, device=self.device), dim=-1)
+        self.items = torch.empty(hi - lo, self.E, device=self.device)
+        label_rows = torch.empty(self.Q, self.E, device=self.device)
+        chunk = 65536
+        for c0 in range(0, self.N, chunk):
+            c1 = min(self.N, c0 + chunk)
+            gi = torch.Generator(device=self.device).manual_seed(1000 + c0 // chunk)
+            rows = torch.nn.functional.normalize(torch.randn(c1 - c0, self.E, generator=gi, device=self.device), dim=-1)
+            a, b = max(c0, lo), min(c1, hi)
+            if a < b:
+                self.items[a - lo:b - lo] = rows[a - c0:b - c0]
+            sel = (self.labels >= c0) & (self.labels < c1)
+            if bool(sel.any()):
+                label_rows[sel] = rows[self.labels[sel] - c0]
+        users = torch.where(planted[:, None], label_rows + 0.5 * users / self.E ** 0.5, users)
+        self.users = torch.nn.functional.normalize(users, dim=-1)
+        del label_rows, users
         self.lo = lo
         self.group = dist.group.WORLD if self.world > 1 else None
         self.table = ShardedItemTable(self.items, id_base=lo, n_total=self.N, group=self.group)
