@@ -239,6 +239,67 @@ __device__ __forceinline__ void warp_sort256x2(u64 (&a)[8], u64 (&b)[8], int lan
         }
     }
 }
+// Same network on 32-bit score keys (half the shuffles, min/max instead of 64-bit compare + selects): used by the
+// in-loop compaction, which only needs the K-th largest SCORE to decide what survives; the order inside the buffer
+// is irrelevant until the unit's final sort.
+__device__ __forceinline__ void cmpx32(uint32_t& a, uint32_t& b, bool desc) {
+    const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
+    a = desc ? hi : lo;
+    b = desc ? lo : hi;
+}
+__device__ __forceinline__ void warp_sort256x2_u32(uint32_t (&a)[8], uint32_t (&b)[8], int lane) {
+#pragma unroll 1
+    for (int size = 2; size <= kCap; size <<= 1) {
+        const bool desc_lane = ((lane * 8) & size) == 0;
+#pragma unroll 1
+        for (int lstride = size >> 4; lstride > 0; lstride >>= 1) {
+            const bool take_max = ((lane & lstride) == 0) == desc_lane;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t oa = __shfl_xor_sync(0xffffffffu, a[r], lstride);
+                const uint32_t ob = __shfl_xor_sync(0xffffffffu, b[r], lstride);
+                a[r] = take_max ? (a[r] > oa ? a[r] : oa) : (a[r] > oa ? oa : a[r]);
+                b[r] = take_max ? (b[r] > ob ? b[r] : ob) : (b[r] > ob ? ob : b[r]);
+            }
+        }
+#pragma unroll
+        for (int stride = 4; stride >= 1; stride >>= 1) {
+            if (stride < size) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if ((r & stride) == 0) {
+                        const bool desc = (((lane * 8) + r) & size) == 0;
+                        cmpx32(a[r], a[r | stride], desc);
+                        cmpx32(b[r], b[r | stride], desc);
+                    }
+            }
+        }
+    }
+}
+__device__ __forceinline__ uint32_t warp_pick32(const uint32_t (&v)[8], int e) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if (r == (e & 7)) x = v[r];
+    return __shfl_sync(0xffffffffu, x, e >> 3);
+}
+// Keep the keys whose score key is >= t, packed to the front of the row buffer (any order).  Returns their number.
+__device__ __forceinline__ int warp_keep_ge(u64* gbuf, const u64 (&k)[8], uint32_t t, int lane) {
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) c += ((uint32_t)(k[r] >> 32) >= t) ? 1 : 0;
+    int incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += n;
+    }
+    int pos = incl - c;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if ((uint32_t)(k[r] >> 32) >= t) gbuf[pos++] = k[r];
+    return __shfl_sync(0xffffffffu, incl, 31);
+}
 // Row buffer (n <= kCap keys in global memory) -> registers (zero padded), element e = lane * 8 + r.
 __device__ __forceinline__ void warp_load_keys(u64 (&v)[8], const u64* gbuf, int n, int lane) {
     const uint4* g4 = reinterpret_cast<const uint4*>(gbuf + lane * 8);
@@ -490,12 +551,22 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                         u64 ka[8], kb[8];
                         warp_load_keys(ka, ga, na, lane);
                         warp_load_keys(kb, gb, nb, lane);
-                        warp_sort256x2(ka, kb, lane);
-                        const int keepa = na < K ? na : K, keepb = nb < K ? nb : K;
-                        warp_store_keys(ga, ka, keepa, lane);
-                        if (L1 != L0) warp_store_keys(gb, kb, keepb, lane);
-                        const uint32_t ta = na >= K ? (uint32_t)(warp_pick(ka, K - 1) >> 32) : 0u;
-                        const uint32_t tb = nb >= K ? (uint32_t)(warp_pick(kb, K - 1) >> 32) : 0u;
+                        // K-th largest score key of each row from a 32-bit sort (na, nb > kCap - kChunk >= K here)
+                        uint32_t sa[8], sb[8];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) { sa[r] = (uint32_t)(ka[r] >> 32); sb[r] = (uint32_t)(kb[r] >> 32); }
+                        warp_sort256x2_u32(sa, sb, lane);
+                        uint32_t ta = warp_pick32(sa, K - 1), tb = warp_pick32(sb, K - 1);
+                        int keepa = warp_keep_ge(ga, ka, ta, lane);
+                        int keepb = L1 != L0 ? warp_keep_ge(gb, kb, tb, lane) : keepa;
+                        if (keepa != K || keepb != K) {
+                            // more than K keys at or above the K-th score (equal scores straddle the cut): the exact
+                            // (score, id) order decides -- rare, full 64-bit sort
+                            warp_sort256x2(ka, kb, lane);
+                            warp_store_keys(ga, ka, K, lane);
+                            if (L1 != L0) warp_store_keys(gb, kb, K, lane);
+                            keepa = keepb = K;
+                        }
                         __syncwarp();
                         if (lane == L0 || lane == L1) {
                             const bool first = lane == L0;

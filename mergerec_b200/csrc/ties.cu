@@ -83,8 +83,8 @@ __global__ void ties_init_kernel(TiesState* st, int K, u64* cut, int32_t* status
 struct PassCounters {
     uint32_t* hist;      // K * kTiesBins
     u64* above;          // K
-    uint32_t* cand_cnt;  // K * gridDim.x   (COLLECT)
-    u64* cand_keys;      // K * gridDim.x * cand_cap
+    uint32_t* cand_cnt;  // K * n_threads (COLLECT): one private candidate list per thread and model
+    u64* cand_keys;      // K * n_threads * cand_cap
     int cand_cap;
 };
 
@@ -118,10 +118,7 @@ __device__ __noinline__ void ties_pass_edge(unsigned char* raw, uint32_t mag, in
     if (key < sm.lo[k]) return;                 // below it
     const uint32_t bin = (uint32_t)((key - sm.lo[k]) >> sm.shift[k]);
     atomicAdd(&sm.hist[k * kTiesBins + bin], 1u);
-    if (COLLECT) {
-        const uint32_t pos = atomicAdd(&sm.cn[k], 1u);
-        if (pos < (uint32_t)cand_cap) cand_keys[((size_t)k * gridDim.x + blockIdx.x) * cand_cap + pos] = key;
-    }
+    (void)cand_keys; (void)cand_cap;   // keys are only stored by the inline COLLECT path of the pass kernel
 }
 
 // One streaming pass: per model, count the keys above the bracket, histogram (and optionally store) the keys inside.
@@ -150,6 +147,7 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
     uint32_t below[K];  // per-thread count of magnitudes < lo_mag (fits 32 bits: d < 2^32)
     uint32_t visited = 0;  // elements this thread looked at
     uint32_t nab[K];       // COLLECT: keys at or below the bracket's upper end among those >= lo_mag
+    uint32_t mycnt[K];     // COLLECT: keys appended to this thread's private candidate lists
     float wreg[K];
     int lom[K];      // bracket bounds in registers: the edge call may touch shared memory, so values read through
     uint32_t span[K];  // `sm` would be reloaded from shared memory for every element
@@ -157,6 +155,7 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
     for (int k = 0; k < K; ++k) {
         below[k] = 0;
         nab[k] = 0;
+        mycnt[k] = 0;
         wreg[k] = W ? w[k] : 1.0f;
         lom[k] = sm.lom[k];
         span[k] = (uint32_t)sm.span[k];
@@ -180,8 +179,9 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
         hit |= t_ <= span[K_];                                                  \
     } while (0)
 // Rare path.  COLLECT (the one full pass of the fast path): classify against the 64-bit bracket inline, count
-// "not above" in a register and store the key -- one shared-memory atomic (the slot), no histogram; the histogram of
-// the ~0.7 % collected keys is built afterwards by ties_cand_hist_kernel.  Otherwise (sample / exact passes, which
+// "not above" in a register and append the key to this thread's private list -- no atomics and no histogram, so
+// the warp never waits on a shared-memory round trip; the histogram of the ~0.7 % collected keys is built
+// afterwards by ties_cand_hist_kernel.  Otherwise (sample / exact passes, which
 // need the histogram and store nothing): the out-of-line ties_pass_edge.
 #define MR_TIES_EDGE(K_, MAG_, J_)                                              \
     do {                                                                        \
@@ -190,10 +190,10 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
                 const u64 key_ = ties_key((MAG_), (J_));                        \
                 if (key_ <= sm.hi[K_]) {                                        \
                     ++nab[K_];                                                  \
-                    if (key_ >= sm.lo[K_]) {                                    \
-                        const uint32_t pos_ = atomicAdd(&sm.cn[K_], 1u);        \
-                        if (pos_ < (uint32_t)pc.cand_cap)                       \
-                            pc.cand_keys[((size_t)(K_) * gridDim.x + blockIdx.x) * pc.cand_cap + pos_] = key_; \
+                    if (key_ >= sm.lo[K_]) { /* thread-private list: no atomic, nothing to wait for */ \
+                        if (mycnt[K_] < (uint32_t)pc.cand_cap)                  \
+                            pc.cand_keys[((size_t)(K_) * gsz + gtid) * pc.cand_cap + mycnt[K_]] = key_; \
+                        ++mycnt[K_];                                            \
                     }                                                           \
                 }                                                               \
             } else {                                                            \
@@ -260,7 +260,10 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
     if (threadIdx.x < K) {
         const uint32_t v = sm.ge[threadIdx.x] - sm.notabove[threadIdx.x];
         if (v) atomicAdd(&pc.above[threadIdx.x], (u64)v);
-        if (COLLECT) pc.cand_cnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = sm.cn[threadIdx.x];
+    }
+    if (COLLECT) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) pc.cand_cnt[(size_t)k * gsz + gtid] = mycnt[k];
     }
     for (int i = threadIdx.x; i < K * kTiesBins; i += blockDim.x) {
         const uint32_t v = sm.hist[i];
@@ -278,11 +281,11 @@ ties_cand_hist_kernel(const TiesState* __restrict__ st, const uint32_t* __restri
     if (s.status != TIES_ST_SEARCH) return;
     for (int i = threadIdx.x; i < kTiesBins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    for (int c = blockIdx.x; c < n_lists; c += gridDim.x) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_lists; c += gridDim.x * blockDim.x) {   // one list per thread
         uint32_t n = cand_cnt[(size_t)k * n_lists + c];
         if (n > (uint32_t)cand_cap) n = (uint32_t)cand_cap;   // overflow is reported by ties_compact_kernel
         const u64* keys = cand_keys + ((size_t)k * n_lists + c) * cand_cap;
-        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+        for (uint32_t e = 0; e < n; ++e) {
             const u64 key = keys[e];                            // every stored key lies inside [lo, hi]
             atomicAdd(&s_hist[(uint32_t)((key - s.lo) >> s.shift)], 1u);
         }
@@ -377,14 +380,15 @@ ties_compact_kernel(TiesState* st, const uint32_t* __restrict__ cand_cnt, const 
     const int k = blockIdx.y;
     if (st[k].status != TIES_ST_SEARCH) return;
     const u64 lo = st[k].lo, hi = st[k].hi;
-    for (int c = blockIdx.x; c < n_lists; c += gridDim.x) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_lists; c += gridDim.x * blockDim.x) {   // one list per thread
         const uint32_t n = cand_cnt[(size_t)k * n_lists + c];
         if (n > (uint32_t)cand_cap) {
-            if (threadIdx.x == 0) { st[k].status = TIES_ERR_CAND_OVERFLOW; status[k] = TIES_ERR_CAND_OVERFLOW; }
+            st[k].status = TIES_ERR_CAND_OVERFLOW;
+            status[k] = TIES_ERR_CAND_OVERFLOW;
             continue;
         }
         const u64* keys = cand_keys + ((size_t)k * n_lists + c) * cand_cap;
-        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+        for (uint32_t e = 0; e < n; ++e) {
             const u64 key = keys[e];
             if (key >= lo && key <= hi) {
                 const uint32_t pos = atomicAdd(&fin_cnt[k], 1u);
@@ -447,33 +451,28 @@ struct BuildArgs {
     int P;
 };
 
-// x / c for an integer count c in [2, 16], bit-identical to IEEE division (ties.py:68, `div_`): one reciprocal
+// x / c for an integer count c in [1, 16], bit-identical to IEEE division (ties.py:68, `div_`): one reciprocal
 // multiply plus a Markstein FMA correction.  Exhaustively checked against x / c for every fp32 mantissa and
-// c = 2..16 (.scratch/divfast.c in the build log; DESIGN.md "TIES build").  The correction needs the quotient and
-// the residual to stay normal, so magnitudes outside [2^-100, 2^100] (never produced by real task vectors)
-// take the IEEE divide.
+// c = 2..16 (DESIGN.md "TIES build"; c = 1 is exact by construction: q0 = x, r = 0).  The correction needs the
+// quotient and the residual to stay normal, so a column whose survivors could leave [2^-100, 2^100] takes the IEEE
+// divide instead: survivors are bounded below by their model's cut magnitude (a kernel-wide flag) and above by
+// the elected same-sign sum (one compare per column; inf / NaN fail it too).
+__constant__ float c_inv_count[MR_MAX_K + 1] = {1.0f,        1.0f,        1.0f / 2,  1.0f / 3,  1.0f / 4,  1.0f / 5,
+                                                1.0f / 6,    1.0f / 7,    1.0f / 8,  1.0f / 9,  1.0f / 10, 1.0f / 11,
+                                                1.0f / 12,   1.0f / 13,   1.0f / 14, 1.0f / 15, 1.0f / 16};
 __device__ __forceinline__ float div_by_count_fast(float x, float fc, float inv) {
     const float q0 = __fmul_rn(x, inv);
     const float r = __fmaf_rn(-q0, fc, x);
     return __fmaf_rn(r, inv, q0);
 }
-// non-zero and exponent outside [27, 227]
-__device__ __forceinline__ bool div_needs_ieee(float x) {
-    const uint32_t e = (__float_as_uint(x) >> 23) & 0xFFu;
-    return x != 0.0f && (e - 27u) > 200u;
-}
-template <int K>
-__device__ __noinline__ void div_column_ieee(float (&res)[K], float fc) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) res[k] = __fdiv_rn(res[k], fc);
-}
 
 // One flat column: trim, sign election, disjoint mean (or the trimmed sum for merge_ties).
 // TAIL = false: the column lies in the sequential part of torch.sum(dim=0) (every column when K <= 4).
+// The hot path is branch-free apart from the (never taken in practice) IEEE-divide escape.
 template <int K, int MODE, bool TAIL>
-__device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_t j, const uint32_t (&cut_mag)[K],
-                                            const uint32_t (&cut_lo)[K], const float* __restrict__ wk, float (&res)[K],
-                                            uint32_t& trim_bits, uint32_t& elect_bits) {
+__device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_t j, const u64 (&cut)[K], bool lo_ok,
+                                            const float* __restrict__ wk, float (&res)[K], uint32_t& trim_bits,
+                                            uint32_t& elect_bits) {
     float s[K];
     trim_bits = 0;
     elect_bits = 0;
@@ -482,8 +481,8 @@ __device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_
     for (int k = 0; k < K; ++k) {
         float u = __fsub_rn(x[k], b);
         if (MODE == TIES_MODE_TRIMSUM) u = __fmul_rn(u, wk[k]);
-        const uint32_t mag = __float_as_uint(u) & 0x7FFFFFFFu;
-        const bool keep = (mag > cut_mag[k]) || (mag == cut_mag[k] && jl >= cut_lo[k]);
+        const u64 key = ((u64)(__float_as_uint(u) & 0x7FFFFFFFu) << 32) | (u64)jl;
+        const bool keep = key >= cut[k];
         s[k] = keep ? u : 0.0f;
         trim_bits |= (keep ? 1u : 0u) << k;
     }
@@ -493,18 +492,16 @@ __device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_
         float pp[K], nn[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            pp[k] = s[k] > 0.0f ? s[k] : 0.0f;   // ties.py:35 (torch.where: -0.0 and NaN become +0.0)
-            nn[k] = s[k] < 0.0f ? s[k] : 0.0f;   // ties.py:36
+            pp[k] = fmaxf(s[k], 0.0f);           // ties.py:35 torch.where(s > 0, s, 0): -0.0 and NaN become +0.0 either way
+            nn[k] = s[k] < 0.0f ? s[k] : 0.0f;   // ties.py:36 (fminf would keep a -0.0)
         }
         const float pos = torch_sum_dim0<K>(pp, TAIL);
         const float neg = torch_sum_dim0<K>(nn, TAIL);
-        bool plus;
-        if (pos != 0.0f && neg != 0.0f) {
-            plus = fabsf(pos) >= fabsf(neg);      // ties.py:41-45
-        } else {
-            const float t = __fadd_rn(pos, neg);  // ties.py:47-48; sign 0 -> +1 (ties.py:50)
-            plus = !(t < 0.0f) && !(t != t);
-        }
+        const float t = __fadd_rn(pos, neg);
+        // both sums non-zero: the larger magnitude wins, ties go to + (ties.py:41-45); otherwise sign(pos + neg) with
+        // 0 -> +1 (ties.py:47-50).  A NaN sum compares false and elects minus, as in the previous formulation.
+        const bool both = (pos != 0.0f) && (neg != 0.0f);
+        const bool plus = both ? (fabsf(pos) >= fabsf(neg)) : (t >= 0.0f);
         int cnt = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -513,155 +510,170 @@ __device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_
             cnt += nz ? 1 : 0;
             elect_bits |= (nz ? 1u : 0u) << k;
         }
-        if (cnt > 1) {                             // ties.py:68-70 (cnt == 0: all zeros; cnt == 1: x / 1)
-            const float fc = (float)cnt;
-            const float inv = __frcp_rn(fc);
-            bool odd = false;
+        // ties.py:68-70: x / cnt (cnt == 0: all zeros stay zero; cnt == 1: exact)
+        const float fc = (float)(cnt > 1 ? cnt : 1);
+        const float bound = fabsf(plus ? pos : neg);
+        if (lo_ok && bound < 0x1p100f) {
+            const float inv = c_inv_count[cnt];
 #pragma unroll
-            for (int k = 0; k < K; ++k) odd |= div_needs_ieee(res[k]);
-            if (odd) {
-                div_column_ieee<K>(res, fc);
-            } else {
+            for (int k = 0; k < K; ++k) res[k] = div_by_count_fast(res[k], fc, inv);
+        } else {
 #pragma unroll
-                for (int k = 0; k < K; ++k) res[k] = div_by_count_fast(res[k], fc, inv);
-            }
+            for (int k = 0; k < K; ++k) res[k] = __fdiv_rn(res[k], fc);
         }
     }
 }
 
+// Block table of the FUSED_MERGE mode, staged in shared memory.
+struct FusedSegs {
+    const float* w;        // (G, K) lambdas
+    const int64_t* end;    // P ascending exclusive block ends (P > 1)
+    const int32_t* grp;    // P group ids
+    int P;
+};
+
+// One quad (4 consecutive flat columns) of the build pass.
+// COLD = false: hot path -- all four columns exist and lie in the sequential part of torch.sum(dim=0).
+// COLD = true : the few remaining quads (a partial last quad, the <= 31 trailing columns that use the interleaved
+//               summation order when K >= 5); same arithmetic with per-column validity / tail decisions.
+template <int K, int MODE, bool VEC, bool MASKS, bool COLD>
+__device__ __forceinline__ void ties_quad(const float* __restrict__ base, const PtrPack<K>& models, int64_t d, int64_t q,
+                                          const u64 (&cut)[K], bool lo_ok, const float (&wk)[K], const BuildArgs& a,
+                                          const FusedSegs& fs, int& hint) {
+    const int64_t j0 = q << 2;
+    const int64_t tail0 = d & ~(int64_t)31;
+    const int nvalid = COLD ? (int)((d - j0) < 4 ? (d - j0) : 4) : 4;
+    const bool full = VEC && nvalid == 4;
+    float bx[4];
+    float xs[K][4];
+    if (full) {
+        const float4 b4 = ldg_stream4(base + j0);
+        bx[0] = b4.x; bx[1] = b4.y; bx[2] = b4.z; bx[3] = b4.w;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float4 v = ldg_stream4(models.p[k] + j0);
+            xs[k][0] = v.x; xs[k][1] = v.y; xs[k][2] = v.z; xs[k][3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool ok = c < nvalid;
+            bx[c] = ok ? base[j0 + c] : 0.0f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) xs[k][c] = ok ? models.p[k][j0 + c] : 0.0f;
+        }
+    }
+    float res[4][K];
+    uint32_t tb[4], eb[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float x[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = xs[k][c];
+        // the interleaved torch.sum order only exists for K >= 5 and only on the last d mod 32 columns
+        if (COLD && K >= 5 && j0 + c >= tail0)
+            ties_column<K, MODE, true>(x, bx[c], j0 + c, cut, lo_ok, wk, res[c], tb[c], eb[c]);
+        else
+            ties_column<K, MODE, false>(x, bx[c], j0 + c, cut, lo_ok, wk, res[c], tb[c], eb[c]);
+    }
+    if (MODE == TIES_MODE_VECTORS) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float* o = a.out + (int64_t)k * a.ldo + j0;
+            if (full) stg_stream4(o, make_float4(res[0][k], res[1][k], res[2][k], res[3][k]));
+            else
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (c < nvalid) o[c] = res[c][k];
+        }
+    } else if (MODE == TIES_MODE_TRIMSUM) {
+        float* o = a.out + j0;
+        if (full) stg_stream4(o, make_float4(res[0][0], res[1][0], res[2][0], res[3][0]));
+        else
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c < nvalid) o[c] = res[c][0];
+    } else {  // FUSED_MERGE: base + sum_dim0_k(w[g,k] * That[k])  (layer_wise.py:76-82 order, blocks = tensors)
+        float r[4];
+        int p = 0;
+        if (fs.P > 1) {
+            // first block with end > j0
+            if (!(j0 < fs.end[hint] && (hint == 0 || j0 >= fs.end[hint - 1]))) {
+                int lo = 0, hi = fs.P - 1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (fs.end[mid] > j0) hi = mid; else lo = mid + 1; }
+                hint = lo;
+            }
+            p = hint;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            bool tail;
+            const float* wrow = fs.w;
+            if (fs.P > 1) {
+                while (c < nvalid && j0 + c >= fs.end[p]) ++p;
+                const int64_t beg = p ? fs.end[p - 1] : 0;
+                const int64_t n = fs.end[p] - beg;
+                tail = (K >= 5) && ((j0 + c - beg) >= (n & ~(int64_t)31));
+                wrow = fs.w + fs.grp[p] * K;
+            } else {
+                tail = (K >= 5) && (j0 + c >= tail0);
+            }
+            float prod[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wrow[k], res[c][k]);
+            r[c] = __fadd_rn(bx[c], torch_sum_dim0<K>(prod, tail));
+        }
+        float* o = a.out + j0;
+        if (full) stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
+        else
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c < nvalid) o[c] = r[c];
+    }
+    if (MASKS) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < nvalid) {
+                    if (a.trim_mask) a.trim_mask[(int64_t)k * d + j0 + c] = (tb[c] >> k) & 1u;
+                    if (a.elect_mask) a.elect_mask[(int64_t)k * d + j0 + c] = (eb[c] >> k) & 1u;
+                }
+    }
+}
+
 template <int K, int MODE, bool VEC, bool MASKS>
-__global__ void __launch_bounds__(kTiesThreads)
+__global__ void __launch_bounds__(kTiesThreads, K <= 8 ? 4 : 2)
 ties_build_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const u64* __restrict__ cut_dev,
                   BuildArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t cut_mag[K], cut_lo[K];
+    u64 cut[K];
     float wk[K];
+    bool lo_ok = true;   // every survivor is at least its model's cut magnitude: >= 2^-100 keeps the fast divide exact
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const u64 c = cut_dev[k];
-        cut_mag[k] = (uint32_t)(c >> 32);
-        cut_lo[k] = (uint32_t)c;
+        cut[k] = cut_dev[k];
         wk[k] = (MODE == TIES_MODE_TRIMSUM) ? a.w[k] : 0.0f;
+        lo_ok = lo_ok && ((uint32_t)(cut[k] >> 32) >= (27u << 23));
     }
     // FUSED_MERGE: lambda rows and the block table in shared memory
-    float* s_w = reinterpret_cast<float*>(smem_raw);
-    int64_t* s_end = nullptr;
-    int32_t* s_grp = nullptr;
-    int G = 1;
+    FusedSegs fs{nullptr, nullptr, nullptr, 1};
     if (MODE == TIES_MODE_FUSED_MERGE) {
-        G = (int)a.ldo;  // number of lambda groups travels in ldo for this mode
-        s_end = reinterpret_cast<int64_t*>(smem_raw + ((G * K * 4 + 15) & ~15));
-        s_grp = reinterpret_cast<int32_t*>(s_end + (a.P > 1 ? a.P : 0));
+        const int G = (int)a.ldo;  // number of lambda groups travels in ldo for this mode
+        float* s_w = reinterpret_cast<float*>(smem_raw);
+        int64_t* s_end = reinterpret_cast<int64_t*>(smem_raw + ((G * K * 4 + 15) & ~15));
+        int32_t* s_grp = reinterpret_cast<int32_t*>(s_end + (a.P > 1 ? a.P : 0));
         for (int i = threadIdx.x; i < G * K; i += blockDim.x) s_w[i] = a.w[i];
         if (a.P > 1)
             for (int i = threadIdx.x; i < a.P; i += blockDim.x) { s_end[i] = a.seg_end[i]; s_grp[i] = a.seg_group[i]; }
         __syncthreads();
+        fs = FusedSegs{s_w, s_end, s_grp, a.P};
     }
-    const int64_t tail0 = d & ~(int64_t)31;
     const int64_t nq = (d + 3) >> 2;
+    // hot quads: complete and (for K >= 5) before the interleaved-order tail of the flat vector
+    const int64_t nq_hot = (K >= 5 ? (d & ~(int64_t)31) : (d & ~(int64_t)3)) >> 2;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
     int hint = 0;
-
-    for (int64_t q = gtid; q < nq; q += gsz) {
-        const int64_t j0 = q << 2;
-        const int nvalid = (int)((d - j0) < 4 ? (d - j0) : 4);
-        const bool full = VEC && nvalid == 4;
-        float bx[4];
-        float xs[K][4];
-        if (full) {
-            const float4 b4 = ldg_stream4(base + j0);
-            bx[0] = b4.x; bx[1] = b4.y; bx[2] = b4.z; bx[3] = b4.w;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float4 v = ldg_stream4(models.p[k] + j0);
-                xs[k][0] = v.x; xs[k][1] = v.y; xs[k][2] = v.z; xs[k][3] = v.w;
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const bool ok = c < nvalid;
-                bx[c] = ok ? base[j0 + c] : 0.0f;
-#pragma unroll
-                for (int k = 0; k < K; ++k) xs[k][c] = ok ? models.p[k][j0 + c] : 0.0f;
-            }
-        }
-        float res[4][K];
-        uint32_t tb[4], eb[4];
-        // the interleaved torch.sum order only exists for K >= 5 and only on the last d mod 32 columns
-        const bool tail_quad = (K >= 5) && (j0 + 3 >= tail0);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float x[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) x[k] = xs[k][c];
-            if (tail_quad && j0 + c >= tail0)
-                ties_column<K, MODE, true>(x, bx[c], j0 + c, cut_mag, cut_lo, wk, res[c], tb[c], eb[c]);
-            else
-                ties_column<K, MODE, false>(x, bx[c], j0 + c, cut_mag, cut_lo, wk, res[c], tb[c], eb[c]);
-        }
-        if (MODE == TIES_MODE_VECTORS) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                float* o = a.out + (int64_t)k * a.ldo + j0;
-                if (full) stg_stream4(o, make_float4(res[0][k], res[1][k], res[2][k], res[3][k]));
-                else
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) if (c < nvalid) o[c] = res[c][k];
-            }
-        } else if (MODE == TIES_MODE_TRIMSUM) {
-            float* o = a.out + j0;
-            if (full) stg_stream4(o, make_float4(res[0][0], res[1][0], res[2][0], res[3][0]));
-            else
-#pragma unroll
-                for (int c = 0; c < 4; ++c) if (c < nvalid) o[c] = res[c][0];
-        } else {  // FUSED_MERGE: base + sum_dim0_k(w[g,k] * That[k])  (layer_wise.py:76-82 order, blocks = tensors)
-            float r[4];
-            int p = 0;
-            if (a.P > 1) {
-                // first block with seg_end > j0
-                if (!(j0 < s_end[hint] && (hint == 0 || j0 >= s_end[hint - 1]))) {
-                    int lo = 0, hi = a.P - 1;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_end[mid] > j0) hi = mid; else lo = mid + 1; }
-                    hint = lo;
-                }
-                p = hint;
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                bool tail;
-                const float* wrow = s_w;
-                if (a.P > 1) {
-                    while (c < nvalid && j0 + c >= s_end[p]) ++p;
-                    const int64_t beg = p ? s_end[p - 1] : 0;
-                    const int64_t n = s_end[p] - beg;
-                    tail = (K >= 5) && ((j0 + c - beg) >= (n & ~(int64_t)31));
-                    wrow = s_w + s_grp[p] * K;
-                } else {
-                    tail = (K >= 5) && (j0 + c >= tail0);
-                }
-                float prod[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wrow[k], res[c][k]);
-                r[c] = __fadd_rn(bx[c], torch_sum_dim0<K>(prod, tail));
-            }
-            float* o = a.out + j0;
-            if (full) stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
-            else
-#pragma unroll
-                for (int c = 0; c < 4; ++c) if (c < nvalid) o[c] = r[c];
-        }
-        if (MASKS) {
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < nvalid) {
-                        if (a.trim_mask) a.trim_mask[(int64_t)k * d + j0 + c] = (tb[c] >> k) & 1u;
-                        if (a.elect_mask) a.elect_mask[(int64_t)k * d + j0 + c] = (eb[c] >> k) & 1u;
-                    }
-        }
-    }
+    for (int64_t q = gtid; q < nq_hot; q += gsz) ties_quad<K, MODE, VEC, MASKS, false>(base, models, d, q, cut, lo_ok, wk, a, fs, hint);
+    for (int64_t q = nq_hot + gtid; q < nq; q += gsz) ties_quad<K, MODE, VEC, MASKS, true>(base, models, d, q, cut, lo_ok, wk, a, fs, hint);
 }
 
 // ---- host-side plumbing ---------------------------------------------------------------------------------------
@@ -680,7 +692,9 @@ struct TiesWs {
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static int ties_pass_blocks() { return sm_count() * 4; }
+// one resident wave: the pass kernel is built for 3 CTAs per SM when K <= 8 (2 above), and a 4th CTA per SM would run
+// alone at a third of the occupancy after the others have finished
+static int ties_pass_blocks(int K) { return sm_count() * (K <= 8 ? 3 : 2); }
 
 static int64_t ties_sample_stride(int64_t d) {
     const int64_t nq = (d + 3) >> 2;
@@ -707,7 +721,7 @@ static void ties_sample_ranks(int64_t d, int64_t k_cnt, int64_t n_s, int64_t* r_
 
 static TiesWs ties_layout(void* ws, int64_t d, int K) {
     TiesWs L;
-    const int n_lists = ties_pass_blocks();
+    const int n_lists = ties_pass_blocks(K) * kTiesThreads;   // one private candidate list per thread of the pass grid
     // expected fraction of keys inside the sample bracket: the +-6 sigma rank window plus bin slack
     const int64_t stride = ties_sample_stride(d);
     const int64_t n_s = ties_sample_count(d, stride);
@@ -716,7 +730,7 @@ static TiesWs ties_layout(void* ws, int64_t d, int K) {
     double frac = (double)(r_lo - r_hi + 2) / (double)n_s + 6.0 / kTiesBins * 0.25;
     if (frac > 1.0) frac = 1.0;
     const double expect = (double)d * frac / n_lists;
-    int64_t cap = (int64_t)(3.0 * expect) + 512;
+    int64_t cap = ((int64_t)(4.0 * expect) + 24 + 7) & ~(int64_t)7;   // Poisson tail of a mean-`expect` list: < 1e-12
     if (cap > d + 4) cap = d + 4;
     L.n_lists = n_lists;
     L.cand_cap = (int)cap;
@@ -743,7 +757,7 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
     for (int k = 0; k < K; ++k) { pack.p[k] = models[k]; vec = vec && host_aligned16(models[k]); }
     PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap};
     const size_t smem = PassSmem<K>::bytes();
-    const int blocks = ties_pass_blocks();
+    const int blocks = ties_pass_blocks(K);
     cudaError_t e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
     if (e != cudaSuccess) { set_error("mr_ties_select: memset: %s", cudaGetErrorString(e)); return (int)e; }
 #define MR_PASS(VEC, W, COLLECT)                                                                               \
@@ -766,11 +780,11 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
 
 static int ties_finish(const TiesWs& L, int K, int64_t k_cnt, u64* cut, int32_t* status, cudaStream_t st) {
     {
-        dim3 hgrid((unsigned)(L.n_lists < 128 ? L.n_lists : 128), (unsigned)K);
+        dim3 hgrid(128, (unsigned)K);
         ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.hist);
     }
     ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, k_cnt, k_cnt, 1, status);
-    dim3 grid((unsigned)(L.n_lists < 256 ? L.n_lists : 256), (unsigned)K);
+    dim3 grid(256, (unsigned)K);
     ties_compact_kernel<<<grid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.fin_cnt,
                                               L.fin_keys, status);
     ties_final_kernel<<<K, 1024, 0, st>>>(L.st, L.fin_cnt, L.fin_keys, k_cnt, cut, status);

@@ -54,7 +54,10 @@ def launches(path):
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):   # already exported on the GPU box (tools/ncu_capture.sh)
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     print(f"# ncu --set full --clock-control none ({path}); one block per profiled launch")
@@ -76,5 +79,26 @@ def full(path):
         print()
 
 
+def source(path, top=25):
+    """Hottest SASS instructions (warp-stall samples) of a `--page source --csv` export (.csv or .csv.gz)."""
+    import gzip
+    text = gzip.open(path, "rt").read() if path.endswith(".gz") else open(path).read()
+    rows = list(csv.reader(io.StringIO(text)))
+    hdr = rows[1]
+    isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+    data = [(int(r[isamp]), int(r[iex]), r[isrc].strip()) for r in rows[2:] if len(r) > iex]
+    tot, totex = sum(d[0] for d in data), sum(d[1] for d in data)
+    print(f"# ncu source page ({path}): {rows[0][1][:120]}")
+    print(f"# {len(data)} SASS instructions, {totex} warp-instructions executed, {tot} stall samples")
+    print(f"{'samples':>8} {'share':>7} {'executed':>12}  instruction")
+    for smp, ex, src in sorted(data, reverse=True)[:top]:
+        print(f"{smp:8d} {100.0 * smp / max(tot, 1):6.2f}% {ex:12d}  {src[:100]}")
+    ops = collections.Counter()
+    for smp, ex, src in data:
+        op = src.split()[1] if src.startswith("@") and len(src.split()) > 1 else src.split()[0]
+        ops[op.split(".")[0]] += ex
+    print("# executed warp-instructions by opcode: " + ", ".join(f"{k} {v}" for k, v in ops.most_common(14)))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "source": source}[sys.argv[1]](sys.argv[2])
