@@ -108,7 +108,8 @@ def dist_env():
 
 
 def event_time_ms(fn, iters: int) -> float:
-    """Average device time of fn() over `iters` calls, CUDA events on the current stream."""
+    """Average device time of fn() over `iters` calls (after one untimed call), CUDA events on the current stream."""
+    fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()

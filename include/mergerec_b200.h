@@ -125,6 +125,10 @@ enum mr_ties_mode {
     /* out = base + sum_dim0_k w[g,k] * That[k] without materialising That: get_ties_vectors followed by the
      * lambda merge (A3/A4) in one pass.  w: dev (G, K); seg_end / seg_group / P as in mr_merge_axpy. */
     MR_TIES_FUSED_MERGE = 2,
+    /* out = Localize-and-Stitch vectors (K rows, leading dimension ldo): tau_k * (mask_k / max(sum_j mask_j, 1)) with
+     * mask_k = the top int(density * d) of |tau_k| (same select as TIES)
+     *                                   ref: merger/algorithms/localize_and_stitch.py:8-49.  w unused. */
+    MR_TIES_LNS = 3,
 };
 
 /* trim_mask / elect_mask: optional dev (K, d) bytes: survived the magnitude trim / survived trim and sign

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmergerec_b200.so")
 
 MR_ORDER_BASE_FIRST, MR_ORDER_SUM_FIRST, MR_ORDER_LINEAR = 0, 1, 2
-MR_TIES_VECTORS, MR_TIES_TRIMSUM, MR_TIES_FUSED_MERGE = 0, 1, 2
+MR_TIES_VECTORS, MR_TIES_TRIMSUM, MR_TIES_FUSED_MERGE, MR_TIES_LNS = 0, 1, 2, 3
 MR_MAX_K = 16
 
 _lib: Optional[C.CDLL] = None

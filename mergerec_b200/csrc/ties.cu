@@ -33,7 +33,8 @@ typedef unsigned long long u64;
 constexpr int kTiesBins = 1024;
 constexpr int kTiesThreads = 256;
 constexpr int kTiesFinalCap = 4096;
-constexpr int64_t kTiesSampleQuads = 131072;  // ~0.5 M sampled elements per model
+constexpr int64_t kTiesSampleQuads = 131072;  // ~0.5 M sampled elements per model (2 M narrows the bracket 2x but its two
+                                              // sample passes cost more than the full pass gains: 1.44 vs 1.23 ms measured)
 
 struct TiesState {  // one per model
     u64 lo, hi;      // inclusive bracket on composite keys
@@ -185,12 +186,15 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 // need the histogram and store nothing): the out-of-line ties_pass_edge.
 #define MR_TIES_EDGE(K_, MAG_, J_)                                              \
     do {                                                                        \
-        if ((MAG_) - (uint32_t)lom[K_] <= span[K_]) {                           \
+        const uint32_t te_ = (MAG_) - (uint32_t)lom[K_];                        \
+        if (te_ <= span[K_]) {                                                  \
             if (COLLECT) {                                                      \
                 const u64 key_ = ties_key((MAG_), (J_));                        \
-                if (key_ <= sm.hi[K_]) {                                        \
+                /* strictly between the bracket's end magnitudes: inside without looking at the 64-bit ends */ \
+                const bool interior_ = te_ - 1u < span[K_] - 1u;                \
+                if (interior_ || key_ <= sm.hi[K_]) {                           \
                     ++nab[K_];                                                  \
-                    if (key_ >= sm.lo[K_]) { /* thread-private list: no atomic, nothing to wait for */ \
+                    if (interior_ || key_ >= sm.lo[K_]) { /* thread-private list: no atomic, no wait */ \
                         if (mycnt[K_] < (uint32_t)pc.cand_cap)                  \
                             pc.cand_keys[((size_t)(K_) * gsz + gtid) * pc.cand_cap + mycnt[K_]] = key_; \
                         ++mycnt[K_];                                            \
@@ -438,7 +442,7 @@ ties_final_kernel(TiesState* st, const uint32_t* __restrict__ fin_cnt, const u64
 }
 
 // ---- build kernels (A6-A9) ----------------------------------------------------------------------------------
-enum { TIES_MODE_VECTORS = 0, TIES_MODE_TRIMSUM = 1, TIES_MODE_FUSED_MERGE = 2 };
+enum { TIES_MODE_VECTORS = 0, TIES_MODE_TRIMSUM = 1, TIES_MODE_FUSED_MERGE = 2, TIES_MODE_LNS = 3 };
 
 struct BuildArgs {
     float* out;           // VECTORS: That (K rows, ldo).  TRIMSUM / FUSED_MERGE: merged (d)
@@ -474,6 +478,7 @@ __device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_
                                             const float* __restrict__ wk, float (&res)[K], uint32_t& trim_bits,
                                             uint32_t& elect_bits) {
     float s[K];
+    float uu[K];
     trim_bits = 0;
     elect_bits = 0;
     const uint32_t jl = 0xFFFFFFFFu - (uint32_t)j;
@@ -484,9 +489,18 @@ __device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_
         const u64 key = ((u64)(__float_as_uint(u) & 0x7FFFFFFFu) << 32) | (u64)jl;
         const bool keep = key >= cut[k];
         s[k] = keep ? u : 0.0f;
+        uu[k] = u;
         trim_bits |= (keep ? 1u : 0u) << k;
     }
-    if constexpr (MODE == TIES_MODE_TRIMSUM) {
+    if constexpr (MODE == TIES_MODE_LNS) {
+        // Localize-and-Stitch (localize_and_stitch.py:33-46): mask_k = 1 on the top-k% of |tau_k|; processed mask =
+        // mask / max(#active masks, 1) (an fp32 division of 1.0 or 0.0), result = processed mask * tau (a product, so
+        // an unselected entry keeps tau's sign on its zero).
+        const float inv = c_inv_count[__popc(trim_bits)];
+        elect_bits = trim_bits;
+#pragma unroll
+        for (int k = 0; k < K; ++k) res[k] = __fmul_rn(((trim_bits >> k) & 1u) ? inv : 0.0f, uu[k]);
+    } else if constexpr (MODE == TIES_MODE_TRIMSUM) {
         res[0] = __fadd_rn(b, torch_sum_dim0<K>(s, TAIL));   // ties.py:81-83
     } else {
         float pp[K], nn[K];
@@ -576,7 +590,7 @@ __device__ __forceinline__ void ties_quad(const float* __restrict__ base, const 
         else
             ties_column<K, MODE, false>(x, bx[c], j0 + c, cut, lo_ok, wk, res[c], tb[c], eb[c]);
     }
-    if (MODE == TIES_MODE_VECTORS) {
+    if (MODE == TIES_MODE_VECTORS || MODE == TIES_MODE_LNS) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             float* o = a.out + (int64_t)k * a.ldo + j0;
@@ -894,15 +908,16 @@ extern "C" int mr_ties_build(const float* base, const float* const* models, int 
     using namespace mr;
     MR_REQUIRE(K >= 1 && K <= MR_MAX_K, "mr_ties_build: K=%d outside [1,%d]", K, MR_MAX_K);
     MR_REQUIRE(d >= 0 && d < ((int64_t)1 << 32), "mr_ties_build: need 0 <= d < 2^32");
-    MR_REQUIRE(mode >= 0 && mode <= 2, "mr_ties_build: bad mode %d", mode);
+    MR_REQUIRE(mode >= 0 && mode <= 3, "mr_ties_build: bad mode %d", mode);
     if (d == 0) return MR_OK;
     MR_REQUIRE(base && models && cut && out, "mr_ties_build: null pointer");
-    MR_REQUIRE(mode == TIES_MODE_VECTORS || w, "mr_ties_build: this mode needs weights");
-    MR_REQUIRE(mode != TIES_MODE_VECTORS || ldo >= d, "mr_ties_build: need ldo >= d");
+    const bool rows_out = mode == TIES_MODE_VECTORS || mode == TIES_MODE_LNS;
+    MR_REQUIRE(rows_out || w, "mr_ties_build: this mode needs weights");
+    MR_REQUIRE(!rows_out || ldo >= d, "mr_ties_build: need ldo >= d");
     MR_REQUIRE(mode != TIES_MODE_FUSED_MERGE || (G >= 1 && P >= 1 && (P == 1 || (seg_end && seg_group))),
                "mr_ties_build: FUSED_MERGE needs G >= 1 and a block table when P > 1");
     cudaStream_t st = (cudaStream_t)stream;
-    bool vec = host_aligned16(base) && host_aligned16(out) && (mode != TIES_MODE_VECTORS || (ldo % 4 == 0));
+    bool vec = host_aligned16(base) && host_aligned16(out) && (!rows_out || (ldo % 4 == 0));
     for (int k = 0; k < K; ++k) vec = vec && host_aligned16(models[k]);
     const bool masks = trim_mask || elect_mask;
     const int64_t nq = (d + 3) >> 2;
@@ -924,6 +939,7 @@ extern "C" int mr_ties_build(const float* base, const float* const* models, int 
         PtrPack<KK> pack;
         for (int k = 0; k < KK; ++k) pack.p[k] = models[k];
         if (mode == TIES_MODE_VECTORS) MR_BUILD_VM(TIES_MODE_VECTORS);
+        else if (mode == TIES_MODE_LNS) MR_BUILD_VM(TIES_MODE_LNS);
         else if (mode == TIES_MODE_TRIMSUM) MR_BUILD_VM(TIES_MODE_TRIMSUM);
         else MR_BUILD_VM(TIES_MODE_FUSED_MERGE);
     });

@@ -5,6 +5,7 @@ from typing import List, Optional, Set
 
 import torch
 
+from ...algorithms.localize_and_stitch import get_localize_and_stitch_vectors
 from ...algorithms.task_vector import get_task_vectors
 from ...algorithms.ties import get_ties_vectors
 from ...enums import LearnType, MergeType
@@ -53,7 +54,11 @@ def load_merging_module(merge_type: MergeType, learn_type: LearnType, model: tor
     elif merge_type is MergeType.TIES:
         assert ties_density is not None, "Density should be provided for ties merging."
         vectors = get_ties_vectors(base_model=merger.base_model, models=merger.models, density=ties_density)
-    elif merge_type in (MergeType.PCB, MergeType.LOCALIZE_AND_STITCH):
+    elif merge_type is MergeType.LOCALIZE_AND_STITCH:
+        assert ties_density is not None, "Density should be provided for localize-and-stitch merging."
+        vectors = get_localize_and_stitch_vectors(base_model=merger.base_model, models=merger.models,
+                                                  density=ties_density)
+    elif merge_type is MergeType.PCB:
         raise NotImplementedError(
             f"{merge_type} is a baseline outside the merger hot path this package implements (SURVEY.md section 8(f)).")
     else:

@@ -238,6 +238,30 @@ def merge_ties(base, models, weights: Sequence[float], density: float) -> np.nda
     return out
 
 
+def lns_vectors(base, models, density: float = 0.05) -> np.ndarray:
+    """get_localize_and_stitch_vectors, merger/algorithms/localize_and_stitch.py:8-49, under the canonical
+    lowest-index tie rule of the top-k (the same select as TIES)."""
+    base = _f32(base)
+    models = [_f32(m) for m in models]
+    K, d = len(models), base.size
+    u = np.stack([m - base for m in models]).astype(np.float32)                       # :26
+    if int(density * d) <= 0:                                                          # :30-33
+        return np.zeros_like(u)
+    cut = ties_select(base, models, density)
+    key = (u.view(np.uint32).astype(np.uint64) & np.uint64(0x7FFFFFFF)) << np.uint64(32)
+    key |= (np.uint64(0xFFFFFFFF) - np.arange(d, dtype=np.uint64))[None, :]
+    masks = (key >= cut[:, None]).astype(np.float32)                                   # :36-39
+    denom = np.maximum(masks.sum(axis=0, dtype=np.float32), np.float32(1.0))           # :42-43
+    return ((masks / denom).astype(np.float32) * u).astype(np.float32)                 # :44-48
+
+
+def merge_localize_and_stitch(base, models, weights: Sequence[float], density: float = 0.05) -> np.ndarray:
+    """merge_localize_and_stitch, localize_and_stitch.py:52-82: base + sum_dim0(vectors * w)."""
+    assert len(models) == len(weights), "Number of models and weights should match."
+    w = np.asarray(weights, np.float64).astype(np.float32).reshape(1, -1)
+    return lambda_merge(base, lns_vectors(base, models, density), w)
+
+
 # ----------------------------------------------------------------------------- evaluator
 def scores_f32(U, I) -> np.ndarray:
     """B1: scores = U @ I.T (module/recommender/module.py:137), fp32 BLAS."""

@@ -25,6 +25,8 @@ from rec_retrieval.evaluator import Evaluator  # noqa: E402
 from rec_retrieval.evaluator.metrics import NDCG, Recall  # noqa: E402
 from rec_retrieval.merger import ModelMerger  # noqa: E402
 from rec_retrieval.merger.algorithms.linear import merge_linear  # noqa: E402
+from rec_retrieval.merger.algorithms.localize_and_stitch import (  # noqa: E402
+    get_localize_and_stitch_vectors, merge_localize_and_stitch)
 from rec_retrieval.merger.algorithms.task_vector import get_task_vectors, merge_task_vector  # noqa: E402
 from rec_retrieval.merger.algorithms.ties import get_ties_vectors, merge_ties  # noqa: E402
 from rec_retrieval.merger.enums import LearnType, MergeType  # noqa: E402
@@ -132,6 +134,16 @@ def gen_ties():
     save("ties", **out)
 
 
+def gen_lns():
+    out = {}
+    for case in gc.LNS_CASES:
+        base, models = synth.make_flat(case["d"], case["K"], seed=case["seed"], tie_free=case["tie_free"])
+        tb, tm = T(base), [T(m) for m in models]
+        out[f"{case['name']}/vectors"] = get_localize_and_stitch_vectors(tb, tm, case["density"]).numpy()
+        out[f"{case['name']}/merged"] = merge_localize_and_stitch(tb, tm, case["weights"], case["density"]).numpy()
+    save("lns", **out)
+
+
 def gen_evaluator():
     out = {}
     table = [1 / (torch.log2(torch.tensor(r + 2)).item()) for r in range(1024)]
@@ -197,9 +209,8 @@ def gen_module_e2e():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
-    gen_merge_flat()
-    gen_model_merger()
-    gen_lambda()
-    gen_ties()
-    gen_evaluator()
-    gen_module_e2e()
+    only = set(sys.argv[1:])   # e.g. `make_golden.py lns` regenerates one file
+    for name, fn in [("merge_flat", gen_merge_flat), ("model_merger", gen_model_merger), ("lambda_merge", gen_lambda),
+                     ("ties", gen_ties), ("lns", gen_lns), ("evaluator", gen_evaluator), ("module_e2e", gen_module_e2e)]:
+        if not only or name in only:
+            fn()

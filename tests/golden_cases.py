@@ -34,6 +34,14 @@ TIES_CASES = [
          weights=[0.5, 0.5, 0.5, 0.5, 0.5, 0.5]),
 ]
 
+LNS_CASES = [
+    dict(name="tiefree_k3", K=3, d=4165, seed=71, tie_free=True, density=0.05, weights=[1.0, 1.0, 1.0]),
+    dict(name="tiefree_k8", K=8, d=4165, seed=72, tie_free=True, density=0.2,
+         weights=[0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]),
+    dict(name="gauss_k5", K=5, d=10007, seed=73, tie_free=False, density=0.05, weights=[0.3, 0.5, 0.7, 0.9, 1.1]),
+    dict(name="tiny_density", K=2, d=64, seed=74, tie_free=True, density=0.01, weights=[1.0, 1.0]),   # int(0.64) = 0
+]
+
 EVAL_CASES = [
     dict(name="gauss_small", kind="gauss", Q=64, N=500, E=32, seed=51, metrics=["NDCG", "RECALL"], ks=[1, 5, 10, 50], prefix=""),
     dict(name="grid_small", kind="grid", Q=64, N=500, E=16, seed=52, metrics=["NDCG", "RECALL"], ks=[1, 5, 10, 50], prefix="test/"),

@@ -154,3 +154,26 @@ def test_topk_merge_equals_unsharded():
     mv, mi = orc.topk_merge(np.stack(pv), np.stack(pi))
     assert np.array_equal(mi, i_all) and np.array_equal(mv, v_all)
     assert np.array_equal(orc.label_rank(mi, mi[:, 3].astype(np.int64)), np.full(32, 3, np.int32))
+
+
+@pytest.mark.parametrize("case", gc.LNS_CASES, ids=lambda c: c["name"])
+def test_localize_and_stitch(case):
+    """Oracle vs the reference's get_localize_and_stitch_vectors / merge_localize_and_stitch (lns.npz)."""
+    g = golden("lns")
+    base, models = synth.make_flat(case["d"], case["K"], seed=case["seed"], tie_free=case["tie_free"])
+    vec = orc.lns_vectors(base, models, case["density"])
+    merged = orc.merge_localize_and_stitch(base, models, case["weights"], case["density"])
+    ref_v, ref_m = g[f"{case['name']}/vectors"], g[f"{case['name']}/merged"]
+    if case["tie_free"]:
+        assert_bit_equal(vec, ref_v, "L&S vectors vs raw reference")
+        assert_bit_equal(merged, ref_m, "L&S merge vs raw reference")
+    else:
+        # torch.topk's choice among equal magnitudes at the threshold is unspecified: differences from the raw
+        # reference must be confined to columns holding a threshold-magnitude entry
+        cut = orc.ties_select(base, models, case["density"])
+        thr = (cut >> np.uint64(32)).astype(np.uint32)
+        mags = np.stack([(m - base).astype(np.float32) for m in models]).view(np.uint32) & np.uint32(0x7FFFFFFF)
+        at_thr = (mags == thr[:, None]).any(axis=0)
+        diff = (vec.view(np.uint32) != ref_v.view(np.uint32)).any(axis=0)
+        assert not (diff & ~at_thr).any()
+        assert not ((merged.view(np.uint32) != ref_m.view(np.uint32)) & ~at_thr).any()

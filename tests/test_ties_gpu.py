@@ -153,3 +153,37 @@ def test_ties_full_size_blair_base():
     want = orc.ties_vectors(hb, hm, 0.2)
     got = host(That)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("case", gc.LNS_CASES, ids=lambda c: c["name"])
+def test_localize_and_stitch_vs_golden_and_oracle(case):
+    """Localize-and-Stitch vectors and merge through the TIES select + build kernels."""
+    from mergerec_b200.merger.algorithms import get_localize_and_stitch_vectors, merge_localize_and_stitch
+    g = golden("lns")
+    base, models = synth.make_flat(case["d"], case["K"], seed=case["seed"], tie_free=case["tie_free"])
+    tb, tm = dev(base), [dev(m) for m in models]
+    vec = host(get_localize_and_stitch_vectors(tb, tm, case["density"]))
+    merged = host(merge_localize_and_stitch(tb, tm, case["weights"], case["density"]))
+    assert_bit_equal(vec, orc.lns_vectors(base, models, case["density"]), "L&S vectors vs oracle")
+    assert_bit_equal(merged, orc.merge_localize_and_stitch(base, models, case["weights"], case["density"]), "L&S merge")
+    if case["tie_free"]:
+        assert_bit_equal(vec, g[f"{case['name']}/vectors"], "L&S vectors vs raw reference")
+        assert_bit_equal(merged, g[f"{case['name']}/merged"], "L&S merge vs raw reference")
+
+
+def test_localize_and_stitch_module(monkeypatch):
+    """load_merging_module(MergeType.LOCALIZE_AND_STITCH, ...) builds the stitched vectors and merges them."""
+    from toy_model import ToyEncoder, make_toy_state_dicts
+    from mergerec_b200.merger.enums import LearnType, MergeType
+    from mergerec_b200.merger.weight_learning.module import load_merging_module
+    pre, fts = make_toy_state_dicts(4, seed=81)
+    torch.manual_seed(1)
+    mod = load_merging_module(MergeType.LOCALIZE_AND_STITCH, LearnType.TASK_WISE, ToyEncoder(), pre, fts, ignore_keys=set(),
+                              ties_density=0.1, initial_per_weight=1.0, disable_softmax=True)
+    keys = list(pre.keys())
+    fb = np.concatenate([pre[k].numpy().reshape(-1).astype(np.float32) for k in keys])
+    fm = [np.concatenate([ft[k].numpy().reshape(-1).astype(np.float32) for k in keys]) for ft in fts]
+    want = orc.merge_localize_and_stitch(fb, fm, [1.0] * 4, 0.1)
+    sd = mod.get_state_dict()
+    got = np.concatenate([sd[k].detach().cpu().numpy().reshape(-1) for k in keys])
+    assert_bit_equal(got, want, "merged state_dict through the L&S module")
