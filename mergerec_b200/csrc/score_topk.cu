@@ -30,20 +30,20 @@ namespace st {
 
 constexpr int kBlockM = 128;   // query rows per CTA (TMEM lanes)
 constexpr int kBlockN = 256;   // items per tile (TMEM columns per accumulator stage)
-constexpr int kBlockK = 32;    // fp32 elements per k-block: 128 bytes = one SWIZZLE_128B atom
+// k-block = fp32 elements per pipeline stage and row: BK = 32 -> 128-byte rows (SWIZZLE_128B), BK = 16 -> 64-byte rows
+// (SWIZZLE_64B): half-size stages, more of them in flight (template parameter BK of the kernel)
 constexpr int kUmmaK = 8;      // tf32: 32 bytes of K per tcgen05.mma
 constexpr int kEpiGroups = 1;  // epilogue warp groups (4 warps each); group g drains accumulator stage g
 constexpr int kThreads = 128 + 128 * kEpiGroups;
 constexpr int kCap = 256;      // per-row candidate buffer (keys); power of two, >= 2 * MR_MAX_FUSED_TOPK
 constexpr int kChunk = 16;     // accumulator columns per tcgen05.ld
 constexpr int kAccStages = 2;
-constexpr int kABytes = kBlockM * kBlockK * 4;   // 16 KB: one of (hi, lo) of the query tile
-
-template <int CG> struct Cfg {
+template <int CG, int BK> struct Cfg {
+    static constexpr int kABytes = kBlockM * BK * 4;         // one of (hi, lo) of the query tile: 16 KB at BK = 32
     static constexpr int kBRows = kBlockN / CG;              // item rows staged by one CTA
-    static constexpr int kBBytes = kBRows * kBlockK * 4;     // 32 KB (CG 1) / 16 KB (CG 2)
+    static constexpr int kBBytes = kBRows * BK * 4;          // 32 KB (CG 1) / 16 KB (CG 2) at BK = 32
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    static constexpr int kStages = CG == 1 ? 2 : 3;
+    static constexpr int kStages = BK == 32 ? (CG == 1 ? 2 : 3) : (CG == 1 ? 4 : 7);
     static constexpr int kBarBytes = 256;
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024 /* alignment slack */;
 };
@@ -159,12 +159,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+// K-major shared-memory matrix descriptor: rows of BK * 4 bytes (= the swizzle span), 8-row groups 8 rows apart.
+template <int BK>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4)   // start address, 16-byte units
-           | ((uint64_t)(1024 >> 4) << 32)       // stride byte offset between 8-row groups
-           | (1ull << 46)                        // descriptor version (sm_100)
-           | (2ull << 61);                       // SWIZZLE_128B
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4)            // start address, 16-byte units
+           | ((uint64_t)((8 * BK * 4) >> 4) << 32)        // stride byte offset between 8-row groups
+           | (1ull << 46)                                 // descriptor version (sm_100)
+           | ((BK == 32 ? 2ull : 4ull) << 61);            // SWIZZLE_128B / SWIZZLE_64B
 }
 // kind::tf32 instruction descriptor: fp32 accumulate, tf32 x tf32, both operands K-major, N = 256, M = 128 * CG
 template <int CG>
@@ -342,12 +343,13 @@ __device__ __forceinline__ void warp_write_list(const Params& p, size_t o, const
     }
 }
 
-template <int CG>
+template <int CG, int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_constant__ CUtensorMap map_ulo,
                   const __grid_constant__ CUtensorMap map_ihi, const __grid_constant__ CUtensorMap map_ilo,
                   const Params p) {
-    using C = Cfg<CG>;
+    using C = Cfg<CG, BK>;
+    constexpr int kABytes = C::kABytes;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* stages = smem;
@@ -420,7 +422,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                         const uint32_t sbase = smem_u32(stages + (size_t)s * C::kStageBytes);
                         const uint32_t bytes = (x3 ? 2u : 1u) * (uint32_t)(kABytes + C::kBBytes);
                         if (leader) mbar_arrive_expect_tx(full, bytes * CG);
-                        const int kc = kb * kBlockK;
+                        const int kc = kb * BK;
                         tma_load_2d<CG>(sbase, &map_uhi, full, kc, qrow);
                         tma_load_2d<CG>(sbase + 2 * kABytes, &map_ihi, full, kc, nrow);
                         if (x3) {
@@ -453,12 +455,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                         tc_fence_after();
                         if (lane == 0) {
                             const uint32_t sbase = smem_u32(stages + (size_t)s * C::kStageBytes);
-                            const uint64_t a_hi = make_smem_desc(sbase);
-                            const uint64_t a_lo = make_smem_desc(sbase + kABytes);
-                            const uint64_t b_hi = make_smem_desc(sbase + 2 * kABytes);
-                            const uint64_t b_lo = make_smem_desc(sbase + 2 * kABytes + C::kBBytes);
+                            const uint64_t a_hi = make_smem_desc<BK>(sbase);
+                            const uint64_t a_lo = make_smem_desc<BK>(sbase + kABytes);
+                            const uint64_t b_hi = make_smem_desc<BK>(sbase + 2 * kABytes);
+                            const uint64_t b_lo = make_smem_desc<BK>(sbase + 2 * kABytes + C::kBBytes);
 #pragma unroll
-                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            for (int k = 0; k < BK / kUmmaK; ++k) {
                                 const uint64_t off = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 bytes of K per step
                                 if (x3) {
                                     umma_tf32<CG>(d_tmem, a_hi + off, b_lo + off, idesc, (kb | k) != 0);
@@ -640,20 +642,21 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 // (rows, E) fp32 row-major -> boxes of (32 floats, box_rows rows), 128-byte swizzle, zero fill out of bounds
-static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int E, int box_rows) {
+static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int E, int box_rows, int bk) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {(cuuint64_t)E, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)E * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct Plan {
-    int cg, QB, T, S, QG, grid;
+    int cg, bk, QB, T, S, QG, grid;
     int64_t cand_bytes, part_bytes;
 };
 static int env_int(const char* name, int dflt) {
@@ -663,29 +666,29 @@ static int env_int(const char* name, int dflt) {
 static Plan make_plan(int64_t Q, int64_t N, int K) {
     Plan pl;
     pl.cg = env_int("MR_SCORE_CTA_GROUP", 2) == 1 ? 1 : 2;
+    pl.bk = env_int("MR_SCORE_BK", 32) == 16 ? 16 : 32;
     const int sms = sm_count();
     const int clusters = sms / pl.cg;
     pl.QB = (int)((Q + (int64_t)kBlockM * pl.cg - 1) / ((int64_t)kBlockM * pl.cg));
     pl.T = (int)((N + kBlockN - 1) / kBlockN);
     pl.QG = env_int("MR_SCORE_QGROUP", 16);
     if (pl.QG < 1) pl.QG = 1;
-    // item splits: enough units to fill the machine evenly, few enough that a unit amortises its top-K warm-up
+    // item splits: each unit pays a top-K warm-up (its first tiles pass everything and trigger bursts of row sorts),
+    // measured at roughly (8 + K / 5) tile-times; units are executed in waves of `clusters`.  Pick the S that
+    // minimises waves * (tiles per unit + warm-up).
     int smax = 8192 / (kEpiGroups * (K > 0 ? K : 1));  // mr_topk_merge takes at most 8192 candidates per row
     if (smax > pl.T) smax = pl.T;
     if (smax < 1) smax = 1;
     int s = env_int("MR_SCORE_SPLITS", 0);
     if (s <= 0) {
-        int smin = pl.T / 16;                  // keep >= 16 tiles per unit when the catalog allows
-        if (smin > 8) smin = 8;
-        if (smin < 1) smin = 1;
-        double best = -1.0;
-        s = smin;
-        for (int c = smin; c <= smax; ++c) {
+        const double warm = 8.0 + K / 5.0;
+        double best = 1e300;
+        s = 1;
+        for (int c = 1; c <= smax; ++c) {
             const int64_t units = (int64_t)pl.QB * c;
             const int64_t waves = (units + clusters - 1) / clusters;
-            const double eff = (double)units / (double)(waves * clusters);
-            if (eff > best + 1e-9) { best = eff; s = c; }
-            if (eff >= 0.97) { s = c; break; }
+            const double cost = (double)waves * ((double)((pl.T + c - 1) / c) + warm);
+            if (cost < best * (1.0 - 1e-9)) { best = cost; s = c; }
         }
     }
     if (s > smax) s = smax;
@@ -698,11 +701,11 @@ static Plan make_plan(int64_t Q, int64_t N, int K) {
     return pl;
 }
 
-template <int CG>
+template <int CG, int BK>
 static int launch(const Plan& pl, const CUtensorMap& muh, const CUtensorMap& mul, const CUtensorMap& mih, const CUtensorMap& mil,
                   const Params& p, cudaStream_t stream) {
-    using C = Cfg<CG>;
-    cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    using C = Cfg<CG, BK>;
+    cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<CG, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("mr_score_topk: shared memory attribute: %s", cudaGetErrorString(e)); return (int)e; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
@@ -716,7 +719,7 @@ static int launch(const Plan& pl, const CUtensorMap& muh, const CUtensorMap& mul
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, score_topk_kernel<CG>, muh, mul, mih, mil, p);
+    e = cudaLaunchKernelEx(&cfg, score_topk_kernel<CG, BK>, muh, mul, mih, mil, p);
     if (e != cudaSuccess) { set_error("mr_score_topk: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return MR_OK;
 }
@@ -775,7 +778,7 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     unsigned char* w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
     st::Params p;
     p.Q = Q; p.N = N; p.E = E; p.K = K; p.mode = mode; p.id_base = id_base;
-    p.KB = (E + st::kBlockK - 1) / st::kBlockK;
+    p.KB = (E + pl.bk - 1) / pl.bk;
     p.T = pl.T; p.QB = pl.QB; p.S = pl.S; p.QG = pl.QG;
     p.cand = reinterpret_cast<mr::u64*>(w);
     p.dbg = g_score_dbg;
@@ -786,12 +789,15 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
 
     CUtensorMap muh, mul, mih, mil;
     const int brows = st::kBlockN / pl.cg;
-    bool ok = st::make_map(&muh, Uhi, Q, E, st::kBlockM) && st::make_map(&mih, Ihi, N, E, brows);
-    if (ok && mode == MR_SCORE_TF32X3) ok = st::make_map(&mul, Ulo, Q, E, st::kBlockM) && st::make_map(&mil, Ilo, N, E, brows);
+    bool ok = st::make_map(&muh, Uhi, Q, E, st::kBlockM, pl.bk) && st::make_map(&mih, Ihi, N, E, brows, pl.bk);
+    if (ok && mode == MR_SCORE_TF32X3)
+        ok = st::make_map(&mul, Ulo, Q, E, st::kBlockM, pl.bk) && st::make_map(&mil, Ilo, N, E, brows, pl.bk);
     else if (ok) { mul = muh; mil = mih; }
     if (!ok) { set_error("mr_score_topk: cuTensorMapEncodeTiled failed (driver without TMA support?)"); return MR_ERR_UNSUPPORTED; }
 
-    int rc = pl.cg == 1 ? st::launch<1>(pl, muh, mul, mih, mil, p, s) : st::launch<2>(pl, muh, mul, mih, mil, p, s);
+    int rc;
+    if (pl.bk == 32) rc = pl.cg == 1 ? st::launch<1, 32>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 32>(pl, muh, mul, mih, mil, p, s);
+    else rc = pl.cg == 1 ? st::launch<1, 16>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 16>(pl, muh, mul, mih, mil, p, s);
     if (rc != MR_OK) return rc;
     return mr_topk_merge(part_val, part_id, pl.S * st::kEpiGroups, Q, K, K, out_val, out_id, stream);
 }

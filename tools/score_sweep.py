@@ -78,16 +78,18 @@ if __name__ == "__main__":
         stamps(2048, 262144, 768, 100)
         sys.exit(0)
     timed(2048, 262144, 768, 100)
-    timed(2048, 262144, 768, 100, mode=1)
+    timed(2048, 262144, 768, 100, MR_SCORE_BK=16)
+    timed(2048, 500000, 768, 100)
+    timed(2048, 500000, 768, 100, MR_SCORE_BK=16)
     timed(2048, 262144, 768, 10)
-    timed(2048, 262144, 768, 100, MR_SCORE_CTA_GROUP=1)
-    timed(2048, 262144, 768, 100, MR_SCORE_SPLITS=37)
-    timed(2048, 262144, 768, 100, MR_SCORE_SPLITS=18)
-    timed(2048, 262144, 768, 100, MR_SCORE_QGROUP=4)
-    timed(2048, 262144, 768, 100, MR_SCORE_QGROUP=1)
+    timed(2048, 262144, 768, 10, MR_SCORE_BK=16)
     timed(8192, 131072, 768, 100)
-    timed(8192, 131072, 768, 100, MR_SCORE_QGROUP=8)
+    timed(8192, 131072, 768, 100, MR_SCORE_BK=16)
     timed(16384, 65536, 768, 100)
-    timed(256, 20000, 768, 10)
     timed(2048, 262144, 1024, 50)
+    timed(2048, 262144, 1024, 50, MR_SCORE_BK=16)
+    timed(2048, 262144, 768, 100, mode=1)
+    timed(2048, 262144, 768, 100, MR_SCORE_CTA_GROUP=1)
+    timed(2048, 262144, 768, 100, MR_SCORE_CTA_GROUP=1, MR_SCORE_BK=16)
+    timed(256, 20000, 768, 10)
     timed(2048, 262144, 128, 100)
