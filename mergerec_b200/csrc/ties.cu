@@ -186,15 +186,13 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 // need the histogram and store nothing): the out-of-line ties_pass_edge.
 #define MR_TIES_EDGE(K_, MAG_, J_)                                              \
     do {                                                                        \
-        const uint32_t te_ = (MAG_) - (uint32_t)lom[K_];                        \
-        if (te_ <= span[K_]) {                                                  \
+        if ((MAG_) - (uint32_t)lom[K_] <= span[K_]) {                           \
             if (COLLECT) {                                                      \
+                /* (an "interior magnitude" shortcut that skips the two 64-bit compares measured 15 % slower) */ \
                 const u64 key_ = ties_key((MAG_), (J_));                        \
-                /* strictly between the bracket's end magnitudes: inside without looking at the 64-bit ends */ \
-                const bool interior_ = te_ - 1u < span[K_] - 1u;                \
-                if (interior_ || key_ <= sm.hi[K_]) {                           \
+                if (key_ <= sm.hi[K_]) {                                        \
                     ++nab[K_];                                                  \
-                    if (interior_ || key_ >= sm.lo[K_]) { /* thread-private list: no atomic, no wait */ \
+                    if (key_ >= sm.lo[K_]) { /* thread-private list: no atomic, no wait */ \
                         if (mycnt[K_] < (uint32_t)pc.cand_cap)                  \
                             pc.cand_keys[((size_t)(K_) * gsz + gtid) * pc.cand_cap + mycnt[K_]] = key_; \
                         ++mycnt[K_];                                            \

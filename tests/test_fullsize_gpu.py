@@ -124,3 +124,48 @@ def test_ties_full_size_properties(blair):
     for k in range(K):      # equal positive weights scale magnitudes uniformly: same survivors as the unweighted trim
         s = s + torch.where(trim[k].bool(), torch.tensor(0.5, device="cuda") * (models[k] - base), torch.zeros((), device="cuda"))
     assert torch.equal(mt, base + s)
+
+
+def test_recformer_large_config4_properties():
+    """BASELINE config 4 merger shapes: Recformer-large, d = 433,610,754 (d mod 32 = 2; every tensor after the
+    4,098-element position_ids starts at a flat offset that is 8- but not 16-byte aligned), K = 8, layer-wise G = 25."""
+    shapes = synth.recformer_shapes()
+    d = synth.total_numel(shapes)
+    assert d == 433_610_754 and d % 32 == 2
+    layout = FlatLayout.from_shape_dict(shapes)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    base = torch.randn(d, generator=g, device="cuda") * 0.02
+    models = [base + 1e-3 * torch.randn(d, generator=g, device="cuda") for _ in range(K)]
+    seg_end, seg_group, keys = layout.device_blocks(True, base.device)
+    assert len(keys) == 25
+    # task arithmetic against torch's own elementwise kernels
+    w = [0.3, 0.2, 0.1, 0.4, 0.25, 0.15, 0.35, 0.05]
+    got = merge_task_vector(base, models, w)
+    acc = base.clone()
+    for m, wk in zip(models, w):
+        acc = acc + torch.tensor(wk, dtype=torch.float32, device="cuda") * (m - base)
+    assert torch.equal(got, acc)
+    del acc, got
+    # TIES: exact count per model, and the fused election + mean + layer-wise merge equals the two-step path, including
+    # the 2-column interleaved tail of the flat vector (K = 8 >= 5) and blocks that straddle 128-bit quads
+    density = 0.2
+    k_cnt = ties_topk_count(density, d)
+    assert k_cnt == 86_722_150
+    That, trim, elect, cut = get_ties_vectors(base, models, density, return_masks=True)
+    assert bool((trim.sum(dim=1) == k_cnt).all())
+    assert torch.equal(That != 0, elect)
+    del trim, elect
+    lam = torch.rand((len(keys), K), device="cuda") * 0.4 + 0.1
+    two_step = merge_axpy(base, list(That.unbind(0)), lam, _lib.MR_ORDER_SUM_FIRST, False, seg_end, seg_group)
+    del That
+    torch.cuda.empty_cache()
+    fused = merge_ties_lambda(base, models, density, lam, seg_end, seg_group, cut=cut)
+    assert torch.equal(fused, two_step)
+    # the last two flat columns use torch.sum's 4-way interleaved order (K >= 5): recompute them by hand in that order
+    T2 = torch.stack([m[d - 2:] - base[d - 2:] for m in models])          # (K, 2) raw task vectors of the tail
+    lam_tail = lam[int(seg_group[-1])]
+    tw = merge_axpy(base, [m - base for m in models], lam[:1].contiguous(), _lib.MR_ORDER_SUM_FIRST, False)   # task-wise
+    prod = lam[0][:, None] * T2
+    p0 = (prod[0] + prod[4]); p1 = (prod[1] + prod[5]); p2 = (prod[2] + prod[6]); p3 = (prod[3] + prod[7])
+    assert torch.equal(tw[d - 2:], base[d - 2:] + (((p0 + p1) + p2) + p3)), "interleaved tail order (task-wise, whole-vector block)"
+    del lam_tail
