@@ -167,12 +167,16 @@ int mr_label_rank(const int32_t* ids, int64_t Q, int K, const int64_t* labels, i
  *   Ihi, Ilo   dev (N, E) row-major: the halves of this GPU's rows of the item table (split once, reused)
  *   id_base    global id of item row 0 (shard offset); returned ids are id_base + row
  *   mode       MR_SCORE_TF32X3: Uhi.Ilo + Ulo.Ihi + Uhi.Ihi, fp32-faithful (default);
- *              MR_SCORE_TF32X1: Uhi.Ihi only (Ulo / Ilo may be NULL)
+ *              MR_SCORE_TF32X1: Uhi.Ihi only (Ulo / Ilo may be NULL);
+ *              MR_SCORE_BF16:   bf16-compat -- Uhi / Ihi point to BF16 arrays (mr_to_bf16; Ulo / Ilo unused), fp32
+ *                               accumulation, scores rounded to bf16 before ranking: what the reference's default
+ *                               `precision="bf16-mixed"` runs compute (ref: configs/base.py:41, utils.py:84), with the
+ *                               canonical tie rule on the many equal bf16 scores.  Needs E % 8 == 0.
  *   out_val / out_id   dev (Q, K), sorted by (score desc, id asc); slots beyond N hold id -1, score -inf
  *   ws         dev scratch of at least mr_score_topk_workspace_bytes(Q, N, E, K) bytes
  * Requires E % 4 == 0, 16-byte aligned operands, 1 <= K <= MR_MAX_FUSED_TOPK.  Scores are exact (hence identical
  * to any fp32 summation order) whenever all products and partial sums are representable, e.g. grid embeddings. */
-enum mr_score_mode { MR_SCORE_TF32X3 = 0, MR_SCORE_TF32X1 = 1 };
+enum mr_score_mode { MR_SCORE_TF32X3 = 0, MR_SCORE_TF32X1 = 1, MR_SCORE_BF16 = 2 };
 int64_t mr_score_topk_workspace_bytes(int64_t Q, int64_t N, int E, int K);
 int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, const float* Ihi, const float* Ilo, int64_t N, int E,
                   int K, int32_t id_base, int mode, float* out_val, int32_t* out_id, void* ws, int64_t ws_bytes,
@@ -181,6 +185,9 @@ int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, const float* Ih
 /* Diagnostics: when dev_buf != NULL, later mr_score_topk launches of this thread make block 0 record clock64()
  * stamps per tile (3 roles x 64 tiles x 4 slots of int64: tools/score_sweep.py prints them).  NULL switches it off. */
 int mr_score_topk_debug_buffer(void* dev_buf, int64_t bytes);
+
+/* out[i] = bf16(x[i]), round to nearest even (the operand conversion of MR_SCORE_BF16). */
+int mr_to_bf16(const float* x, int64_t n, uint16_t* out, mr_stream_t stream);
 
 /* hi = rna_tf32(x), lo = rna_tf32(x - hi): the operand split of the fp32-faithful 3xTF32 contraction. */
 int mr_split_tf32(const float* x, int64_t n, float* hi, float* lo, mr_stream_t stream);

@@ -150,6 +150,18 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float*
     }
 }
 
+// fp32 -> bf16, round to nearest even (what `tensor.to(torch.bfloat16)` / autocast do); NaN stays NaN
+__global__ void to_bf16_kernel(const float* __restrict__ x, int64_t n, uint16_t* __restrict__ out) {
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gsz) {
+        const uint32_t u = __float_as_uint(x[i]);
+        uint32_t r;
+        if ((u & 0x7F800000u) == 0x7F800000u) r = (u & 0x007FFFFFu) ? (u | 0x00400000u) : u;   // NaN (quieted) / inf
+        else r = u + 0x7FFFu + ((u >> 16) & 1u);
+        out[i] = (uint16_t)(r >> 16);
+    }
+}
+
 // ---- B1 in plain fp32 on CUDA cores ("fp32 mode"; also the on-device cross-check of the tensor-core path) ------------
 // out[q, n] = sum_e U[q,e] * I[n,e], one fp32 FMA chain per score, sequential in e.
 constexpr int kSfTile = 64, kSfBk = 16;
@@ -252,6 +264,19 @@ extern "C" int mr_split_tf32(const float* x, int64_t n, float* hi, float* lo, mr
     if (blocks > cap) blocks = cap;
     split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, hi, lo);
     MR_CUDA_LAUNCH_CHECK("mr_split_tf32");
+    return MR_OK;
+}
+
+extern "C" int mr_to_bf16(const float* x, int64_t n, uint16_t* out, mr_stream_t stream) {
+    using namespace mr;
+    MR_REQUIRE(n >= 0, "mr_to_bf16: n < 0");
+    if (n == 0) return MR_OK;
+    MR_REQUIRE(x && out, "mr_to_bf16: null pointer");
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    to_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+    MR_CUDA_LAUNCH_CHECK("mr_to_bf16");
     return MR_OK;
 }
 

@@ -38,12 +38,14 @@ constexpr int kThreads = 128 + 128 * kEpiGroups;
 constexpr int kCap = 256;      // per-row candidate buffer (keys); power of two, >= 2 * MR_MAX_FUSED_TOPK
 constexpr int kChunk = 16;     // accumulator columns per tcgen05.ld
 constexpr int kAccStages = 2;
-template <int CG, int BK> struct Cfg {
+// BF16 (bf16-compat mode): one bf16 operand pair per stage, rows of 64 bf16 = 128 bytes (same geometry as BK = 32).
+template <int CG, int BK, bool BF16> struct Cfg {
     static constexpr int kABytes = kBlockM * BK * 4;         // one of (hi, lo) of the query tile: 16 KB at BK = 32
     static constexpr int kBRows = kBlockN / CG;              // item rows staged by one CTA
     static constexpr int kBBytes = kBRows * BK * 4;          // 32 KB (CG 1) / 16 KB (CG 2) at BK = 32
-    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    static constexpr int kStages = BK == 32 ? (CG == 1 ? 2 : 3) : (CG == 1 ? 4 : 7);
+    static constexpr int kStageBytes = (BF16 ? 1 : 2) * (kABytes + kBBytes);
+    static constexpr int kStages = BF16 ? (CG == 1 ? 4 : 6) : BK == 32 ? (CG == 1 ? 2 : 3) : (CG == 1 ? 4 : 7);
+    static constexpr int kElemsPerBlock = BF16 ? 2 * BK : BK;   // K elements per k-block
     static constexpr int kBarBytes = 256;
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024 /* alignment slack */;
 };
@@ -138,6 +140,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
             ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
     }
 }
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    }
+}
 // tcgen05.commit: the barrier is arrived on when every previously issued MMA of this thread has completed
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -168,9 +182,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
            | ((BK == 32 ? 2ull : 4ull) << 61);            // SWIZZLE_128B / SWIZZLE_64B
 }
 // kind::tf32 instruction descriptor: fp32 accumulate, tf32 x tf32, both operands K-major, N = 256, M = 128 * CG
-template <int CG>
+template <int CG, bool BF16>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)((kBlockM * CG) >> 4) << 24);
+    return (1u << 4) | ((BF16 ? 1u : 2u) << 7) | ((BF16 ? 1u : 2u) << 10) | ((uint32_t)(kBlockN >> 3) << 17) |
+           ((uint32_t)((kBlockM * CG) >> 4) << 24);
 }
 
 // diagnostics: block 0 stamps clock64() per tile into dbg[role][tile][slot] (role 0 producer, 1 mma, 2 epilogue)
@@ -343,12 +358,12 @@ __device__ __forceinline__ void warp_write_list(const Params& p, size_t o, const
     }
 }
 
-template <int CG, int BK>
+template <int CG, int BK, bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_constant__ CUtensorMap map_ulo,
                   const __grid_constant__ CUtensorMap map_ihi, const __grid_constant__ CUtensorMap map_ilo,
                   const Params p) {
-    using C = Cfg<CG, BK>;
+    using C = Cfg<CG, BK, BF16>;
     constexpr int kABytes = C::kABytes;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -366,7 +381,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x / CG;
     const int num_clusters = gridDim.x / CG;
-    const bool x3 = p.mode == 0;
+    const bool x3 = !BF16 && p.mode == 0;
 
     if (CG > 1) cluster_sync_all();  // both CTAs resident before the paired TMEM allocation
     if (warp == 0 && lane == 0) {
@@ -422,9 +437,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                         const uint32_t sbase = smem_u32(stages + (size_t)s * C::kStageBytes);
                         const uint32_t bytes = (x3 ? 2u : 1u) * (uint32_t)(kABytes + C::kBBytes);
                         if (leader) mbar_arrive_expect_tx(full, bytes * CG);
-                        const int kc = kb * BK;
+                        const int kc = kb * C::kElemsPerBlock;
                         tma_load_2d<CG>(sbase, &map_uhi, full, kc, qrow);
-                        tma_load_2d<CG>(sbase + 2 * kABytes, &map_ihi, full, kc, nrow);
+                        tma_load_2d<CG>(sbase + (BF16 ? 1 : 2) * kABytes, &map_ihi, full, kc, nrow);
                         if (x3) {
                             tma_load_2d<CG>(sbase + kABytes, &map_ulo, full, kc, qrow);
                             tma_load_2d<CG>(sbase + 2 * kABytes + C::kBBytes, &map_ilo, full, kc, nrow);
@@ -437,7 +452,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA; one lane issues) =====
         if (leader) {
-            constexpr uint32_t idesc = make_idesc<CG>();
+            constexpr uint32_t idesc = make_idesc<CG, BF16>();
             uint32_t kiter = 0, it = 0;
             Unit u;
             for (int ui = cluster_id; get_unit(p, ui, u); ui += num_clusters) {
@@ -457,12 +472,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                             const uint32_t sbase = smem_u32(stages + (size_t)s * C::kStageBytes);
                             const uint64_t a_hi = make_smem_desc<BK>(sbase);
                             const uint64_t a_lo = make_smem_desc<BK>(sbase + kABytes);
-                            const uint64_t b_hi = make_smem_desc<BK>(sbase + 2 * kABytes);
+                            const uint64_t b_hi = make_smem_desc<BK>(sbase + (BF16 ? 1 : 2) * kABytes);
                             const uint64_t b_lo = make_smem_desc<BK>(sbase + 2 * kABytes + C::kBBytes);
 #pragma unroll
                             for (int k = 0; k < BK / kUmmaK; ++k) {
                                 const uint64_t off = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 bytes of K per step
-                                if (x3) {
+                                if (BF16) {
+                                    umma_bf16<CG>(d_tmem, a_hi + off, b_hi + off, idesc, (kb | k) != 0);
+                                } else if (x3) {
                                     umma_tf32<CG>(d_tmem, a_hi + off, b_lo + off, idesc, (kb | k) != 0);
                                     umma_tf32<CG>(d_tmem, a_lo + off, b_hi + off, idesc, 1u);
                                     umma_tf32<CG>(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
@@ -520,6 +537,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                     const long long c1 = p.dbg ? clock64() : 0;
                     // Phase 1, branch-free: bit j of m = "column c + j may enter the row's list" (cheap superset test:
                     // key(f) > thr implies f > thr_f or f is NaN).  No per-element branches, so the 16 tests overlap.
+                    if (BF16) {   // the reference's bf16 autocast matmul returns bf16 scores: round the fp32 accumulator (RN-even)
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j) {
+                            const uint32_t u = v[j];
+                            const uint32_t r = ((u & 0x7F800000u) == 0x7F800000u) ? u : u + 0x7FFFu + ((u >> 16) & 1u);
+                            v[j] = r & 0xFFFF0000u;
+                        }
+                    }
                     uint32_t m = 0;
 #pragma unroll
                     for (int j = 0; j < kChunk; ++j) m |= (!(__uint_as_float(v[j]) <= thr_f)) ? (1u << j) : 0u;
@@ -642,14 +667,15 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 // (rows, E) fp32 row-major -> boxes of (32 floats, box_rows rows), 128-byte swizzle, zero fill out of bounds
-static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int E, int box_rows, int bk) {
+static bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int E, int box_rows, int bk, bool bf16) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {(cuuint64_t)E, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)E * 4};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)E * (bf16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * bk : bk), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+    return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides,
+              box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -701,11 +727,11 @@ static Plan make_plan(int64_t Q, int64_t N, int K) {
     return pl;
 }
 
-template <int CG, int BK>
+template <int CG, int BK, bool BF16>
 static int launch(const Plan& pl, const CUtensorMap& muh, const CUtensorMap& mul, const CUtensorMap& mih, const CUtensorMap& mil,
                   const Params& p, cudaStream_t stream) {
-    using C = Cfg<CG, BK>;
-    cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<CG, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    using C = Cfg<CG, BK, BF16>;
+    cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<CG, BK, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("mr_score_topk: shared memory attribute: %s", cudaGetErrorString(e)); return (int)e; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
@@ -719,7 +745,7 @@ static int launch(const Plan& pl, const CUtensorMap& muh, const CUtensorMap& mul
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, score_topk_kernel<CG, BK>, muh, mul, mih, mil, p);
+    e = cudaLaunchKernelEx(&cfg, score_topk_kernel<CG, BK, BF16>, muh, mul, mih, mil, p);
     if (e != cudaSuccess) { set_error("mr_score_topk: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return MR_OK;
 }
@@ -753,13 +779,14 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     using namespace mr;
     MR_REQUIRE(Q >= 0 && N >= 0 && E >= 1, "mr_score_topk: need Q, N >= 0 and E >= 1");
     MR_REQUIRE(K >= 1 && K <= MR_MAX_FUSED_TOPK, "mr_score_topk: K=%d outside [1,%d]", K, MR_MAX_FUSED_TOPK);
-    MR_REQUIRE(mode == MR_SCORE_TF32X3 || mode == MR_SCORE_TF32X1, "mr_score_topk: unknown mode %d", mode);
-    MR_REQUIRE(E % 4 == 0, "mr_score_topk: E=%d must be a multiple of 4 (16-byte rows for TMA)", E);
+    MR_REQUIRE(mode == MR_SCORE_TF32X3 || mode == MR_SCORE_TF32X1 || mode == MR_SCORE_BF16, "mr_score_topk: unknown mode %d", mode);
+    const bool bf16 = mode == MR_SCORE_BF16;
+    MR_REQUIRE(E % (bf16 ? 8 : 4) == 0, "mr_score_topk: E=%d must be a multiple of %d (16-byte rows for TMA)", E, bf16 ? 8 : 4);
     MR_REQUIRE(Q < (1ll << 31) - 512 && N < (1ll << 31) - 512 && (int64_t)id_base + N < (1ll << 31),
                "mr_score_topk: Q, N and id_base + N must fit 31 bits");
     if (Q == 0) return MR_OK;
     MR_REQUIRE(Uhi && Ihi && out_val && out_id, "mr_score_topk: null pointer");
-    MR_REQUIRE(mode == MR_SCORE_TF32X1 || (Ulo && Ilo), "mr_score_topk: the 3xTF32 mode needs the lo operands");
+    MR_REQUIRE(mode != MR_SCORE_TF32X3 || (Ulo && Ilo), "mr_score_topk: the 3xTF32 mode needs the lo operands");
     MR_REQUIRE(host_aligned16(Uhi) && host_aligned16(Ihi) && host_aligned16(Ulo) && host_aligned16(Ilo),
                "mr_score_topk: operands must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
@@ -778,7 +805,9 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     unsigned char* w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
     st::Params p;
     p.Q = Q; p.N = N; p.E = E; p.K = K; p.mode = mode; p.id_base = id_base;
-    p.KB = (E + pl.bk - 1) / pl.bk;
+    const int bk = bf16 ? 32 : pl.bk;                 // bf16 rows are 64 elements = 128 bytes: the BK = 32 geometry
+    const int kelems = bf16 ? 64 : bk;
+    p.KB = (E + kelems - 1) / kelems;
     p.T = pl.T; p.QB = pl.QB; p.S = pl.S; p.QG = pl.QG;
     p.cand = reinterpret_cast<mr::u64*>(w);
     p.dbg = g_score_dbg;
@@ -789,15 +818,16 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
 
     CUtensorMap muh, mul, mih, mil;
     const int brows = st::kBlockN / pl.cg;
-    bool ok = st::make_map(&muh, Uhi, Q, E, st::kBlockM, pl.bk) && st::make_map(&mih, Ihi, N, E, brows, pl.bk);
+    bool ok = st::make_map(&muh, Uhi, Q, E, st::kBlockM, bk, bf16) && st::make_map(&mih, Ihi, N, E, brows, bk, bf16);
     if (ok && mode == MR_SCORE_TF32X3)
-        ok = st::make_map(&mul, Ulo, Q, E, st::kBlockM, pl.bk) && st::make_map(&mil, Ilo, N, E, brows, pl.bk);
+        ok = st::make_map(&mul, Ulo, Q, E, st::kBlockM, bk, false) && st::make_map(&mil, Ilo, N, E, brows, bk, false);
     else if (ok) { mul = muh; mil = mih; }
     if (!ok) { set_error("mr_score_topk: cuTensorMapEncodeTiled failed (driver without TMA support?)"); return MR_ERR_UNSUPPORTED; }
 
     int rc;
-    if (pl.bk == 32) rc = pl.cg == 1 ? st::launch<1, 32>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 32>(pl, muh, mul, mih, mil, p, s);
-    else rc = pl.cg == 1 ? st::launch<1, 16>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 16>(pl, muh, mul, mih, mil, p, s);
+    if (bf16) rc = pl.cg == 1 ? st::launch<1, 32, true>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 32, true>(pl, muh, mul, mih, mil, p, s);
+    else if (bk == 32) rc = pl.cg == 1 ? st::launch<1, 32, false>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 32, false>(pl, muh, mul, mih, mil, p, s);
+    else rc = pl.cg == 1 ? st::launch<1, 16, false>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 16, false>(pl, muh, mul, mih, mil, p, s);
     if (rc != MR_OK) return rc;
     return mr_topk_merge(part_val, part_id, pl.S * st::kEpiGroups, Q, K, K, out_val, out_id, stream);
 }

@@ -2,6 +2,7 @@
 from .enums import MetricType
 from .evaluator import Evaluator
 from .metrics import NDCG, BaseMetric, Recall
-from .sharded import ShardedItemTable, shard_bounds
+from .sharded import MR_SCORE_BF16, MR_SCORE_TF32X1, MR_SCORE_TF32X3, ShardedItemTable, shard_bounds
 
-__all__ = ["Evaluator", "MetricType", "Recall", "NDCG", "BaseMetric", "ShardedItemTable", "shard_bounds"]
+__all__ = ["Evaluator", "MetricType", "Recall", "NDCG", "BaseMetric", "ShardedItemTable", "shard_bounds",
+           "MR_SCORE_TF32X3", "MR_SCORE_TF32X1", "MR_SCORE_BF16"]

@@ -18,7 +18,8 @@ import torch
 from .. import _lib
 from .enums import MetricType
 from .metrics import label_rank
-from .sharded import MAX_FUSED_TOPK, MR_SCORE_TF32X3, ShardedItemTable, exchange_topk, split_tf32
+from .sharded import (MAX_FUSED_TOPK, MR_SCORE_BF16, MR_SCORE_TF32X3, ShardedItemTable, exchange_topk, split_tf32,
+                      to_bf16)
 
 MAX_TOPK = 1024
 
@@ -93,18 +94,24 @@ class Evaluator:
 
         ``item_emb`` is an (N, E) tensor (single GPU) or a ``ShardedItemTable`` (reusable, possibly one shard of
         a multi-GPU catalog -- then every rank passes the same queries and receives the same merged lists).
-        ``normalize`` applies the reference's cosine normalisation to the queries (and to a raw item tensor)."""
+        ``normalize`` applies the reference's cosine normalisation to the queries (and to a raw item tensor).
+        ``mode``: ``MR_SCORE_TF32X3`` (default, fp32-faithful), ``MR_SCORE_TF32X1``, or ``MR_SCORE_BF16`` -- the
+        bf16-compat mode that mirrors the reference's default ``precision="bf16-mixed"`` runs (bf16 operands, fp32
+        accumulation, scores rounded to bf16; configs/base.py:41) with the canonical tie rule on equal scores."""
         k = self._max_k if k is None else k
         if k > MAX_FUSED_TOPK:
             raise ValueError(f"fused top-k supports k <= {MAX_FUSED_TOPK}")
         dev = _lib.require_cuda()
-        table = item_emb if isinstance(item_emb, ShardedItemTable) else ShardedItemTable(item_emb, normalize=normalize)
+        table = item_emb if isinstance(item_emb, ShardedItemTable) else ShardedItemTable(
+            item_emb, normalize=normalize, bf16=(mode == MR_SCORE_BF16))
+        if table.bf16 != (mode == MR_SCORE_BF16):
+            raise ValueError("the item table was prepared for a different scoring mode (bf16 table <-> MR_SCORE_BF16)")
         if k > table.n_total:
             raise RuntimeError(f"selected index k out of range (k={k}, N={table.n_total})")
         users = user_emb.to(device=dev, dtype=torch.float32)
         if normalize:
             users = torch.nn.functional.normalize(users, p=2, dim=-1)
-        u_hi, u_lo = split_tf32(users)
+        u_hi, u_lo = (to_bf16(users), None) if table.bf16 else split_tf32(users)
         vals, ids = score_topk(u_hi, u_lo, table, k, mode)
         if table.group is not None:
             vals, ids = exchange_topk(vals, ids, k, table.group)

@@ -14,7 +14,7 @@ import torch
 
 from .. import _lib
 
-MR_SCORE_TF32X3, MR_SCORE_TF32X1 = 0, 1
+MR_SCORE_TF32X3, MR_SCORE_TF32X1, MR_SCORE_BF16 = 0, 1, 2
 MAX_FUSED_TOPK = 128
 
 
@@ -38,6 +38,17 @@ def split_tf32(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         _lib.check(lib.mr_split_tf32(_lib.dptr(x), x.numel(), _lib.dptr(hi), _lib.dptr(lo), _lib.stream_handle()),
                    "mr_split_tf32")
     return hi, lo
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of an fp32 tensor, round to nearest even (`mr_to_bf16`): the operand of the bf16-compat mode."""
+    dev = _lib.require_cuda()
+    lib = _lib.load()
+    x = x.to(device=dev, dtype=torch.float32).contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
+    if x.numel():
+        _lib.check(lib.mr_to_bf16(_lib.dptr(x), x.numel(), _lib.dptr(out), _lib.stream_handle()), "mr_to_bf16")
+    return out
 
 
 def topk_merge(vals: torch.Tensor, ids: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -64,28 +75,32 @@ class ShardedItemTable:
     """
 
     def __init__(self, items: torch.Tensor, id_base: int = 0, n_total: Optional[int] = None, group=None,
-                 normalize: bool = False):
+                 normalize: bool = False, bf16: bool = False):
         dev = _lib.require_cuda()
         items = items.to(device=dev, dtype=torch.float32)
         if items.dim() != 2:
             raise ValueError("item table must be (N, E)")
         if normalize:
             items = torch.nn.functional.normalize(items, p=2, dim=-1)  # module/recommender/module.py:74-77
-        self.hi, self.lo = split_tf32(items)
+        self.bf16 = bool(bf16)
+        if self.bf16:      # bf16-compat mode (the reference's default bf16-mixed runs): one bf16 table, no split
+            self.hi, self.lo = to_bf16(items), None
+        else:
+            self.hi, self.lo = split_tf32(items)
         self.n_local, self.dim = items.shape
         self.id_base = int(id_base)
         self.n_total = int(n_total if n_total is not None else self.n_local)
         self.group = group
 
     @classmethod
-    def from_full(cls, items: torch.Tensor, group=None, normalize: bool = False) -> "ShardedItemTable":
+    def from_full(cls, items: torch.Tensor, group=None, normalize: bool = False, bf16: bool = False) -> "ShardedItemTable":
         """Keep this rank's slice of a table every rank can see (host tensor or replicated)."""
         import torch.distributed as dist
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         rank = dist.get_rank(group) if world > 1 else 0
         lo, hi = shard_bounds(items.shape[0], world, rank)
         return cls(items[lo:hi], id_base=lo, n_total=items.shape[0], group=group if world > 1 else None,
-                   normalize=normalize)
+                   normalize=normalize, bf16=bf16)
 
     @property
     def world(self) -> int:

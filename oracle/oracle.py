@@ -272,6 +272,22 @@ def scores_f64(U, I) -> np.ndarray:
     return np.asarray(U, np.float64) @ np.asarray(I, np.float64).T
 
 
+def to_bf16(x) -> np.ndarray:
+    """fp32 -> bf16 -> fp32, round to nearest even (torch's `.to(torch.bfloat16)`)."""
+    u = _f32(x).view(np.uint32).astype(np.uint64)
+    r = (u + np.uint64(0x7FFF) + ((u >> np.uint64(16)) & np.uint64(1))) & np.uint64(0xFFFF0000)
+    nan_inf = (u & np.uint64(0x7F800000)) == np.uint64(0x7F800000)
+    r = np.where(nan_inf, u & np.uint64(0xFFFF0000), r)
+    return r.astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
+def scores_bf16(U, I) -> np.ndarray:
+    """The reference's default pipeline (Lightning precision="bf16-mixed", configs/base.py:41): bf16 operands, fp32
+    accumulation, bf16 result.  Exact (order-independent) whenever the fp32 sum of the bf16 products is exact, e.g.
+    on the grid catalogs; returned as fp32 holding bf16 values."""
+    return to_bf16(to_bf16(U).astype(np.float32) @ to_bf16(I).astype(np.float32).T)
+
+
 def normalize(x) -> np.ndarray:
     """_maybe_normalize for cosine similarity (module.py:74-77): x / max(||x||_2, 1e-12)."""
     x = _f32(x)

@@ -170,6 +170,35 @@ def gen_evaluator():
     save("evaluator", **out)
 
 
+def gen_evaluator_bf16():
+    """The reference's default bf16-mixed pipeline on grid catalogs: scores = (U.bf16 @ I.bf16.T) as torch computes them
+    (bf16 result), canonical ids = stable descending sort, metrics from the reference's own Recall / NDCG objects."""
+    out = {}
+    for case in gc.EVAL_CASES:
+        if case["kind"] != "grid":
+            continue
+        users, items, labels = synth.make_catalog(case["Q"], case["N"], case["E"], kind=case["kind"], seed=case["seed"])
+        scores = T(users).to(torch.bfloat16) @ T(items).to(torch.bfloat16).T
+        assert scores.dtype == torch.bfloat16
+        kmax = max(case["ks"])
+        order = torch.sort(scores.float(), dim=1, descending=True, stable=True)
+        canon = order.indices[:, :kmax]
+        out[f"{case['name']}/canon_topk"] = canon.numpy().astype(np.int32)
+        out[f"{case['name']}/canon_vals"] = order.values[:, :kmax].numpy()
+        tl = T(labels)
+        vals = {}
+        for m in case["metrics"]:
+            for k in case["ks"]:
+                obj = {"RECALL": Recall, "NDCG": NDCG}[m](k)
+                vals[case["prefix"] + obj.name] = obj(y_true=tl, y_pred=canon)
+        out[f"{case['name']}/canon_keys"] = np.array(list(vals.keys()))
+        out[f"{case['name']}/canon_values"] = np.asarray(list(vals.values()), np.float64)
+        # raw torch.topk on the bf16 scores picks the same score multiset per row
+        raw = torch.topk(scores, kmax, dim=1)
+        assert torch.equal(raw.values.float(), order.values[:, :kmax])
+    save("evaluator_bf16", **out)
+
+
 def gen_module_e2e():
     """load_merging_module on the toy encoder + 3 Adam steps on lambda (stack B of SURVEY.md section 3)."""
     from toy_model import ToyEncoder, make_toy_state_dicts
@@ -211,6 +240,7 @@ if __name__ == "__main__":
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
     only = set(sys.argv[1:])   # e.g. `make_golden.py lns` regenerates one file
     for name, fn in [("merge_flat", gen_merge_flat), ("model_merger", gen_model_merger), ("lambda_merge", gen_lambda),
-                     ("ties", gen_ties), ("lns", gen_lns), ("evaluator", gen_evaluator), ("module_e2e", gen_module_e2e)]:
+                     ("ties", gen_ties), ("lns", gen_lns), ("evaluator", gen_evaluator), ("evaluator_bf16", gen_evaluator_bf16),
+                     ("module_e2e", gen_module_e2e)]:
         if not only or name in only:
             fn()

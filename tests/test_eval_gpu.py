@@ -305,3 +305,51 @@ def test_fused_argument_errors():
         Evaluator(["RECALL"], [200]).topk_embeddings(torch.zeros(4, 8), torch.zeros(300, 8))
     with pytest.raises(RuntimeError):
         Evaluator(["RECALL"], [20]).topk_embeddings(torch.zeros(4, 8), torch.zeros(10, 8))
+
+
+# ------------------------------------------------------------------------------------------ bf16-compat mode (8f row 4)
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("case", [c for c in gc.EVAL_CASES if c["kind"] == "grid"], ids=lambda c: c["name"])
+def test_fused_bf16_compat_grid(case, cg, monkeypatch):
+    """bf16 operands, fp32 accumulation, bf16-rounded scores: bit-exact vs the reference's bf16 matmul + stable sort."""
+    from mergerec_b200.evaluator import MR_SCORE_BF16
+    from mergerec_b200.evaluator.sharded import to_bf16
+    monkeypatch.setenv("MR_SCORE_CTA_GROUP", str(cg))
+    g = golden("evaluator_bf16")
+    users, items, labels = synth.make_catalog(case["Q"], case["N"], case["E"], kind=case["kind"], seed=case["seed"])
+    assert np.array_equal(host(to_bf16(dev(users)).float()), orc.to_bf16(users))
+    ev = Evaluator(case["metrics"], case["ks"])
+    vals, ids = ev.topk_embeddings(dev(users), dev(items), mode=MR_SCORE_BF16)
+    assert np.array_equal(host(ids), g[f"{case['name']}/canon_topk"])
+    assert_bit_equal(host(vals), g[f"{case['name']}/canon_vals"], "bf16 scores")
+    res = ev.evaluate_embeddings(dev(users), dev(items), dev(labels), metric_prefix=case["prefix"], mode=MR_SCORE_BF16)
+    assert list(res.keys()) == list(g[f"{case['name']}/canon_keys"])
+    assert np.array_equal(np.asarray(list(res.values()), np.float64), g[f"{case['name']}/canon_values"])
+
+
+def test_fused_bf16_compat_gauss_and_shards():
+    from mergerec_b200.evaluator import MR_SCORE_BF16
+    Q, N, E, k = 300, 20011, 64, 50
+    users, items, _ = synth.make_catalog(Q, N, E, kind="gauss", seed=43)
+    ev = Evaluator(["RECALL"], [k])
+    v, i = ev.topk_embeddings(dev(users), dev(items), mode=MR_SCORE_BF16)
+    v, i = host(v), host(i)
+    ref = orc.to_bf16(users).astype(np.float64) @ orc.to_bf16(items).astype(np.float64).T
+    got = np.take_along_axis(ref, i.astype(np.int64), 1)
+    assert np.abs(v - got).max() <= 2.0 ** -8 * np.abs(got).max(), "each returned score is its pair's bf16-rounded dot product"
+    assert (np.diff(v, axis=1) <= 0).all(), "descending scores"
+    same = np.diff(v, axis=1) == 0
+    assert (np.diff(i, axis=1)[same] > 0).all(), "equal scores in ascending id order"
+    kth = np.sort(orc.to_bf16(ref.astype(np.float32)), axis=1)[:, ::-1][:, k - 1]
+    assert (np.abs(v[:, -1] - kth) <= 2.0 ** -7 * np.abs(kth)).all(), "k-th score within one bf16 step of the oracle's"
+    # shards + merge == single table, bit for bit
+    pv, pi = [], []
+    for r in range(3):
+        a, b = shard_bounds(N, 3, r)
+        tv, ti = ev.topk_embeddings(dev(users), ShardedItemTable(dev(items[a:b]), id_base=a, n_total=N, bf16=True), mode=MR_SCORE_BF16)
+        pv.append(tv)
+        pi.append(ti)
+    mv, mi = topk_merge(torch.stack(pv), torch.stack(pi), k)
+    assert np.array_equal(host(mi), i) and np.array_equal(host(mv).view(np.uint32), v.view(np.uint32))
+    with pytest.raises(ValueError):
+        ev.topk_embeddings(dev(users), ShardedItemTable(dev(items)), mode=MR_SCORE_BF16)   # fp32-split table, bf16 mode

@@ -177,3 +177,17 @@ def test_localize_and_stitch(case):
         diff = (vec.view(np.uint32) != ref_v.view(np.uint32)).any(axis=0)
         assert not (diff & ~at_thr).any()
         assert not ((merged.view(np.uint32) != ref_m.view(np.uint32)) & ~at_thr).any()
+
+
+@pytest.mark.parametrize("case", [c for c in gc.EVAL_CASES if c["kind"] == "grid"], ids=lambda c: c["name"])
+def test_evaluator_bf16_compat(case):
+    """bf16-compat scoring (the reference's default bf16-mixed runs): oracle vs torch's own bf16 matmul + stable sort."""
+    g = golden("evaluator_bf16")
+    users, items, labels = synth.make_catalog(case["Q"], case["N"], case["E"], kind=case["kind"], seed=case["seed"])
+    kmax = max(case["ks"])
+    vals, ids = orc.topk_rows(orc.scores_bf16(users, items), kmax)
+    assert np.array_equal(ids, g[f"{case['name']}/canon_topk"])
+    assert_bit_equal(vals, g[f"{case['name']}/canon_vals"], "bf16 scores")
+    res = orc.evaluate_ids(ids, labels, case["metrics"], case["ks"], case["prefix"])
+    assert list(res.keys()) == list(g[f"{case['name']}/canon_keys"])
+    assert np.array_equal(np.asarray(list(res.values()), np.float64), g[f"{case['name']}/canon_values"])
