@@ -148,7 +148,7 @@ class TiesCfg2(LambdaMergeK8):
     by the layer-wise lambda merge (A4).  Algorithmic bytes per step: (2K+1)*d*4 + (K+2)*d*4."""
 
     name = "ties_cfg2"
-    launches_per_step = 11  # init + 2x(memset+pass+pick) sample + pass + pick + compact + final + build + merge
+    launches_per_step = 12  # own kernels: init, 3 x pass, 3 x pick, cand_hist, compact, final, build, merge
 
     def __init__(self, rank, world, device):
         super().__init__(rank, world, device)
@@ -328,7 +328,7 @@ class EvalCatalog(Workload):
         self.K = int(os.environ.get("MR_BENCH_EVAL_K", 100))
         self.mode = int(os.environ.get("MR_BENCH_EVAL_MODE", 0))
         self.flops = 2.0 * self.Q * self.N * self.E
-        self.launches_per_step = 5 if world == 1 else 6  # split(users), score_topk, [split merge], [shard merge], label_rank
+        self.launches_per_step = 4 if world == 1 else 5  # split_tf32(users), score_topk, topk_merge, [shard merge], label_rank
 
     def config(self):
         return {"workload": f"BASELINE config 5: {self.Q} query seqs x {self.N}-item catalog, E={self.E}, "

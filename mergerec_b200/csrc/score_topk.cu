@@ -537,14 +537,6 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                     const long long c1 = p.dbg ? clock64() : 0;
                     // Phase 1, branch-free: bit j of m = "column c + j may enter the row's list" (cheap superset test:
                     // key(f) > thr implies f > thr_f or f is NaN).  No per-element branches, so the 16 tests overlap.
-                    if (BF16) {   // the reference's bf16 autocast matmul returns bf16 scores: round the fp32 accumulator (RN-even)
-#pragma unroll
-                        for (int j = 0; j < kChunk; ++j) {
-                            const uint32_t u = v[j];
-                            const uint32_t r = ((u & 0x7F800000u) == 0x7F800000u) ? u : u + 0x7FFFu + ((u >> 16) & 1u);
-                            v[j] = r & 0xFFFF0000u;
-                        }
-                    }
                     uint32_t m = 0;
 #pragma unroll
                     for (int j = 0; j < kChunk; ++j) m |= (!(__uint_as_float(v[j]) <= thr_f)) ? (1u << j) : 0u;
@@ -558,6 +550,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                         uint32_t bits = v[0];
 #pragma unroll
                         for (int jj = 1; jj < kChunk; ++jj) bits = (j == jj) ? v[jj] : bits;
+                        if (BF16) {
+                            // the reference's bf16 autocast matmul returns bf16 scores: round the fp32 accumulator
+                            // (RN-even).  Only survivors of the superset test get here -- rounding is monotone and
+                            // thr_f is a bf16 value, so bf16(acc) > thr_f implies acc > thr_f.
+                            if ((bits & 0x7F800000u) != 0x7F800000u) bits += 0x7FFFu + ((bits >> 16) & 1u);
+                            bits &= 0xFFFF0000u;
+                        }
                         const uint32_t key = score_key(__uint_as_float(bits));
                         if (key > thr) my_buf[cnt++] = ((u64)key << 32) | (u64)(0xFFFFFFFFu - (id0 + (uint32_t)j));
                     }
