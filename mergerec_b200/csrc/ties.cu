@@ -125,7 +125,7 @@ __device__ __noinline__ void ties_pass_edge(unsigned char* raw, uint32_t mag, in
 // One streaming pass: per model, count the keys above the bracket, histogram (and optionally store) the keys inside.
 // Per element and model the common path is FSUB, AND, ISUB, compare+count, compare+branch; everything 64-bit lives
 // in ties_pass_edge.  VEC: all pointers 16-byte aligned (128-bit loads); otherwise scalar loads.
-template <int K, bool VEC, bool W, bool COLLECT>
+template <int K, bool VEC, bool W, int COLLECT>
 __global__ void __launch_bounds__(kTiesThreads, K <= 8 ? 3 : 2)
 ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const float* __restrict__ w,
                  int64_t stride, const TiesState* __restrict__ st, PassCounters pc) {
@@ -147,16 +147,16 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 
     uint32_t below[K];  // per-thread count of magnitudes < lo_mag (fits 32 bits: d < 2^32)
     uint32_t visited = 0;  // elements this thread looked at
-    uint32_t nab[K];       // COLLECT: keys at or below the bracket's upper end among those >= lo_mag
     uint32_t mycnt[K];     // COLLECT: keys appended to this thread's private candidate lists
+    uint32_t nab[K];       // COLLECT == 2: keys with a window magnitude that lie below the bracket
     float wreg[K];
     int lom[K];      // bracket bounds in registers: the edge call may touch shared memory, so values read through
     uint32_t span[K];  // `sm` would be reloaded from shared memory for every element
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         below[k] = 0;
-        nab[k] = 0;
         mycnt[k] = 0;
+        nab[k] = 0;
         wreg[k] = W ? w[k] : 1.0f;
         lom[k] = sm.lom[k];
         span[k] = (uint32_t)sm.span[k];
@@ -182,21 +182,28 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 // Rare path.  COLLECT (the one full pass of the fast path): classify against the 64-bit bracket inline, count
 // "not above" in a register and append the key to this thread's private list -- no atomics and no histogram, so
 // the warp never waits on a shared-memory round trip; the histogram of the ~0.7 % collected keys is built
-// afterwards by ties_cand_hist_kernel.  Otherwise (sample / exact passes, which
+// afterwards by ties_cand_hist_kernel (which also corrects the "above" counter).  Otherwise (sample / exact passes, which
 // need the histogram and store nothing): the out-of-line ties_pass_edge.
 #define MR_TIES_EDGE(K_, MAG_, J_)                                              \
     do {                                                                        \
         if ((MAG_) - (uint32_t)lom[K_] <= span[K_]) {                           \
-            if (COLLECT) {                                                      \
-                /* (an "interior magnitude" shortcut that skips the two 64-bit compares measured 15 % slower) */ \
+            if (COLLECT == 1) {                                                 \
+                /* fast path: every key whose MAGNITUDE lies in [lo_mag, hi_mag] goes to the thread-private list: */ \
+                /* no atomic, no shared-memory read, no 64-bit classification here -- ties_cand_hist_kernel sorts */ \
+                /* the few keys outside [lo, hi] (an end magnitude, index on the wrong side) into above / ignore. */ \
+                /* Millions of equal magnitudes overflow the lists: reported, and the exact path takes over.       */ \
+                if (mycnt[K_] < (uint32_t)pc.cand_cap)                          \
+                    pc.cand_keys[((size_t)(K_) * gsz + gtid) * pc.cand_cap + mycnt[K_]] = ties_key((MAG_), (J_)); \
+                ++mycnt[K_];                                                    \
+            } else if (COLLECT == 2) {                                          \
+                /* exact path (bracket already narrowed to <= cand_cap keys): classify against the 64-bit ends */ \
                 const u64 key_ = ties_key((MAG_), (J_));                        \
-                if (key_ <= sm.hi[K_]) {                                        \
-                    ++nab[K_];                                                  \
-                    if (key_ >= sm.lo[K_]) { /* thread-private list: no atomic, no wait */ \
-                        if (mycnt[K_] < (uint32_t)pc.cand_cap)                  \
-                            pc.cand_keys[((size_t)(K_) * gsz + gtid) * pc.cand_cap + mycnt[K_]] = key_; \
-                        ++mycnt[K_];                                            \
-                    }                                                           \
+                if (key_ < sm.lo[K_]) {                                         \
+                    ++nab[K_]; /* below the bracket: not "above", and not collected (the hist kernel cannot see it) */ \
+                } else if (key_ <= sm.hi[K_]) {                                 \
+                    if (mycnt[K_] < (uint32_t)pc.cand_cap)                      \
+                        pc.cand_keys[((size_t)(K_) * gsz + gtid) * pc.cand_cap + mycnt[K_]] = key_; \
+                    ++mycnt[K_];                                                \
                 }                                                               \
             } else {                                                            \
                 ties_pass_edge<K, false>(smem_raw, (MAG_), (J_), (K_), pc.cand_keys, pc.cand_cap); \
@@ -250,7 +257,8 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 #undef MR_TIES_MAG
 #undef MR_TIES_EDGE
 
-    // above = (#magnitudes >= lo_mag) - (#of those that turned out not to be above the bracket)
+    // above = (#magnitudes >= lo_mag) - (#of those that turned out not to be above the bracket); in a COLLECT pass the
+    // second term is subtracted later by ties_cand_hist_kernel, which sees every collected key
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         uint32_t v = visited - below[k] - nab[k];
@@ -276,27 +284,37 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 // ---- histogram of the keys collected by the full pass (replaces per-element histogram atomics in that pass) ----------
 __global__ void __launch_bounds__(256)
 ties_cand_hist_kernel(const TiesState* __restrict__ st, const uint32_t* __restrict__ cand_cnt,
-                      const u64* __restrict__ cand_keys, int cand_cap, int n_lists, uint32_t* __restrict__ hist) {
+                      const u64* __restrict__ cand_keys, int cand_cap, int n_lists, uint32_t* __restrict__ hist,
+                      u64* __restrict__ above) {
     __shared__ uint32_t s_hist[kTiesBins];
+    __shared__ uint32_t s_not_above;
     const int k = blockIdx.y;
     const TiesState s = st[k];
     if (s.status != TIES_ST_SEARCH) return;
     for (int i = threadIdx.x; i < kTiesBins; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_not_above = 0;
     __syncthreads();
+    uint32_t not_above = 0;   // collected keys <= hi: the pass counted every collected key as "above"
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_lists; c += gridDim.x * blockDim.x) {   // one list per thread
         uint32_t n = cand_cnt[(size_t)k * n_lists + c];
         if (n > (uint32_t)cand_cap) n = (uint32_t)cand_cap;   // overflow is reported by ties_compact_kernel
         const u64* keys = cand_keys + ((size_t)k * n_lists + c) * cand_cap;
         for (uint32_t e = 0; e < n; ++e) {
-            const u64 key = keys[e];                            // every stored key lies inside [lo, hi]
-            atomicAdd(&s_hist[(uint32_t)((key - s.lo) >> s.shift)], 1u);
+            const u64 key = keys[e];     // magnitude inside [lo_mag, hi_mag]; the key itself may fall just outside [lo, hi]
+            if (key > s.hi) continue;
+            ++not_above;
+            if (key >= s.lo) atomicAdd(&s_hist[(uint32_t)((key - s.lo) >> s.shift)], 1u);
         }
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) not_above += __shfl_xor_sync(0xffffffffu, not_above, off);
+    if ((threadIdx.x & 31) == 0 && not_above) atomicAdd(&s_not_above, not_above);
     __syncthreads();
     for (int i = threadIdx.x; i < kTiesBins; i += blockDim.x) {
         const uint32_t v = s_hist[i];
         if (v) atomicAdd(&hist[k * kTiesBins + i], v);
     }
+    if (threadIdx.x == 0 && s_not_above) atomicAdd(&above[k], (u64)0 - (u64)s_not_above);   // two's-complement subtract
 }
 
 // ---- pick: turn a histogram into a narrower bracket ---------------------------------------------------
@@ -763,7 +781,7 @@ static TiesWs ties_layout(void* ws, int64_t d, int K) {
 
 template <int K>
 static int ties_launch_pass(const float* base, const float* const* models, int64_t d, const float* w, int64_t stride,
-                            bool collect, const TiesWs& L, cudaStream_t st) {
+                            int collect /* 0 none, 1 magnitude window (fast path), 2 exact */, const TiesWs& L, cudaStream_t st) {
     PtrPack<K> pack;
     bool vec = host_aligned16(base);
     for (int k = 0; k < K; ++k) { pack.p[k] = models[k]; vec = vec && host_aligned16(models[k]); }
@@ -779,11 +797,11 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
         kern<<<blocks, kTiesThreads, smem, st>>>(base, pack, d, w, stride, L.st, pc);                          \
     } while (0)
     if (vec) {
-        if (w) { if (collect) MR_PASS(true, true, true); else MR_PASS(true, true, false); }
-        else   { if (collect) MR_PASS(true, false, true); else MR_PASS(true, false, false); }
+        if (w) { if (collect == 1) MR_PASS(true, true, 1); else if (collect == 2) MR_PASS(true, true, 2); else MR_PASS(true, true, 0); }
+        else   { if (collect == 1) MR_PASS(true, false, 1); else if (collect == 2) MR_PASS(true, false, 2); else MR_PASS(true, false, 0); }
     } else {
-        if (w) { if (collect) MR_PASS(false, true, true); else MR_PASS(false, true, false); }
-        else   { if (collect) MR_PASS(false, false, true); else MR_PASS(false, false, false); }
+        if (w) { if (collect == 1) MR_PASS(false, true, 1); else if (collect == 2) MR_PASS(false, true, 2); else MR_PASS(false, true, 0); }
+        else   { if (collect == 1) MR_PASS(false, false, 1); else if (collect == 2) MR_PASS(false, false, 2); else MR_PASS(false, false, 0); }
     }
 #undef MR_PASS
     MR_CUDA_LAUNCH_CHECK("mr_ties_select(pass)");
@@ -793,7 +811,7 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
 static int ties_finish(const TiesWs& L, int K, int64_t k_cnt, u64* cut, int32_t* status, cudaStream_t st) {
     {
         dim3 hgrid(128, (unsigned)K);
-        ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.hist);
+        ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.hist, L.above);
     }
     ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, k_cnt, k_cnt, 1, status);
     dim3 grid(256, (unsigned)K);
@@ -848,11 +866,11 @@ extern "C" int mr_ties_select(const float* base, const float* const* models, int
     ties_sample_ranks(d, k_cnt, n_s, &r_hi, &r_lo);
     MR_DISPATCH_K(K, {
         for (int it = 0; it < 2; ++it) {  // two sample passes: 2^63 -> quarter-octave bins -> ~1 % bracket
-            rc = ties_launch_pass<KK>(base, models, d, w, stride, false, L, st);
+            rc = ties_launch_pass<KK>(base, models, d, w, stride, 0, L, st);
             if (rc != MR_OK) return rc;
             ties_pick_kernel<<<KK, kTiesBins, 0, st>>>(L.st, L.hist, L.above, r_hi, r_lo, 0, status);
         }
-        rc = ties_launch_pass<KK>(base, models, d, w, 1, true, L, st);
+        rc = ties_launch_pass<KK>(base, models, d, w, 1, 1, L, st);
         if (rc != MR_OK) return rc;
     });
     return ties_finish(L, K, k_cnt, reinterpret_cast<u64*>(cut), status, st);
@@ -875,7 +893,7 @@ extern "C" int mr_ties_select_exact(const float* base, const float* const* model
     TiesState host[MR_MAX_K];
     for (int it = 0; it < 8; ++it) {
         MR_DISPATCH_K(K, {
-            rc = ties_launch_pass<KK>(base, models, d, w, 1, false, L, st);
+            rc = ties_launch_pass<KK>(base, models, d, w, 1, 0, L, st);
             if (rc != MR_OK) return rc;
             ties_pick_kernel<<<KK, kTiesBins, 0, st>>>(L.st, L.hist, L.above, k_cnt, k_cnt, 1, status);
         });
@@ -890,7 +908,7 @@ extern "C" int mr_ties_select_exact(const float* base, const float* const* model
         if (fits) break;
     }
     MR_DISPATCH_K(K, {
-        rc = ties_launch_pass<KK>(base, models, d, w, 1, true, L, st);
+        rc = ties_launch_pass<KK>(base, models, d, w, 1, 2, L, st);
         if (rc != MR_OK) return rc;
     });
     rc = ties_finish(L, K, k_cnt, reinterpret_cast<u64*>(cut), status, st);
