@@ -170,3 +170,51 @@ def test_lambda_grad_full_size_blair_base():
         want[grp[p]] += T[:, o:o + n].double() @ grad[o:o + n].double()
     scale = want.abs().max()
     assert (got - want).abs().max() <= LAMBDA_GRAD_RTOL * scale
+
+
+def test_merge_test_flow_from_files(tmp_path):
+    """Stack A of SURVEY.md section 3 from the reference's on-disk formats: extracted state_dict.pt files (one
+    "model." prefix too many, item_embeddings inside) -> load_merging_module -> weight file ("average" and a jsonl
+    log line) -> get_state_dict, against the oracle's task-arithmetic merge of the same tensors."""
+    from toy_model import ToyEncoder, make_toy_state_dicts
+    from mergerec_b200 import io as mio
+    from mergerec_b200.merger.enums import LearnType, MergeType
+    from mergerec_b200.merger.weight_learning.module import load_merging_module
+    K = 3
+    pre, fts = make_toy_state_dicts(K, seed=91)
+    paths = []
+    for k, ft in enumerate(fts):
+        sd = {"model." + n: v for n, v in ft.items()}
+        sd["item_embeddings"] = torch.randn(5, 24)
+        p = tmp_path / f"domain{k}" / "state_dict.pt"
+        p.parent.mkdir()
+        torch.save(sd, p)
+        paths.append(p)
+    loaded = mio.load_finetuned_state_dicts(paths)
+    assert all(list(sd.keys()) == list(pre.keys()) for sd in loaded)
+    torch.manual_seed(5)
+    model = ToyEncoder()
+    model.load_state_dict(pre)
+    mod = load_merging_module(MergeType.TASK_VECTOR, LearnType.TASK_WISE, model, model.state_dict(), loaded,
+                              ignore_keys=set(), disable_softmax=True)
+    keys = list(pre.keys())
+    fb = np.concatenate([pre[k].numpy().reshape(-1).astype(np.float32) for k in keys])
+    fm = [np.concatenate([ft[k].numpy().reshape(-1).astype(np.float32) for k in keys]) for ft in fts]
+    T = orc.task_vectors(fb, fm)
+
+    def merged_flat():
+        sd = mod.get_state_dict()
+        return np.concatenate([sd[k].detach().cpu().numpy().reshape(-1) for k in keys])
+
+    mod.load_weights_from_dict(mio.resolve_weights("average", 0, K))
+    w = np.full((1, K), np.float32(1.0) * np.float32(1.0 / K) + np.float32(0.0), np.float32)
+    assert_bit_equal(merged_flat(), orc.lambda_merge(fb, T, w), "average weights")
+    with mio.WeightLog("v1", tmp_path / "weights", log_every_steps=1) as log:
+        mod.load_weights_from_dict({"global_weights": {"all": [1.0]}, "global_biases": {"all": [0.0]},
+                                    "per_weights": {"all": [0.7, 0.2, 0.4]}})
+        log.on_train_batch_end(0, 0, 0, mod)
+        mod.load_weights_from_dict(mio.resolve_weights("uniform", 0.3, K))
+        log.on_train_batch_end(0, 1, 1, mod)
+    mod.load_weights_from_dict(mio.resolve_weights(tmp_path / "weights" / "v1.jsonl", 0, K))
+    w = np.asarray([[0.7, 0.2, 0.4]], np.float32)
+    assert_bit_equal(merged_flat(), orc.lambda_merge(fb, T, w), "line 0 of the lambda log")
