@@ -103,6 +103,26 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
 
 
+def use_all_host_threads() -> int:
+    """The CPU arms use every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would otherwise
+    serialise the OpenMP oracle and numpy's BLAS.  Returns the thread count in effect."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    from oracle import oracle as orc
+    orc.set_threads(n)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+    except Exception:  # noqa: BLE001
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -180,7 +200,10 @@ def run_ours(args):
 
     roof = wl.roofline(measured_peaks()) if rank == 0 else None
     clocks = sampler.stop() if rank == 0 else None
-    cpu = wl.cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        use_all_host_threads()
+        cpu = wl.cpu_baseline()
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -211,6 +234,7 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
+    use_all_host_threads()
     wl = WORKLOADS[args.workload](rank=0, world=1, device=None)
     res = wl.reference_arm(steps=args.steps, warmup=args.warmup)
     line = {
