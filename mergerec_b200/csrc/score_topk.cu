@@ -13,11 +13,12 @@
 // tiles, each CTA stages its own 128 query rows and half of the item tile) walks a static unit list ordered so
 // that concurrently running units share item tiles through L2 while their query blocks stay L2-resident.
 // Warp roles per CTA: 0 = TMA producer, 1 = MMA issuer (leader CTA of a pair only), 2 = TMEM allocator,
-// 4..7 = epilogue: thread t owns accumulator lane (= query row) t, filters the 256 scores of a tile against the
-// row's running threshold (score of its K-th best so far) and appends survivors to a per-row candidate buffer in
-// global memory (L2-resident); when a buffer fills, the warp sorts it cooperatively in shared memory (bitonic,
-// 64-bit keys = (score desc, id asc)) and keeps the best K.  After its last tile a unit writes one sorted list
-// per row; lists of different splits are merged by mr_topk_merge.
+// 4..7 = epilogue: thread t owns accumulator lane (= query row) t, tests the 256 scores of a tile branch-free against
+// the row's running threshold (score of its K-th best so far) and appends survivors to a per-row candidate buffer
+// in global memory (L2-resident); when a buffer fills, the warp finds the row's K-th largest score with a register
+// bitonic network (8 keys per lane, shuffles across lanes, two rows interleaved) and keeps what is at or above it.
+// After its last tile a unit sorts each row by the 64-bit key (score desc, id asc) and writes one list per row;
+// lists of different splits are merged by mr_topk_merge.
 //
 // Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i + 1.
 #include <cuda.h>
@@ -336,15 +337,6 @@ __device__ __forceinline__ void warp_store_keys(u64* gbuf, const u64 (&v)[8], in
             o4[h] = make_uint4((uint32_t)v[2 * h], (uint32_t)(v[2 * h] >> 32), (uint32_t)v[2 * h + 1],
                                (uint32_t)(v[2 * h + 1] >> 32));
 }
-// sorted element e (warp-uniform index) broadcast to every lane
-__device__ __forceinline__ u64 warp_pick(const u64 (&v)[8], int e) {
-    u64 x = 0;
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-        if (r == (e & 7)) x = v[r];
-    return __shfl_sync(0xffffffffu, x, e >> 3);
-}
-
 // sorted registers -> one (val, id) list of K entries; keys are zero beyond the row's candidates
 __device__ __forceinline__ void warp_write_list(const Params& p, size_t o, const u64 (&v)[8], int K, int lane) {
 #pragma unroll
