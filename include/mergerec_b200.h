@@ -64,8 +64,9 @@ enum mr_merge_order {
  *                 computed on the fly) or task-vector rows (src_is_model = 0, u_k = src_k).
  *   w             dev, (G, K) row-major fp32 lambdas; row g applies to blocks with seg_group == g.
  *   seg_end       dev, P ascending exclusive block ends (seg_end[P-1] == d), or NULL when P == 1
- *                 (one block [0, d), group 0).  Blocks are the reference's sum(dim=0) operands:
- *                 the whole vector for task-wise, one state_dict tensor each for layer-wise.
+ *                 (one block [0, d), group 0; a one-entry table with a seg_group is honoured too).  Blocks are the
+ *                 reference's sum(dim=0) operands: the whole vector for task-wise, one state_dict tensor each for
+ *                 layer-wise.
  *   seg_group     dev, P group ids in [0, G), or NULL when P == 1.
  *   out           dev, d floats.  May alias base. */
 int mr_merge_axpy(const float* base, const float* const* src, int K, int64_t d, const float* w, int G,

@@ -146,7 +146,7 @@ static int launch_merge(const float* base, const float* const* src, int64_t d, c
         pack.p[k] = src[k];
         vec = vec && host_aligned16(src[k]);
     }
-    const bool segmented = (P > 1);
+    const bool segmented = (P > 1) || (seg_end && seg_group);   // a one-block table may still name a group other than 0
     SegView sv{seg_end, seg_group, segmented ? P : 0};
     size_t smem = ((size_t)(G * K * 4 + 15) & ~(size_t)15) + (segmented ? (size_t)P * 12 : 0) + 16;
     const int64_t work = vec ? (d >> 2) + 3 : d;

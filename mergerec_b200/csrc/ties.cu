@@ -624,7 +624,7 @@ __device__ __forceinline__ void ties_quad(const float* __restrict__ base, const 
     } else {  // FUSED_MERGE: base + sum_dim0_k(w[g,k] * That[k])  (layer_wise.py:76-82 order, blocks = tensors)
         float r[4];
         int p = 0;
-        if (fs.P > 1) {
+        if (fs.end) {
             // first block with end > j0
             if (!(j0 < fs.end[hint] && (hint == 0 || j0 >= fs.end[hint - 1]))) {
                 int lo = 0, hi = fs.P - 1;
@@ -637,7 +637,7 @@ __device__ __forceinline__ void ties_quad(const float* __restrict__ base, const 
         for (int c = 0; c < 4; ++c) {
             bool tail;
             const float* wrow = fs.w;
-            if (fs.P > 1) {
+            if (fs.end) {
                 while (c < nvalid && j0 + c >= fs.end[p]) ++p;
                 const int64_t beg = p ? fs.end[p - 1] : 0;
                 const int64_t n = fs.end[p] - beg;
@@ -689,12 +689,13 @@ ties_build_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, 
         const int G = (int)a.ldo;  // number of lambda groups travels in ldo for this mode
         float* s_w = reinterpret_cast<float*>(smem_raw);
         int64_t* s_end = reinterpret_cast<int64_t*>(smem_raw + ((G * K * 4 + 15) & ~15));
-        int32_t* s_grp = reinterpret_cast<int32_t*>(s_end + (a.P > 1 ? a.P : 0));
+        const bool table = a.seg_end && a.seg_group;   // a one-block table may still name a group other than 0
+        int32_t* s_grp = reinterpret_cast<int32_t*>(s_end + (table ? a.P : 0));
         for (int i = threadIdx.x; i < G * K; i += blockDim.x) s_w[i] = a.w[i];
-        if (a.P > 1)
+        if (table)
             for (int i = threadIdx.x; i < a.P; i += blockDim.x) { s_end[i] = a.seg_end[i]; s_grp[i] = a.seg_group[i]; }
         __syncthreads();
-        fs = FusedSegs{s_w, s_end, s_grp, a.P};
+        fs = FusedSegs{s_w, table ? s_end : nullptr, table ? s_grp : nullptr, a.P};
     }
     const int64_t nq = (d + 3) >> 2;
     // hot quads: complete and (for K >= 5) before the interleaved-order tail of the flat vector
@@ -943,7 +944,7 @@ extern "C" int mr_ties_build(const float* base, const float* const* models, int 
     BuildArgs a{out, mode == TIES_MODE_FUSED_MERGE ? (int64_t)G : ldo, trim_mask, elect_mask, w, seg_end, seg_group,
                 mode == TIES_MODE_FUSED_MERGE ? P : 1};
     size_t smem = 16;
-    if (mode == TIES_MODE_FUSED_MERGE) smem = (((size_t)G * K * 4 + 15) & ~(size_t)15) + (P > 1 ? (size_t)P * 12 : 0) + 16;
+    if (mode == TIES_MODE_FUSED_MERGE) smem = (((size_t)G * K * 4 + 15) & ~(size_t)15) + ((seg_end && seg_group) ? (size_t)P * 12 : 0) + 16;
 #define MR_BUILD(MODE, VEC, MASKS) \
     ties_build_kernel<KK, MODE, VEC, MASKS><<<(unsigned)blocks, kTiesThreads, smem, st>>>(base, pack, d, reinterpret_cast<const u64*>(cut), a)
 #define MR_BUILD_VM(MODE)                                                        \
