@@ -445,5 +445,147 @@ class EvalCatalog(Workload):
         return {"value": n / t, "ms_per_step": t * 1e3, "cores": cores, "sample": self._cpu_sample}
 
 
-WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8, TiesCfg2.name: TiesCfg2, EvalCatalog.name: EvalCatalog}
+class CollabStepCfg3(Workload):
+    """BASELINE config 3: one MergeRec collaborative-merging optimisation step at K = 8 BLaIR-base (RoBERTa-base)
+    domains -- layer-wise lambda merge (A4) into one flat buffer whose slices become the encoder's parameters,
+    encoder forward + backward in PyTorch on a pseudo-user batch (16 sequences x 512 tokens), lambda-gradient
+    reduction (A5), Adam on lambda (stack B of SURVEY.md section 3; `load_merging_module` + `DistillSequenceModule`'s
+    optimiser set-up, sequence/module.py:94-100).  The two kernels of this package are timed inside the step and
+    alone; the encoder is stock HF RoBERTa under bf16 autocast like the reference's Trainer (configs/base.py:41)."""
+
+    name = "collab_cfg3"
+    metric = "collaborative-merging steps/sec (lambda merge + encoder fwd/bwd + lambda-gradient + Adam)"
+    unit = "steps/s"
+    dtype = "f32 merge / lambda-gradient, bf16-autocast encoder"
+    K = 8
+    launches_per_step = 3   # merge_kernel, lg_partial_kernel, lg_finish kernel (the encoder's kernels are PyTorch's)
+    e2e_steps_cap = 3
+
+    def __init__(self, rank, world, device):
+        super().__init__(rank, world, device)
+        self.B, self.L = 16, 512
+        self.shapes = synth.roberta_shapes()
+        self.d = synth.total_numel(self.shapes)
+
+    def config(self):
+        return {"workload": "BASELINE config 3: collaborative merging step, K=8 BLaIR-base (RoBERTa-base, d=124,645,632), "
+                            "layer-wise lambda (G=13), batch 16 x 512 tokens, Adam(lr 1e-3) on lambda",
+                "K": self.K, "d": self.d, "batch": self.B, "seq_len": self.L,
+                "l2": "4.5 GB of task vectors per merge / gradient pass exceed L2",
+                "parallelism": f"data-parallel replicas x{self.world} (lambda-gradient all-reduce of G x K floats)"
+                if self.world > 1 else "1 GPU"}
+
+    def setup(self):
+        import torch.distributed as dist
+        from transformers import RobertaConfig, RobertaModel
+        from mergerec_b200.merger.enums import LearnType, MergeType
+        from mergerec_b200.merger.weight_learning.module import load_merging_module
+
+        class Wrapped(torch.nn.Module):      # the reference's BaseEncoderModel keeps the HF model under `.model`
+            def __init__(self, hf):
+                super().__init__()
+                self.model = hf
+
+            def forward(self, ids):
+                return self.model(input_ids=ids).last_hidden_state[:, 0]   # CLS pooling (encoder/_base.py:32-39)
+
+        torch.manual_seed(0)
+        cfg = RobertaConfig(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1, pad_token_id=1,
+                            layer_norm_eps=1e-5, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        model = Wrapped(RobertaModel(cfg, add_pooling_layer=True)).to(self.device)
+        pre = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        g = torch.Generator(device=self.device).manual_seed(100 + self.rank)
+        fts = [{k: (v + 1e-3 * torch.randn(v.shape, generator=g, device=self.device)) if v.is_floating_point() else v.clone()
+                for k, v in pre.items()} for _ in range(self.K)]
+        self.module = load_merging_module(MergeType.TASK_VECTOR, LearnType.LAYER_WISE, model, pre, fts, ignore_keys=set(),
+                                          initial_per_weight=0.2, disable_softmax=True)
+        del fts, pre
+        self.opt = torch.optim.Adam(self.module.trainable_parameters(True, True, False), lr=1e-3)
+        self.ids = torch.randint(3, 50000, (self.B, self.L), generator=g, device=self.device)
+        self.group = dist.group.WORLD if self.world > 1 else None
+        self.loss = None
+
+    def step(self):
+        import torch.distributed as dist
+        self.opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            rep = self.module(self.ids)
+        loss = rep.float().square().mean()
+        loss.backward()
+        if self.group is not None:
+            for p in self.module.per_weights.parameters():
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
+        self.opt.step()
+        self.loss = loss.detach()
+
+    def units_per_step_all_ranks(self):
+        return float(self.world)
+
+    def setup_e2e(self):
+        self.h_ids = _pinned(self.ids.cpu())
+        self.h2d_bytes = self.h_ids.numel() * 8
+        self.d2h_bytes = 4
+
+    def step_e2e(self):
+        self.ids.copy_(self.h_ids, non_blocking=True)
+        self.step()
+        float(self.loss)      # device -> host read of the step's loss
+
+    def roofline(self, peaks):
+        from bench import event_time_ms
+        from mergerec_b200.merger.weight_learning.module._base import _lambda_grad
+        m = self.module
+        w = m._effective_weights().detach()
+        ms_merge = event_time_ms(lambda: m._merge_flat(w), 10)
+        _, seg_group, keys = m._blocks()
+        grad = torch.randn(self.d, device=self.device)
+        grads = [grad[o:o + n] for o, n in zip(m._layout.offsets, m._layout.sizes)]
+        ms_grad = event_time_ms(lambda: _lambda_grad(grads, m._layout, m._task_rows(), seg_group, len(keys)), 10)
+        ms_step = event_time_ms(self.step, 3)
+        bytes_merge, bytes_grad = (self.K + 2) * self.d * 4, (self.K + 1) * self.d * 4
+        ach = bytes_grad / GB / (ms_grad * 1e-3)
+        return {"bound": "hbm", "kernel": "mr::lg_partial_kernel<8> (+ finish): lambda-gradient reduction (A5)",
+                "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms_grad,
+                "algorithmic_bytes_per_launch": bytes_grad,
+                "other_kernels": {"lambda merge forward (merge_kernel, A4)": {"ms": ms_merge, "GB/s": bytes_merge / GB / (ms_merge * 1e-3), "bytes": bytes_merge}},
+                "step_ms": ms_step, "merge_plus_grad_share_of_step": (ms_merge + ms_grad) / ms_step}
+
+    def extra(self):
+        return {"loss": None if self.loss is None else float(self.loss),
+                "per_weights": {k: [round(x, 6) for x in v.tolist()] for k, v in list(self.module.per_weights.items())[:2]}}
+
+    # -- CPU arm: the oracle port of the two merger kernels of the step (the encoder is PyTorch on both sides)
+    def _cpu_time(self, reps):
+        from oracle import oracle as orc
+        rng = np.random.Generator(np.random.PCG64(7))
+        d = self.d
+        base = rng.standard_normal(d, dtype=np.float32) * np.float32(0.02)
+        T = rng.standard_normal((self.K, d), dtype=np.float32) * np.float32(1e-3)
+        sb, se, sg, keys = orc.segment_table(self.shapes, layer_wise=True)
+        w = rng.uniform(0.1, 0.5, size=(len(keys), self.K)).astype(np.float32)
+        grad = rng.standard_normal(d, dtype=np.float32)
+        ts = []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            orc.lambda_merge(base, T, w, sb, se, sg)
+            orc.lambda_grad(grad, T, len(keys), sb, se, sg)
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts[1:])), orc.max_threads()
+
+    def cpu_baseline(self):
+        t, cores = self._cpu_time(2)
+        return {"value": 1.0 / t, "unit": self.unit, "cores": cores, "kind": "port",
+                "sample": "the step's two merger passes only (lambda merge + lambda-gradient, full d, K=8), OpenMP C oracle "
+                          "port; the encoder forward/backward is not included on the CPU side",
+                "seconds_per_step": t}
+
+    def reference_arm(self, steps, warmup):
+        t, cores = self._cpu_time(max(1, min(steps, 3)))
+        return {"value": 1.0 / t, "ms_per_step": t * 1e3, "cores": cores,
+                "sample": "the step's two merger passes only (lambda merge + lambda-gradient, full d, K=8), OpenMP C oracle port"}
+
+
+WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8, TiesCfg2.name: TiesCfg2, EvalCatalog.name: EvalCatalog,
+             CollabStepCfg3.name: CollabStepCfg3}
 DEFAULT_WORKLOAD = TiesCfg2.name
