@@ -586,6 +586,109 @@ class CollabStepCfg3(Workload):
                 "sample": "the step's two merger passes only (lambda merge + lambda-gradient, full d, K=8), OpenMP C oracle port"}
 
 
+class DistillStep(Workload):
+    """The distillation half of a collaborative-merging step (reference:
+    module/distiller/sequence/module.py:59-76 + loss_fn.py KD loss): catalogue logits of 16 pseudo-user representations
+    against their domains' item tables (8 domains x 25,000 items, E = 768 -- the per-domain share of BASELINE config 4's
+    200K-item union catalogue), KD loss against device-resident teacher logits, gradient w.r.t. the representations.
+    Algorithmic bytes per step: every used item table once in the forward and once in the backward pass."""
+
+    name = "distill_step"
+    metric = "distillation samples/sec (catalogue logits + KD loss + representation gradient)"
+    unit = "samples/s"
+    dtype = "f32"
+    launches_per_step = 4     # ds_logits, ds_loss, ds_grad, ds_grad_finish
+    D, N, E, B, NSEQ = 8, 25000, 768, 16, 512
+
+    def config(self):
+        return {"workload": "distillation step: 16 samples over 8 domains x 25,000 items, E=768, KD loss (T=2), "
+                            "teacher logits device-resident (512 sequences per domain)",
+                "B": self.B, "domains": self.D, "items_per_domain": self.N, "E": self.E,
+                "l2": "item tables (614 MB) exceed L2", "parallelism": f"data-parallel replicas x{self.world}" if self.world > 1 else "1 GPU"}
+
+    def setup(self):
+        from mergerec_b200.module.distiller import TeacherScores
+        from mergerec_b200.module.recommender.loss_fn import DistillKDLoss
+        g = torch.Generator(device=self.device).manual_seed(77 + self.rank)
+        mk = lambda *shape: torch.randn(*shape, generator=g, device=self.device)
+        t_items = [mk(self.N, self.E) for _ in range(self.D)]
+        t_seqs = [mk(self.NSEQ, self.E) for _ in range(self.D)]
+        self.teacher = TeacherScores(t_items, t_seqs)
+        self.tables = [torch.nn.functional.normalize(t, dim=-1) + 0.02 * mk(self.N, self.E) for t in t_items]
+        self.dom = [b % self.D for b in range(self.B)]
+        self.seq_ids = [int(x) for x in torch.randint(0, self.NSEQ, (self.B,), generator=g, device=self.device).tolist()]
+        self.rep = torch.nn.functional.normalize(torch.stack([t_seqs[d][s] for d, s in zip(self.dom, self.seq_ids)]) + 0.3 * mk(self.B, self.E), dim=-1)
+        self.rep.requires_grad_(True)
+        self.spec = DistillKDLoss(2.0).spec
+        _, self.ptrs = self.teacher.rows(self.dom, self.seq_ids)
+        self.bytes_tables = self.D * self.N * self.E * 4
+        self.loss = None
+
+    def step(self):
+        from mergerec_b200.module.distiller.sequence.module import fused_distill_losses
+        self.rep.grad = None
+        loss = fused_distill_losses(self.rep, self.tables, self.dom, self.ptrs, self.spec).mean()
+        loss.backward()
+        self.loss = loss.detach()
+
+    def units_per_step_all_ranks(self):
+        return float(self.B * self.world)
+
+    def setup_e2e(self):
+        self.h_rep = _pinned(self.rep.detach().cpu())
+        self.h_grad = torch.empty((self.B, self.E), dtype=torch.float32, pin_memory=True)
+        self.h2d_bytes = self.B * self.E * 4
+        self.d2h_bytes = self.B * self.E * 4 + 4
+
+    def step_e2e(self):
+        with torch.no_grad():
+            self.rep.copy_(self.h_rep, non_blocking=True)
+        _, self.ptrs = self.teacher.rows(self.dom, self.seq_ids)
+        self.step()
+        self.h_grad.copy_(self.rep.grad, non_blocking=True)
+        float(self.loss)
+
+    def roofline(self, peaks):
+        from bench import event_time_ms
+        from mergerec_b200.module.distiller.sequence.module import distill_logits
+        rep = self.rep.detach()
+        out = distill_logits(rep, self.tables, self.dom)
+        ms = event_time_ms(lambda: distill_logits(rep, self.tables, self.dom, out=out), 20)
+        ms_step = event_time_ms(self.step, 10)
+        ach = self.bytes_tables / GB / (ms * 1e-3)
+        return {"bound": "hbm", "kernel": "mr::ds_logits_kernel<6, 2> (catalogue logits, every item table read once)",
+                "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
+                "algorithmic_bytes_per_launch": self.bytes_tables, "step_ms": ms_step,
+                "step_GB/s (tables read twice)": 2 * self.bytes_tables / GB / (ms_step * 1e-3)}
+
+    def extra(self):
+        return {"loss": None if self.loss is None else float(self.loss)}
+
+    def _cpu_time(self, reps):
+        from oracle import oracle as orc
+        rng = np.random.Generator(np.random.PCG64(7))
+        tables = [rng.standard_normal((self.N, self.E), dtype=np.float32) * np.float32(0.05) for _ in range(self.D)]
+        rep = rng.standard_normal((self.B, self.E), dtype=np.float32)
+        trows = [rng.standard_normal(self.N, dtype=np.float32) for _ in range(self.B)]
+        ts = []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            orc.distill_step(rep, tables, self.dom if hasattr(self, "dom") else [b % self.D for b in range(self.B)], trows, "KD", temperature=2.0)
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts[1:])), os.cpu_count() or 1
+
+    def cpu_baseline(self):
+        t, cores = self._cpu_time(2)
+        return {"value": self.B / t, "unit": self.unit, "cores": cores, "kind": "port",
+                "sample": "the full step (16 samples, 8 x 25,000 x 768 tables), numpy fp64 oracle port (BLAS threads)", "seconds_per_step": t}
+
+    def reference_arm(self, steps, warmup):
+        t, cores = self._cpu_time(max(1, min(steps, 3)))
+        return {"value": self.B / t, "ms_per_step": t * 1e3, "cores": cores,
+                "sample": "the full step (16 samples, 8 x 25,000 x 768 tables), numpy fp64 oracle port"}
+
+
 WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8, TiesCfg2.name: TiesCfg2, EvalCatalog.name: EvalCatalog,
-             CollabStepCfg3.name: CollabStepCfg3}
+             CollabStepCfg3.name: CollabStepCfg3, DistillStep.name: DistillStep}
 DEFAULT_WORKLOAD = TiesCfg2.name

@@ -198,6 +198,59 @@ int mr_split_tf32(const float* x, int64_t n, float* hi, float* lo, mr_stream_t s
 int mr_scores_fp32(const float* U, int64_t Q, const float* I, int64_t N, int E, float* out, int64_t ldo,
                    mr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Distillation step between merger and evaluator: per-sample catalogue
+ * logits of the merged model, loss against the single-domain ("teacher") logits, gradient w.r.t. the
+ * merged model's representations.   ref: module/distiller/sequence/module.py:59-76 (_forward_distill),
+ * module/recommender/loss_fn.py:36-231, merge_train.py:116-126 (teacher logits from normalised embeddings).
+ * Floating-point contract: fp32 arithmetic, fp64 block sums; compared at 2e-5 relative, not bit-exact.
+ * ---------------------------------------------------------------------------------------------- */
+#define MR_DISTILL_MAX_B 128     /* samples per call */
+#define MR_DISTILL_MAX_GROUPS 64 /* (domain, up to 4 samples) groups per call */
+#define MR_DISTILL_MAX_E 1024
+
+enum mr_distill_loss_type { /* ref: merger/enums.py LossType + the two extra classes of loss_fn.py */
+    MR_LOSS_CE = 0,
+    MR_LOSS_KD = 1,
+    MR_LOSS_MSE = 2,
+    MR_LOSS_ADAMERGING = 3,
+    MR_LOSS_ADAMERGING_KD = 4,
+    MR_LOSS_MERGED_PSEUDO_LABEL = 5,
+    MR_LOSS_MERGED_PSEUDO_LABEL_KD = 6,
+    MR_LOSS_SINGLE_PSEUDO_LABEL = 7,
+    MR_LOSS_SINGLE_PSEUDO_LABEL_KD = 8,
+    MR_LOSS_PAIRWISE = 9,
+    MR_LOSS_LISTNET = 10,
+};
+
+/* logits[b, n] = <rep[b, :], item_ptrs[sample_domain[b]][n, :]>  for n < item_rows[sample_domain[b]].
+ *   rep            dev (B, E) fp32, 16-byte aligned; E a multiple of 4, <= MR_DISTILL_MAX_E
+ *   item_ptrs      host array of nD dev pointers, table d is (item_rows[d], E) row-major, 16-byte aligned
+ *   item_rows      host int64[nD];  sample_domain  host int32[B] (the batch's dataset_indexes)
+ *   logits         dev (B, ld), ld >= the largest table used.  Every used table is read once for all of its samples.
+ *                                                        ref: sequence/module.py:64-66 */
+int mr_distill_logits(const float* rep, int B, int E, const float* const* item_ptrs, const int64_t* item_rows, int nD,
+                      const int32_t* sample_domain, float* logits, int64_t ld, mr_stream_t stream);
+
+/* loss[b] = loss_type(logits[b, :n_b], teacher_rows[b][:n_b]) exactly as loss_fn(merged.unsqueeze(0), single.unsqueeze(0))
+ * (the caller takes the mean over b, sequence/module.py:73); grad_logits[b, :n_b] = d loss[b] / d logits (NULL: skip).
+ *   teacher_rows   host array of B dev pointers (NULL entries / NULL array only for the losses that ignore the teacher)
+ *   n_per_sample   host int64[B];  temperature for KD / ListNet, coefficient for the *_KD mixes, margin for PAIRWISE.
+ * argmax ties take the lowest index (torch.argmax).      ref: loss_fn.py:36-231 */
+int mr_distill_loss(const float* logits, int64_t ld, const float* const* teacher_rows, const int64_t* n_per_sample, int B,
+                    int loss_type, float temperature, float coefficient, float margin, float* loss, float* grad_logits,
+                    int64_t ldg, mr_stream_t stream);
+
+/* grad_rep[b, :] = grad_out[b] * sum_n grad_logits[b, n] * item_ptrs[sample_domain[b]][n, :]  (grad_out NULL: 1).
+ * Same host tables as mr_distill_logits; ws: dev scratch of mr_distill_grad_workspace_bytes(E) bytes. Deterministic. */
+int64_t mr_distill_grad_workspace_bytes(int E);
+int mr_distill_grad(const float* grad_logits, int64_t ldg, const float* grad_out, int B, int E,
+                    const float* const* item_ptrs, const int64_t* item_rows, int nD, const int32_t* sample_domain,
+                    float* grad_rep, void* ws, int64_t ws_bytes, mr_stream_t stream);
+
+/* out[r, :] = x[r, :] / ||x[r, :]||_2  (may run in place)           ref: merge_train.py:122-123 */
+int mr_normalize_rows(const float* x, int64_t rows, int E, float* out, mr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmergerec_b200.so")
 MR_ORDER_BASE_FIRST, MR_ORDER_SUM_FIRST, MR_ORDER_LINEAR = 0, 1, 2
 MR_TIES_VECTORS, MR_TIES_TRIMSUM, MR_TIES_FUSED_MERGE, MR_TIES_LNS = 0, 1, 2, 3
 MR_MAX_K = 16
+MR_DISTILL_MAX_B, MR_DISTILL_MAX_GROUPS, MR_DISTILL_MAX_E = 128, 64, 1024
 
 _lib: Optional[C.CDLL] = None
 
@@ -42,6 +43,11 @@ SIGNATURES = {
     "mr_to_bf16": ([_vp, _i64, _vp, _vp], C.c_int),
     "mr_split_tf32": ([_vp, _i64, _vp, _vp, _vp], C.c_int),
     "mr_scores_fp32": ([_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp], C.c_int),
+    "mr_distill_logits": ([_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp], C.c_int),
+    "mr_distill_loss": ([_vp, _i64, _vp, _vp, _i32, _i32, C.c_float, C.c_float, C.c_float, _vp, _vp, _i64, _vp], C.c_int),
+    "mr_distill_grad_workspace_bytes": ([_i32], _i64),
+    "mr_distill_grad": ([_vp, _i64, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp], C.c_int),
+    "mr_normalize_rows": ([_vp, _i64, _i32, _vp, _vp], C.c_int),
     "mr_ties_build": ([_vp, _vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp], C.c_int),
 }
 

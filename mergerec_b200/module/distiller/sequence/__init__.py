@@ -1,0 +1,1 @@
+from .module import DistillSequenceModule, BatchDistillationSequence, TeacherScores, make_score_embeddings  # noqa: F401

@@ -186,3 +186,21 @@ def make_catalog(Q: int, N: int, E: int, kind: str = "grid", seed: int = 2,
     else:
         raise ValueError(kind)
     return users, items, labels
+
+
+def make_distill_case(B: int, E: int, rows: Sequence[int], n_seq: int = 6, seed: int = 0, planted: float = 1.0):
+    """Inputs of one distillation step: per-domain merged-model item tables, teacher
+    item / sequence embeddings (un-normalised), the batch's (dataset index, sequence id) pairs and the merged model's
+    representations.  Student tables are the teacher's plus noise so that losses are non-trivial."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    D = len(rows)
+    t_items = [rng.standard_normal((n, E), dtype=np.float32) for n in rows]
+    t_seqs = [rng.standard_normal((n_seq, E), dtype=np.float32) for _ in rows]
+    tables = [(ti / np.linalg.norm(ti, axis=-1, keepdims=True) + np.float32(0.05) * rng.standard_normal(ti.shape, dtype=np.float32)).astype(np.float32)
+              for ti in t_items]
+    dataset_indexes = [int(x) for x in rng.integers(0, D, size=B)]
+    sequence_ids = [int(x) for x in rng.integers(0, n_seq, size=B)]
+    rep = np.stack([planted * t_seqs[d][s] / np.linalg.norm(t_seqs[d][s]) for d, s in zip(dataset_indexes, sequence_ids)]).astype(np.float32)
+    rep = (rep + np.float32(0.3) * rng.standard_normal(rep.shape, dtype=np.float32)).astype(np.float32)
+    return dict(tables=tables, teacher_items=t_items, teacher_seqs=t_seqs, dataset_indexes=dataset_indexes,
+                sequence_ids=sequence_ids, rep=rep)

@@ -360,3 +360,107 @@ def evaluate(scores, labels, metrics: Sequence[str], ks: Sequence[int], prefix: 
     """Evaluator.__call__ (evaluator/evaluator.py:31-49) with canonical top-K order."""
     _, ids = topk_rows(scores, max(ks))
     return evaluate_ids(ids, labels, metrics, ks, prefix)
+
+
+# ---- distillation step (SURVEY.md section 8(f) rank 1) -------------------------------------------------------------
+# fp64 restatement of rec_retrieval/module/recommender/loss_fn.py on ONE sample (the reference calls every loss with
+# `(1, num_items)` tensors, sequence/module.py:69) plus the analytic gradient w.r.t. the merged model's logits.
+def _softmax64(x):
+    x = np.asarray(x, dtype=np.float64)
+    e = np.exp(x - x.max())
+    return e / e.sum()
+
+
+def _lse64(x):
+    x = np.asarray(x, dtype=np.float64)
+    m = x.max()
+    return m + math.log(np.exp(x - m).sum())
+
+
+def distill_loss(z, t, loss_type: str, temperature: float = 1.0, coefficient: float = 0.0, margin: float = 0.0):
+    """(loss, d loss / d z) for merged logits z (n,) and teacher logits t (n,).  loss_type: the reference's LossType
+    names plus "PAIRWISE" / "LISTNET" (classes of loss_fn.py that the factory does not list).  argmax = first maximum."""
+    z = np.asarray(z, dtype=np.float64)
+    t = None if t is None else np.asarray(t, dtype=np.float64)
+    n = z.shape[0]
+    T = float(temperature)
+
+    def ce(target):                                     # F.cross_entropy, loss_fn.py:41-42
+        p = _softmax64(z)
+        g = p.copy()
+        g[target] -= 1.0
+        return _lse64(z) - z[target], g
+
+    def kd():                                           # loss_fn.py:52-58
+        P, Q = _softmax64(t / T), _softmax64(z / T)
+        logP = t / T - _lse64(t / T)
+        logQ = z / T - _lse64(z / T)
+        return float((P * (logP - logQ)).sum()) * T * T, T * (Q - P)
+
+    def entropy():                                      # loss_fn.py:64-67 (fp32 1e-8 inside the log)
+        p = _softmax64(z)
+        eps = float(np.float32(1e-8))
+        h = -(np.log(p + eps) + p / (p + eps))
+        return float(-(p * np.log(p + eps)).sum()), p * (h - float((p * h).sum()))
+
+    if loss_type in ("CE", "SINGLE_PSEUDO_LABEL"):
+        return ce(int(np.argmax(t)))
+    if loss_type == "KD":
+        return kd()
+    if loss_type == "MSE":                              # loss_fn.py:185
+        return float(((z - t) ** 2).mean()), 2.0 * (z - t) / n
+    if loss_type == "ADAMERGING":
+        return entropy()
+    if loss_type == "ADAMERGING_KD":                    # loss_fn.py:81-86
+        (a, ga), (b, gb) = entropy(), kd()
+        return a + coefficient * b, ga + coefficient * gb
+    if loss_type == "MERGED_PSEUDO_LABEL":              # loss_fn.py:96-104
+        return ce(int(np.argmax(z)))
+    if loss_type == "MERGED_PSEUDO_LABEL_KD":
+        (a, ga), (b, gb) = ce(int(np.argmax(z))), kd()
+        return a + coefficient * b, ga + coefficient * gb
+    if loss_type == "SINGLE_PSEUDO_LABEL_KD":
+        (a, ga), (b, gb) = ce(int(np.argmax(t))), kd()
+        return a + coefficient * b, ga + coefficient * gb
+    if loss_type == "PAIRWISE":                         # loss_fn.py:195-210
+        pos = int(np.argmax(t))
+        masked = t.copy()
+        masked[pos] = -np.inf
+        neg = int(np.argmax(masked))
+        h = margin - (z[pos] - z[neg])
+        g = np.zeros(n)
+        if h > 0:
+            g[pos] -= 1.0
+            g[neg] += 1.0
+        return max(h, 0.0), g
+    if loss_type == "LISTNET":                          # loss_fn.py:221-228
+        P, Q = _softmax64(t / T), _softmax64(z / T)
+        logQ = z / T - _lse64(z / T)
+        return float(-(P * logQ).sum()), (Q - P) / T
+    raise ValueError(f"unknown loss type {loss_type}")
+
+
+def teacher_scores(item_embedding, sequence_embedding) -> np.ndarray:
+    """merge_train.py:116-126: normalised sequence embeddings @ normalised item embeddings.T (fp64 here)."""
+    I = np.asarray(item_embedding, dtype=np.float64)
+    S = np.asarray(sequence_embedding, dtype=np.float64)
+    I = I / np.linalg.norm(I, axis=-1, keepdims=True)
+    S = S / np.linalg.norm(S, axis=-1, keepdims=True)
+    return S @ I.T
+
+
+def distill_step(rep, item_tables, dataset_indexes, teacher_rows, loss_type: str, temperature: float = 1.0,
+                 coefficient: float = 0.0, margin: float = 0.0):
+    """`_forward_distill` (sequence/module.py:59-76) in fp64: per-sample losses, their mean, and the gradient of the
+    mean w.r.t. the representations (item tables carry no gradient, callbacks.py:48-50)."""
+    rep = np.asarray(rep, dtype=np.float64)
+    B = rep.shape[0]
+    losses = np.zeros(B)
+    grad = np.zeros_like(rep)
+    for i, d in enumerate(dataset_indexes):
+        items = np.asarray(item_tables[d], dtype=np.float64)
+        z = items @ rep[i]
+        lv, gz = distill_loss(z, None if teacher_rows is None else teacher_rows[i], loss_type, temperature, coefficient, margin)
+        losses[i] = lv
+        grad[i] = (gz @ items) / B
+    return losses, float(losses.mean()), grad

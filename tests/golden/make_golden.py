@@ -235,12 +235,73 @@ def gen_module_e2e():
     save("module_e2e", **out)
 
 
+def _load_reference_loss_fn():
+    """rec_retrieval/module/recommender/loss_fn.py without its package __init__ (which pulls in lightning / peft, absent
+    here): the parent packages are registered as empty namespaces, the file itself is executed unmodified."""
+    import importlib.util
+    import types
+    import rec_retrieval.merger.enums  # noqa: F401  (the real module the file imports)
+    for name in ("rec_retrieval.module", "rec_retrieval.module.recommender"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = ["/root/reference/" + name.replace(".", "/")]
+            sys.modules[name] = m
+    spec = importlib.util.spec_from_file_location("rec_retrieval.module.recommender.loss_fn",
+                                                  "/root/reference/rec_retrieval/module/recommender/loss_fn.py")
+    lf = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = lf
+    spec.loader.exec_module(lf)
+    return lf
+
+
+def reference_loss(lf, name, kw):
+    cls = {"CE": lf.DistillCELoss, "KD": lf.DistillKDLoss, "MSE": lf.DistillMSELoss, "ADAMERGING": lf.DistillAdaMergingLoss,
+           "ADAMERGING_KD": lf.DistillAdaMergingKDLoss, "MERGED_PSEUDO_LABEL": lf.MergedPseudoLabelLoss,
+           "MERGED_PSEUDO_LABEL_KD": lf.MergedPseudoLabelKDLoss, "SINGLE_PSEUDO_LABEL": lf.SinglePseudoLabelLoss,
+           "SINGLE_PSEUDO_LABEL_KD": lf.SinglePseudoLabelKDLoss, "PAIRWISE": lf.DistillPairwiseLoss,
+           "LISTNET": lf.DistillListNetLoss}[name]
+    return cls(**kw)
+
+
+def gen_distill():
+    """The reference's own loss classes driven by the loop of DistillSequenceModule._forward_distill
+    (sequence/module.py:59-76; the module itself needs lightning) with teacher logits built as merge_train.py:116-126
+    does, in fp32 on the CPU: per-sample losses, the batch loss and its gradient w.r.t. the representations."""
+    lf = _load_reference_loss_fn()
+    out = {}
+    for case in gc.DISTILL_CASES:
+        c = synth.make_distill_case(case["B"], case["E"], case["rows"], case["n_seq"], case["seed"], planted=case["scale"])
+        score_embeddings = []
+        for item_embedding, sequence_embedding in zip(c["teacher_items"], c["teacher_seqs"]):
+            item_embedding, sequence_embedding = T(item_embedding), T(sequence_embedding)
+            item_embedding = item_embedding / item_embedding.norm(dim=-1, keepdim=True)
+            sequence_embedding = sequence_embedding / sequence_embedding.norm(dim=-1, keepdim=True)
+            score_embeddings.append(sequence_embedding @ item_embedding.T)
+        for d, s in enumerate(score_embeddings):
+            out[f"{case['name']}/score_embeddings{d}"] = s.numpy()
+        item_embeddings = [T(t) for t in c["tables"]]
+        for lname, kw in gc.DISTILL_LOSSES:
+            loss_fn = reference_loss(lf, lname, kw)
+            rep = T(c["rep"]).clone().requires_grad_(True)
+            losses = []
+            for i, (dataset_index, sequence_id) in enumerate(zip(c["dataset_indexes"], c["sequence_ids"])):
+                merged_model_logit = rep[i] @ item_embeddings[dataset_index].T
+                single_model_logit = score_embeddings[dataset_index][sequence_id]
+                losses.append(loss_fn(merged_model_logit.unsqueeze(0), single_model_logit.unsqueeze(0)))
+            loss = torch.stack(losses).mean()
+            loss.backward()
+            out[f"{case['name']}/{lname}/losses"] = torch.stack(losses).detach().numpy()
+            out[f"{case['name']}/{lname}/loss"] = np.asarray(float(loss), np.float64)
+            out[f"{case['name']}/{lname}/grad_rep"] = rep.grad.numpy()
+    save("distill", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
     only = set(sys.argv[1:])   # e.g. `make_golden.py lns` regenerates one file
     for name, fn in [("merge_flat", gen_merge_flat), ("model_merger", gen_model_merger), ("lambda_merge", gen_lambda),
                      ("ties", gen_ties), ("lns", gen_lns), ("evaluator", gen_evaluator), ("evaluator_bf16", gen_evaluator_bf16),
-                     ("module_e2e", gen_module_e2e)]:
+                     ("module_e2e", gen_module_e2e), ("distill", gen_distill)]:
         if not only or name in only:
             fn()

@@ -56,3 +56,18 @@ MODULE_CASES = [
     dict(name="ties_layerwise_softmax", merge_type="TIES", learn_type="LAYER_WISE", K=5, seed=63, density=0.2,
          disable_softmax=False),
 ]
+
+# Distillation step.  rows: items per domain (ragged, odd sizes, one domain with a
+# single sample and one with more than four so that a table is walked by two sample groups).
+DISTILL_LOSSES = [
+    ("CE", {}), ("KD", dict(temperature=2.0)), ("MSE", {}), ("ADAMERGING", {}),
+    ("ADAMERGING_KD", dict(temperature=0.5, coefficient=0.3)), ("MERGED_PSEUDO_LABEL", {}),
+    ("MERGED_PSEUDO_LABEL_KD", dict(temperature=2.0, coefficient=0.7)), ("SINGLE_PSEUDO_LABEL", {}),
+    ("SINGLE_PSEUDO_LABEL_KD", dict(temperature=1.0, coefficient=0.5)), ("PAIRWISE", dict(margin=0.2)),
+    ("LISTNET", dict(temperature=0.1)),
+]
+DISTILL_CASES = [
+    dict(name="b6_e64", B=6, E=64, rows=[37, 130, 257], n_seq=5, seed=81, scale=8.0),
+    dict(name="b16_e768", B=16, E=768, rows=[301, 64, 999], n_seq=7, seed=82, scale=20.0),
+    dict(name="b9_e1024", B=9, E=1024, rows=[513, 1], n_seq=4, seed=83, scale=5.0),
+]
