@@ -82,24 +82,43 @@ static int ds_build_plan(const float* const* item_ptrs, const int64_t* item_rows
             ++in_group;
         }
     }
-    const int64_t target = (int64_t)sm_count() * 2;
+    // One persistent CTA per SM (the stage ring fills shared memory): hand out exactly sm_count CTAs in proportion to
+    // the rows of each group (largest remainders first), at least one and at most one per 16 rows.
+    const int64_t target = sm_count() > ng ? sm_count() : ng;
+    int64_t given = 0;
+    int64_t share[MR_DISTILL_MAX_GROUPS], rem[MR_DISTILL_MAX_GROUPS];
+    for (int i = 0; i < ng; ++i) {
+        const int64_t rows = plan->g[i].rows;
+        const int64_t cap = rows > 0 ? (rows + 15) / 16 : 1;
+        int64_t c = total_rows > 0 ? target * rows / total_rows : 1;
+        rem[i] = total_rows > 0 ? (target * rows) % total_rows : 0;
+        if (c < 1) { c = 1; rem[i] = 0; }
+        if (c >= cap) { c = cap; rem[i] = -1; }
+        share[i] = c;
+        given += c;
+    }
+    while (given < target) {
+        int best = -1;
+        for (int i = 0; i < ng; ++i)
+            if (rem[i] >= 0 && (best < 0 || rem[i] > rem[best])) best = i;
+        if (best < 0) break;
+        const int64_t cap = (plan->g[best].rows + 15) / 16;
+        ++share[best];
+        ++given;
+        rem[best] = share[best] >= cap ? -1 : 0;
+    }
     int next = 0;
     for (int i = 0; i < ng; ++i) {
-        DsGroup& G = plan->g[i];
-        int64_t c = total_rows > 0 ? (target * G.rows + total_rows / 2) / total_rows : 1;
-        const int64_t cap = (G.rows + 15) / 16;  // at least 16 rows per CTA
-        if (c > cap) c = cap;
-        if (c < 1) c = 1;
-        G.cta_begin = next;
-        G.cta_count = (int32_t)c;
-        next += (int)c;
+        plan->g[i].cta_begin = next;
+        plan->g[i].cta_count = (int32_t)share[i];
+        next += (int)share[i];
     }
     plan->ngroups = ng;
     plan->total_ctas = next;
     return MR_OK;
 }
 
-static inline int64_t ds_max_ctas() { return (int64_t)sm_count() * 2 + MR_DISTILL_MAX_GROUPS; }
+static inline int64_t ds_max_ctas() { return (int64_t)sm_count() + 2 * MR_DISTILL_MAX_GROUPS; }
 
 __device__ __forceinline__ int ds_find_group(const DsPlan& plan, int cta) {
     int gi = 0;
@@ -135,16 +154,99 @@ __device__ __forceinline__ float warp_multi_sum(float (&v)[V], int lane) {
     return r;
 }
 
+// ---- item-table streaming: 1-D TMA bulk copies into a ring of shared-memory stages ------------------------------------
+// A CTA owns rows [r0, r1) of one table and walks them in tiles of R rows (R * E * 4 bytes, contiguous in HBM).
+// Thread 0 keeps S tiles in flight (`cp.async.bulk` completing on one mbarrier per stage); the eight warps wait for a
+// stage, consume two rows each per 16-row slab straight from shared memory, and a CTA barrier hands the stage back.
+// Bytes in flight per SM = (S-1) tiles (~144 KB) independent of register pressure.
+__device__ __forceinline__ uint32_t ds_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ds_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ds_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool ds_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void ds_mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!ds_mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void ds_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct DsTiling {
+    int R, S;
+    size_t smem;
+};
+static inline DsTiling ds_tiling(int E) {
+    DsTiling t;
+    t.R = E > 384 ? 16 : 32;
+    const size_t stage = (size_t)t.R * E * 4;
+    const size_t fit = (size_t)(200 * 1024) / stage;
+    t.S = (int)(fit < 4 ? fit : 4);
+    t.smem = 128 + t.S * stage;
+    return t;
+}
+
+struct DsStream {
+    uint32_t bar0;
+    float* stage0;
+    const float* items;
+    int64_t r0, r1;
+    int R, S, E, ntiles;
+    __device__ __forceinline__ void init(unsigned char* smem, const DsGroup& G, int local, int R_, int S_, int E_) {
+        bar0 = ds_smem_u32(smem);
+        stage0 = reinterpret_cast<float*>(smem + 128);
+        items = G.items;
+        r0 = (int64_t)G.rows * local / G.cta_count;
+        r1 = (int64_t)G.rows * (local + 1) / G.cta_count;
+        R = R_; S = S_; E = E_;
+        ntiles = (int)((r1 - r0 + R - 1) / R);
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < S; ++s) ds_mbar_init(bar0 + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int t = 0; t < S && t < ntiles; ++t) issue(t);
+    }
+    __device__ __forceinline__ int rows_in(int tile) const {
+        const int64_t left = r1 - (r0 + (int64_t)tile * R);
+        return (int)(left < R ? left : R);
+    }
+    __device__ __forceinline__ void issue(int tile) const {
+        const int s = tile % S;
+        const uint32_t bytes = (uint32_t)rows_in(tile) * (uint32_t)E * 4u;
+        ds_mbar_expect_tx(bar0 + 8 * s, bytes);
+        ds_bulk_load(ds_smem_u32(stage0 + (size_t)s * R * E), items + (r0 + (int64_t)tile * R) * E, bytes, bar0 + 8 * s);
+    }
+    __device__ __forceinline__ const float4* wait(int tile) const {
+        const int s = tile % S;
+        ds_mbar_wait(bar0 + 8 * s, (uint32_t)((tile / S) & 1));
+        return reinterpret_cast<const float4*>(stage0 + (size_t)s * R * E);
+    }
+    __device__ __forceinline__ void release(int tile) const {  // all threads; the stage is refilled with tile + S
+        __syncthreads();
+        if (threadIdx.x == 0 && tile + S < ntiles) issue(tile + S);
+    }
+};
+
 // ---- logits[b, n] = <rep[b], items_dom(b)[n]> ---------------------------------------------------------------------
-// A warp owns two item rows per iteration (EV 128-bit loads per lane and row, all issued before the first use);
-// the group's <= NB representation vectors stay in registers.
+// The group's <= NB representation vectors stay in registers; a warp takes two rows of the stage at a time.
 template <int EV, int NB>
-__global__ void __launch_bounds__(kDsThreads)
-ds_logits_kernel(const __grid_constant__ DsPlan plan, const float* __restrict__ rep, int E, float* __restrict__ logits,
-                 int64_t ld) {
+__global__ void __launch_bounds__(kDsThreads, 1)
+ds_logits_kernel(const __grid_constant__ DsPlan plan, const float* __restrict__ rep, int E, int R, int S,
+                 float* __restrict__ logits, int64_t ld) {
+    extern __shared__ __align__(128) unsigned char ds_smem[];
     const DsGroup& G = plan.g[ds_find_group(plan, (int)blockIdx.x)];
-    const int local = (int)blockIdx.x - G.cta_begin;
-    const int64_t r0 = (int64_t)G.rows * local / G.cta_count, r1 = (int64_t)G.rows * (local + 1) / G.cta_count;
+    DsStream st;
+    st.init(ds_smem, G, (int)blockIdx.x - G.cta_begin, R, S, E);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int EQ = E >> 2;
     float4 u[NB][EV];
@@ -156,52 +258,55 @@ ds_logits_kernel(const __grid_constant__ DsPlan plan, const float* __restrict__ 
             u[s][i] = (s < G.nb && c < EQ) ? *reinterpret_cast<const float4*>(rep + (int64_t)G.sample[s] * E + 4 * c)
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    const float* items = G.items;
-    for (int64_t r = r0 + warp * 2; r < r1; r += kDsWarps * 2) {
-        const bool two = (r + 1 < r1);
-        const float* pa = items + r * E;
-        const float* pb = two ? pa + E : pa;
-        float4 a[EV], b[EV];
-#pragma unroll
-        for (int i = 0; i < EV; ++i) {
-            const int c = lane + 32 * i;
-            a[i] = (c < EQ) ? ldg_stream4(pa + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < EV; ++i) {
-            const int c = lane + 32 * i;
-            b[i] = (c < EQ) ? ldg_stream4(pb + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float acc[NB * 2];
-#pragma unroll
-        for (int s = 0; s < NB; ++s) {
-            float xa = 0.f, xb = 0.f;
+    for (int tile = 0; tile < st.ntiles; ++tile) {
+        const float4* sm = st.wait(tile);
+        const int nrows = st.rows_in(tile);
+        const int64_t row0 = st.r0 + (int64_t)tile * R;
+        for (int rr = warp * 2; rr < nrows; rr += kDsWarps * 2) {
+            const bool two = (rr + 1 < nrows);
+            const float4* pa = sm + (size_t)rr * EQ;
+            const float4* pb = two ? pa + EQ : pa;
+            float4 a[EV], b[EV];
 #pragma unroll
             for (int i = 0; i < EV; ++i) {
-                xa = dot4(u[s][i], a[i], xa);
-                xb = dot4(u[s][i], b[i], xb);
+                const int c = lane + 32 * i;
+                a[i] = (c < EQ) ? pa[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+                b[i] = (c < EQ) ? pb[c] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            acc[2 * s] = xa;
-            acc[2 * s + 1] = xb;
+            float acc[NB * 2];
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
+                float xa = 0.f, xb = 0.f;
+#pragma unroll
+                for (int i = 0; i < EV; ++i) {
+                    xa = dot4(u[s][i], a[i], xa);
+                    xb = dot4(u[s][i], b[i], xb);
+                }
+                acc[2 * s] = xa;
+                acc[2 * s + 1] = xb;
+            }
+            const float tot = warp_multi_sum<NB * 2>(acc, lane);
+            constexpr int kSub = 32 / (NB * 2);
+            if ((lane % kSub) == 0) {
+                const int j = lane / kSub, s = j >> 1, h = j & 1;
+                if (s < G.nb && (h == 0 || two)) logits[(int64_t)G.sample[s] * ld + row0 + rr + h] = tot;
+            }
         }
-        const float tot = warp_multi_sum<NB * 2>(acc, lane);
-        constexpr int kSub = 32 / (NB * 2);
-        if ((lane % kSub) == 0) {
-            const int j = lane / kSub, s = j >> 1, h = j & 1;
-            if (s < G.nb && (h == 0 || two)) logits[(int64_t)G.sample[s] * ld + r + h] = tot;
-        }
+        st.release(tile);
     }
 }
 
 // ---- per-CTA partial of grad_rep[b, :] = sum_n gz[b, n] * items[n, :] -----------------------------------------------
+// Same stream; the tile's <= 32 gradient values of every sample are fetched by the lanes before the wait and
+// broadcast with shuffles.
 template <int EV, int NB>
-__global__ void __launch_bounds__(kDsThreads)
-ds_grad_kernel(const __grid_constant__ DsPlan plan, const float* __restrict__ gz, int64_t ldg, int E,
+__global__ void __launch_bounds__(kDsThreads, 1)
+ds_grad_kernel(const __grid_constant__ DsPlan plan, const float* __restrict__ gz, int64_t ldg, int E, int R, int S,
                float* __restrict__ partial) {
-    __shared__ float4 s_red[kDsWarps][32 * EV];
+    extern __shared__ __align__(128) unsigned char ds_smem[];
     const DsGroup& G = plan.g[ds_find_group(plan, (int)blockIdx.x)];
-    const int local = (int)blockIdx.x - G.cta_begin;
-    const int64_t r0 = (int64_t)G.rows * local / G.cta_count, r1 = (int64_t)G.rows * (local + 1) / G.cta_count;
+    DsStream st;
+    st.init(ds_smem, G, (int)blockIdx.x - G.cta_begin, R, S, E);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int EQ = E >> 2;
     float4 acc[NB][EV];
@@ -209,50 +314,59 @@ ds_grad_kernel(const __grid_constant__ DsPlan plan, const float* __restrict__ gz
     for (int s = 0; s < NB; ++s)
 #pragma unroll
         for (int i = 0; i < EV; ++i) acc[s][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* items = G.items;
     const float* gzrow[NB];
 #pragma unroll
     for (int s = 0; s < NB; ++s) gzrow[s] = gz + (int64_t)G.sample[s < G.nb ? s : 0] * ldg;
-    for (int64_t r = r0 + warp * 2; r < r1; r += kDsWarps * 2) {
-        const bool two = (r + 1 < r1);
-        const float* pa = items + r * E;
-        const float* pb = two ? pa + E : pa;
-        float4 a[EV], b[EV];
+    for (int tile = 0; tile < st.ntiles; ++tile) {
+        const int nrows = st.rows_in(tile);
+        const int64_t row0 = st.r0 + (int64_t)tile * R;
+        float gv[NB];
 #pragma unroll
-        for (int i = 0; i < EV; ++i) {
-            const int c = lane + 32 * i;
-            a[i] = (c < EQ) ? ldg_stream4(pa + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < EV; ++i) {
-            const int c = lane + 32 * i;
-            b[i] = (c < EQ) ? ldg_stream4(pb + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int s = 0; s < NB; ++s) {
-            const float ga = (s < G.nb) ? __ldg(gzrow[s] + r) : 0.f;
-            const float gb = (s < G.nb && two) ? __ldg(gzrow[s] + r + 1) : 0.f;
+        for (int s = 0; s < NB; ++s) gv[s] = (s < G.nb && lane < nrows) ? __ldg(gzrow[s] + row0 + lane) : 0.f;
+        const float4* sm = st.wait(tile);
+        for (int rr = warp * 2; rr < nrows; rr += kDsWarps * 2) {
+            const bool two = (rr + 1 < nrows);
+            const float4* pa = sm + (size_t)rr * EQ;
+            const float4* pb = two ? pa + EQ : pa;
+            float4 a[EV], b[EV];
 #pragma unroll
             for (int i = 0; i < EV; ++i) {
-                acc[s][i].x = fmaf(ga, a[i].x, fmaf(gb, b[i].x, acc[s][i].x));
-                acc[s][i].y = fmaf(ga, a[i].y, fmaf(gb, b[i].y, acc[s][i].y));
-                acc[s][i].z = fmaf(ga, a[i].z, fmaf(gb, b[i].z, acc[s][i].z));
-                acc[s][i].w = fmaf(ga, a[i].w, fmaf(gb, b[i].w, acc[s][i].w));
+                const int c = lane + 32 * i;
+                a[i] = (c < EQ) ? pa[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+                b[i] = (c < EQ) ? pb[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
+                const float ga = __shfl_sync(0xffffffffu, gv[s], rr);
+                const float gb0 = __shfl_sync(0xffffffffu, gv[s], (rr + 1) & 31);
+                const float gb = two ? gb0 : 0.f;
+#pragma unroll
+                for (int i = 0; i < EV; ++i) {
+                    acc[s][i].x = fmaf(ga, a[i].x, fmaf(gb, b[i].x, acc[s][i].x));
+                    acc[s][i].y = fmaf(ga, a[i].y, fmaf(gb, b[i].y, acc[s][i].y));
+                    acc[s][i].z = fmaf(ga, a[i].z, fmaf(gb, b[i].z, acc[s][i].z));
+                    acc[s][i].w = fmaf(ga, a[i].w, fmaf(gb, b[i].w, acc[s][i].w));
+                }
             }
         }
+        st.release(tile);
     }
-    // cross-warp sum in a fixed order, one sample slot at a time
+    // cross-warp sum in a fixed order, one sample slot at a time; the (idle) stage ring is the scratch
+    float4* s_red = reinterpret_cast<float4*>(ds_smem + 128);  // [kDsWarps][EQ]
 #pragma unroll
     for (int s = 0; s < NB; ++s) {
         if (s < G.nb) {  // uniform over the CTA
 #pragma unroll
-            for (int i = 0; i < EV; ++i) s_red[warp][lane + 32 * i] = acc[s][i];
+            for (int i = 0; i < EV; ++i) {
+                const int c = lane + 32 * i;
+                if (c < EQ) s_red[warp * EQ + c] = acc[s][i];
+            }
             __syncthreads();
             for (int c = threadIdx.x; c < EQ; c += kDsThreads) {
-                float4 t = s_red[0][c];
+                float4 t = s_red[c];
 #pragma unroll
                 for (int w = 1; w < kDsWarps; ++w) {
-                    const float4 o = s_red[w][c];
+                    const float4 o = s_red[w * EQ + c];
                     t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
                 }
                 *reinterpret_cast<float4*>(partial + ((int64_t)blockIdx.x * kDsNB + s) * E + 4 * c) = t;
@@ -525,8 +639,11 @@ extern "C" int mr_distill_logits(const float* rep, int B, int E, const float* co
                    plan.g[i].rows);
     if (plan.total_ctas == 0) return MR_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    MR_DISPATCH_EV_NB(E, ds_max_nb(plan),
-                      (ds_logits_kernel<EVV, NBB><<<plan.total_ctas, kDsThreads, 0, st>>>(plan, rep, E, logits, ld)));
+    const DsTiling tl = ds_tiling(E);
+    MR_DISPATCH_EV_NB(E, ds_max_nb(plan), {
+        cudaFuncSetAttribute(ds_logits_kernel<EVV, NBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem);
+        ds_logits_kernel<EVV, NBB><<<plan.total_ctas, kDsThreads, tl.smem, st>>>(plan, rep, E, tl.R, tl.S, logits, ld);
+    });
     MR_CUDA_LAUNCH_CHECK("mr_distill_logits");
     return MR_OK;
 }
@@ -584,8 +701,11 @@ extern "C" int mr_distill_grad(const float* grad_logits, int64_t ldg, const floa
                    plan.g[i].rows);
     cudaStream_t st = (cudaStream_t)stream;
     float* partial = reinterpret_cast<float*>(ws);
-    MR_DISPATCH_EV_NB(E, ds_max_nb(plan),
-                      (ds_grad_kernel<EVV, NBB><<<plan.total_ctas, kDsThreads, 0, st>>>(plan, grad_logits, ldg, E, partial)));
+    const DsTiling tl = ds_tiling(E);
+    MR_DISPATCH_EV_NB(E, ds_max_nb(plan), {
+        cudaFuncSetAttribute(ds_grad_kernel<EVV, NBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem);
+        ds_grad_kernel<EVV, NBB><<<plan.total_ctas, kDsThreads, tl.smem, st>>>(plan, grad_logits, ldg, E, tl.R, tl.S, partial);
+    });
     ds_grad_finish_kernel<<<B, 256, 0, st>>>(plan, partial, grad_out, E, grad_rep);
     MR_CUDA_LAUNCH_CHECK("mr_distill_grad");
     return MR_OK;
