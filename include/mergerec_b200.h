@@ -251,6 +251,19 @@ int mr_distill_grad(const float* grad_logits, int64_t ldg, const float* grad_out
 /* out[r, :] = x[r, :] / ||x[r, :]||_2  (may run in place)           ref: merge_train.py:122-123 */
 int mr_normalize_rows(const float* x, int64_t rows, int E, float* out, mr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * PCB-merging vectors.        ref: merger/algorithms/pcb.py:37-58
+ * out[k, j] = sign(tau) * clamp(|tau|, lo_k, hi_k) * scale / max(sum_k scale, 1e-12) / K  with the intra- /
+ * inter-balancing weights of pcb.py:44-53.  clamp_lo / clamp_hi (dev, K floats) are the int(d*0.01)-th and
+ * int(d*0.99 - 1)-th smallest |tau_k| (pcb.py:17-27; obtained with mr_ties_select on the magnitudes);
+ * q_index = int(d * (1 - density)) is the ascending rank of the lower clamp of the balancing weights, found here
+ * exactly with three histogram passes.  task_out (K rows, ldo) / thr_out (K x {q, max}) are optional diagnostics.
+ * exp / tanh are CUDA's: values agree with torch's CPU kernels to ~1 ulp (floating-point contract, not bit-exact). */
+int64_t mr_pcb_workspace_bytes(int K);
+int mr_pcb_vectors(const float* base, const float* const* models, int K, int64_t d, const float* clamp_lo,
+                   const float* clamp_hi, int64_t q_index, float* out, int64_t ldo, float* task_out, float* thr_out,
+                   void* ws, int64_t ws_bytes, mr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

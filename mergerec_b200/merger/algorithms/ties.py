@@ -22,20 +22,20 @@ def ties_topk_count(density: float, numel: int) -> int:
     return int(density * numel)
 
 
-def ties_select(base_model: FlattenedModel, rows: Sequence[torch.Tensor], density: float,
-                w: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Per-model 64-bit cut keys (int64 tensor of K, bit pattern of the uint64): model k keeps element j iff
+def select_kth_largest(base_model: FlattenedModel, rows: Sequence[torch.Tensor], k_cnt: int,
+                       w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-model 64-bit keys (int64 tensor of K, bit pattern of the uint64) of the ``k_cnt``-th largest
+    ``|w_k (m_k - base)|`` under the order (magnitude, lower flat index first): model k keeps element j iff
     ``(bits(|u_kj|) << 32 | (0xFFFFFFFF - j)) >= cut[k]``.  Runs the stream-ordered sampled-bracket select and,
     if a model's bracket missed or overflowed (adversarial inputs), the exact multi-pass select."""
     lib = _lib.load()
     K, d = len(rows), base_model.numel()
     dev = base_model.device
-    k_cnt = ties_topk_count(density, d)
     ws_bytes = int(lib.mr_ties_workspace_bytes(d, K))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     cut = torch.empty(K, dtype=torch.int64, device=dev)
     status = torch.zeros(K, dtype=torch.int32, device=dev)
-    args = (_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(w), k_cnt, _lib.dptr(cut),
+    args = (_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(w), int(k_cnt), _lib.dptr(cut),
             _lib.dptr(status), _lib.dptr(ws), ws_bytes, _lib.stream_handle())
     _lib.check(lib.mr_ties_select(*args), "mr_ties_select")
     st = status.cpu()
@@ -45,6 +45,12 @@ def ties_select(base_model: FlattenedModel, rows: Sequence[torch.Tensor], densit
         if bool((st != 1).any()):
             raise _lib.MergeRecLibraryError(f"TIES select failed with status {st.tolist()}")
     return cut
+
+
+def ties_select(base_model: FlattenedModel, rows: Sequence[torch.Tensor], density: float,
+                w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Cut keys of the TIES trim: the ``int(density * d)`` largest magnitudes survive (ties.py:14-23)."""
+    return select_kth_largest(base_model, rows, ties_topk_count(density, base_model.numel()), w)
 
 
 def _build(base_model, rows, cut, mode, w=None, G=1, seg_end=None, seg_group=None, out=None, ldo=0,

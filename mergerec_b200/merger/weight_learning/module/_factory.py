@@ -6,6 +6,7 @@ from typing import List, Optional, Set
 import torch
 
 from ...algorithms.localize_and_stitch import get_localize_and_stitch_vectors
+from ...algorithms.pcb import get_pcb_vectors
 from ...algorithms.task_vector import get_task_vectors
 from ...algorithms.ties import get_ties_vectors
 from ...enums import LearnType, MergeType
@@ -59,8 +60,7 @@ def load_merging_module(merge_type: MergeType, learn_type: LearnType, model: tor
         vectors = get_localize_and_stitch_vectors(base_model=merger.base_model, models=merger.models,
                                                   density=ties_density)
     elif merge_type is MergeType.PCB:
-        raise NotImplementedError(
-            f"{merge_type} is a baseline outside the merger hot path this package implements (SURVEY.md section 8(f)).")
+        vectors = get_pcb_vectors(base_model=merger.base_model, models=merger.models, density=ties_density)
     else:
         raise ValueError(f"Invalid merge type: {merge_type}")
 

@@ -464,3 +464,55 @@ def distill_step(rep, item_tables, dataset_indexes, teacher_rows, loss_type: str
         losses[i] = lv
         grad[i] = (gz @ items) / B
     return losses, float(losses.mean()), grad
+
+
+# ---- PCB merging --------------------------------------------------------------------
+def _sum_dim0(X: np.ndarray) -> np.ndarray:
+    """torch.sum(X, dim=0) for a (K, d) fp32 matrix in ATen's order (0 + 1*x is exact, so the lambda merge does it)."""
+    X = _f32(X)
+    return lambda_merge(np.zeros(X.shape[1], np.float32), X, np.ones((1, X.shape[0]), np.float32))
+
+
+def pcb_vectors(base, models, density: float = 0.2, return_task: bool = False):
+    """get_pcb_vectors, merger/algorithms/pcb.py:37-58, in numpy fp32 (numpy's exp / tanh stand in for torch's: both
+    are within an ulp of the true value, so the restatement is pinned to the golden vectors at ~1e-6, not bitwise)."""
+    base = _f32(base)
+    tv = np.stack([_f32(m) - base for m in models]).astype(np.float32)                 # :38
+    n, d = tv.shape
+
+    def clamp(x, min_ratio, max_ratio):                                                # :16-29
+        s = np.sort(x, axis=1)
+        lo = s[:, int(d * min_ratio)][:, None]
+        hi = s[:, int(d * (1 - max_ratio) - 1)][:, None]
+        return np.minimum(np.maximum(x, lo), hi), lo, hi
+
+    def normalize(x):                                                                  # :9-13
+        mn, mx = x.min(axis=1, keepdims=True), x.max(axis=1, keepdims=True)
+        return ((x - mn) / (mx - mn)).astype(np.float32)
+
+    A, lo, hi = clamp(np.abs(tv), 0.01, 0.01)                                          # :42
+    clamped = (np.sign(tv) * A).astype(np.float32)                                     # :43
+    self_pcb = normalize(A)
+    self_pcb = (self_pcb * self_pcb).astype(np.float32)                                # :45
+    self_act = np.exp(np.float32(n) * self_pcb).astype(np.float32)                     # :46
+    cross = (tv * _sum_dim0(tv)[None, :]).astype(np.float32)                           # :48
+    task = (self_act * np.tanh(cross).astype(np.float32)).astype(np.float32)           # :49-51
+    cl, q, mx = clamp(task, 1 - density, 0)
+    scale = normalize(cl)                                                              # :53
+    pcb = (clamped * scale).astype(np.float32)                                         # :54
+    pcb = (pcb / np.maximum(_sum_dim0(scale), np.float32(1e-12))[None, :]).astype(np.float32)   # :55
+    pcb = (pcb / np.float32(n)).astype(np.float32)                                     # :56
+    if return_task:
+        return pcb, task, q[:, 0], mx[:, 0], lo[:, 0], hi[:, 0]
+    return pcb
+
+
+def merge_pcb(base, models, weights: Sequence[float], density: float = 0.2) -> np.ndarray:
+    """merge_pcb, pcb.py:61-73: base-first accumulation of weights[i] * pcb_vector_i."""
+    assert len(models) == len(weights), "Number of models and weights should match."
+    base = _f32(base)
+    vec = pcb_vectors(base, models, density)
+    acc = base.copy()
+    for i in range(len(models)):
+        acc = (acc + (np.float32(weights[i]) * vec[i]).astype(np.float32)).astype(np.float32)
+    return acc

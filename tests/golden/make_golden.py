@@ -296,12 +296,23 @@ def gen_distill():
     save("distill", **out)
 
 
+def gen_pcb():
+    from rec_retrieval.merger.algorithms.pcb import get_pcb_vectors, merge_pcb
+    out = {}
+    for case in gc.PCB_CASES:
+        base, models = synth.make_flat(case["d"], case["K"], seed=case["seed"])
+        tb, tm = T(base), [T(m) for m in models]
+        out[f"{case['name']}/vectors"] = get_pcb_vectors(tb, tm, density=case["density"]).numpy()
+        out[f"{case['name']}/merged"] = merge_pcb(tb, tm, case["weights"], density=case["density"]).numpy()
+    save("pcb", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
     only = set(sys.argv[1:])   # e.g. `make_golden.py lns` regenerates one file
     for name, fn in [("merge_flat", gen_merge_flat), ("model_merger", gen_model_merger), ("lambda_merge", gen_lambda),
                      ("ties", gen_ties), ("lns", gen_lns), ("evaluator", gen_evaluator), ("evaluator_bf16", gen_evaluator_bf16),
-                     ("module_e2e", gen_module_e2e), ("distill", gen_distill)]:
+                     ("module_e2e", gen_module_e2e), ("distill", gen_distill), ("pcb", gen_pcb)]:
         if not only or name in only:
             fn()

@@ -71,3 +71,11 @@ DISTILL_CASES = [
     dict(name="b16_e768", B=16, E=768, rows=[301, 64, 999], n_seq=7, seed=82, scale=20.0),
     dict(name="b9_e1024", B=9, E=1024, rows=[513, 1], n_seq=4, seed=83, scale=5.0),
 ]
+
+# PCB merging: d with a 5-column interleaved tail, an odd d, a larger d.
+PCB_CASES = [
+    dict(name="k3_d4165", K=3, d=4165, seed=91, density=0.2, weights=[0.3, 0.5, 0.7]),
+    dict(name="k8_d4165", K=8, d=4165, seed=92, density=0.2, weights=[0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]),
+    dict(name="k5_d10007", K=5, d=10007, seed=93, density=0.1, weights=[1.0, 0.5, 0.25, 2.0, 1.5]),
+    dict(name="k2_d40000", K=2, d=40000, seed=94, density=0.5, weights=[0.6, 0.4]),
+]
