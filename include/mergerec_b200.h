@@ -264,6 +264,16 @@ int mr_pcb_vectors(const float* base, const float* const* models, int K, int64_t
                    const float* clamp_hi, int64_t q_index, float* out, int64_t ldo, float* task_out, float* thr_out,
                    void* ws, int64_t ws_bytes, mr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Sharded merger: the flat vector is split over ranks; the global TIES trim
+ * (ref: merger/algorithms/ties.py:14-23, top-k over the WHOLE vector) is found by three radix passes over the
+ * 31 magnitude bits.  hist[k, bin] += #{ j < d : |w_k (m_k[j] - base[j])| falls in `bin` }, bins of 11 / 10 / 10
+ * bits (pass 0: bits >> 20; pass 1: (bits >> 10) & 1023 among bits >> 20 == prefix[k]; pass 2: bits & 1023 among
+ * bits >> 10 == prefix[k]).  hist: dev int64 (K, 2048), accumulated; the caller zeroes it, all-reduces it over the
+ * ranks and picks the bin (mergerec_b200/merger/sharded.py).  w: dev K floats or NULL. */
+int mr_ties_mag_hist(const float* base, const float* const* models, int K, int64_t d, const float* w, int pass,
+                     const uint32_t* prefix, int64_t* hist, mr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

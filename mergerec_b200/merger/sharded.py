@@ -1,0 +1,259 @@
+"""Training-free merges over a flat vector that is SHARDED across GPUs (merger rows).
+
+The reference is single-process (`ModelMerger`, merger/merger.py:10-107).  Here rank r keeps columns [lo_r, hi_r) of
+every flat vector (`flat_shard_bounds`: boundaries are multiples of 32, so ATen's interleaved `torch.sum(dim=0)` order
+on the trailing `d mod 32` columns falls entirely on the last rank, exactly where the single-GPU kernels apply it) and:
+
+* task-arithmetic / linear merges need no communication at all (independent columns);
+* the TIES trim is GLOBAL over the whole vector (ties.py:14-23), so the k-th largest magnitude is found with three
+  radix passes (`mr_ties_mag_hist`) whose (K, 2048) int64 histograms are summed with ONE all-reduce per pass; when
+  equal magnitudes straddle the cut, an all-gather of the per-rank tie counts and an exclusive scan in rank order keep
+  the lowest GLOBAL indices (the canonical tie rule) -- the result is bit-identical to the single-GPU merge;
+* `gather_flat` (one all-gather of the merged slices) rebuilds the full vector where a caller wants it on every rank.
+
+One process per GPU, `torch.distributed` (NCCL over NVLink) for the collectives; with the gloo backend the small
+histogram tensors hop through the host, which lets the same code run in world-size-2 tests on one GPU or on CPU
+(with `kernels=` replaced by a stand-in -- the product path always uses the CUDA kernels)."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib
+from .algorithms import ties as _ties
+from .algorithms._common import as_rows, merge_axpy, weights_tensor
+from .layout import alloc_rows
+from .merger import ModelMerger
+from .types import StateDict
+from .utils.model_operations import unflatten_model
+
+__all__ = ["flat_shard_bounds", "sharded_select", "get_ties_vectors_sharded", "merge_ties_sharded",
+           "merge_task_vector_sharded", "merge_linear_sharded", "gather_flat", "ShardedModelMerger", "CudaKernels"]
+
+BINS = 2048
+
+
+def flat_shard_bounds(d: int, world: int, rank: int) -> Tuple[int, int]:
+    """Columns [lo, hi) of the flat vector owned by `rank`: contiguous 32-column blocks, sizes differ by at most one
+    block, the (possibly partial) last block goes to the last non-empty rank."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    nblk = (d + 31) // 32
+    base, rem = divmod(nblk, world)
+    lo_blk = rank * base + min(rank, rem)
+    hi_blk = lo_blk + base + (1 if rank < rem else 0)
+    return min(lo_blk * 32, d), min(hi_blk * 32, d)
+
+
+def _world(group) -> Tuple[int, int]:
+    if group is None:
+        return 1, 0
+    import torch.distributed as dist
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _host_hop(t: torch.Tensor, group) -> bool:
+    import torch.distributed as dist
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
+def _all_reduce_sum(t: torch.Tensor, group) -> torch.Tensor:
+    if group is None:
+        return t
+    import torch.distributed as dist
+    if _host_hop(t, group):
+        c = t.cpu()
+        dist.all_reduce(c, group=group)
+        t.copy_(c)
+    else:
+        dist.all_reduce(t, group=group)
+    return t
+
+
+def _all_gather(t: torch.Tensor, group) -> torch.Tensor:
+    """(world, *t.shape)."""
+    world, _ = _world(group)
+    if world == 1:
+        return t.unsqueeze(0)
+    import torch.distributed as dist
+    src = t.cpu() if _host_hop(t, group) else t
+    out = torch.empty((world * src.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    dist.all_gather_into_tensor(out, src.contiguous(), group=group)
+    return out.view((world,) + tuple(src.shape)).to(t.device)
+
+
+class CudaKernels:
+    """The three kernel entry points the sharded path needs (the product path; tests may inject stand-ins)."""
+
+    @staticmethod
+    def mag_hist(base, rows, w, p: int, prefix, hist) -> None:
+        d = base.numel()
+        rc = _lib.load().mr_ties_mag_hist(_lib.dptr(base, torch.float32), _lib.ptr_array(rows), len(rows), d, _lib.dptr(w), p,
+                                          _lib.dptr(prefix), _lib.dptr(hist), _lib.stream_handle())
+        _lib.check(rc, "mr_ties_mag_hist")
+
+    @staticmethod
+    def ties_build(base, rows, cut, mode: int, w=None, out=None, ldo: int = 0) -> None:
+        _ties._build(base, rows, cut, mode, w=w, out=out, ldo=ldo)
+
+    @staticmethod
+    def merge(base, rows, w, order: int, src_is_model: bool):
+        return merge_axpy(base, rows, w, order, src_is_model)
+
+    @staticmethod
+    def alloc_rows(K: int, d: int, device):
+        return alloc_rows(K, d, device)
+
+
+def _tie_index(base, row, wk, mag: int, keep: int) -> int:
+    """Local index of the `keep`-th (1-based, ascending) element whose weighted-update magnitude has bit pattern `mag`
+    (rare path: equal magnitudes straddling the global cut inside this rank)."""
+    u = row - base                                   # ties.py:18
+    if wk is not None:
+        u = u * wk                                   # ties.py:20
+    bits = u.view(torch.int32) & 0x7FFFFFFF
+    idx = (bits == mag).nonzero().reshape(-1)
+    return int(idx[keep - 1])
+
+
+def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: int, d_global: int,
+                   w: Optional[torch.Tensor] = None, group=None, kernels=CudaKernels) -> torch.Tensor:
+    """Per-model cut keys FOR THIS RANK'S SLICE (int64 (K,), bit pattern of the uint64 `mr_ties_build` expects with
+    LOCAL indices) such that, over all ranks, exactly the `k_cnt` largest `|w_k (m_k - base)|` of the whole vector
+    survive, equal magnitudes resolved towards the lowest global index."""
+    K, dev = len(rows_l), base_l.device
+    world, rank = _world(group)
+    if k_cnt <= 0:
+        return torch.full((K,), -1, dtype=torch.int64, device=dev)          # 0xFFFF...: nothing survives
+    if k_cnt >= d_global:
+        return torch.zeros(K, dtype=torch.int64, device=dev)                # everything survives
+    left = torch.full((K,), int(k_cnt), dtype=torch.int64, device=dev)
+    prefix = None
+    local_last = None
+    chosen = None
+    for p in range(3):
+        hist = torch.zeros((K, BINS), dtype=torch.int64, device=dev)
+        if base_l.numel():
+            kernels.mag_hist(base_l, rows_l, w, p, None if prefix is None else prefix.to(torch.int32), hist)
+        if p == 2:
+            local_last = hist.clone()
+        hist = _all_reduce_sum(hist, group)
+        top = hist.flip(1).cumsum(1)                                         # top[:, i] = count in the i+1 highest bins
+        i = (top < left[:, None]).sum(1).clamp(max=BINS - 1)                # first i with top[:, i] >= left
+        above = torch.where(i > 0, top.gather(1, (i - 1).clamp(min=0)[:, None]).squeeze(1), torch.zeros_like(left))
+        left = left - above
+        chosen = (BINS - 1) - i
+        prefix = chosen if p == 0 else ((prefix << 10) | chosen)
+    mag = prefix                                                             # 31 magnitude bits of the cut
+    mine = local_last.gather(1, chosen[:, None]).squeeze(1)                  # my elements at exactly that magnitude
+    counts = _all_gather(mine, group)                                        # (world, K)
+    before = counts[:rank].sum(0) if rank > 0 else torch.zeros_like(mine)
+    keep = torch.minimum((left - before).clamp(min=0), mine)                 # how many of MY ties survive
+    cut_all = mag << 32                                                      # every element at `mag` survives here
+    cut_none = (mag + 1) << 32                                               # none does
+    cut = torch.where(keep >= mine, cut_all, cut_none)
+    partial = (keep > 0) & (keep < mine)
+    if bool(partial.any()):
+        for k in torch.nonzero(partial).reshape(-1).tolist():
+            j = _tie_index(base_l, rows_l[k], None if w is None else w.reshape(-1)[k], int(mag[k]), int(keep[k]))
+            cut[k] = (int(mag[k]) << 32) | (0xFFFFFFFF - j)
+    return cut
+
+
+def _local(models) -> List[torch.Tensor]:
+    return as_rows(models)
+
+
+def get_ties_vectors_sharded(base_l: torch.Tensor, models_l, density: float, d_global: int, group=None,
+                             kernels=CudaKernels) -> torch.Tensor:
+    """This rank's columns of `get_ties_vectors` (ties.py:55-72) of the whole vector: (K, d_local)."""
+    rows = _local(models_l)
+    K, d = len(rows), base_l.numel()
+    cut = sharded_select(base_l, rows, _ties.ties_topk_count(density, d_global), d_global, None, group, kernels)
+    out = kernels.alloc_rows(K, d, base_l.device)
+    if d:
+        kernels.ties_build(base_l, rows, cut, _lib.MR_TIES_VECTORS, out=out, ldo=max(out.stride(0), d))
+    return out
+
+
+def merge_ties_sharded(base_l: torch.Tensor, models_l, weights: Sequence[float], density: float, d_global: int,
+                       group=None, kernels=CudaKernels) -> torch.Tensor:
+    """This rank's columns of `merge_ties` (ties.py:75-83): weight, global trim, sum -- no election."""
+    rows = _local(models_l)
+    assert len(rows) == len(weights), "Number of models and weights should match."
+    w = torch.tensor([float(x) for x in weights], dtype=torch.float32, device=base_l.device)
+    cut = sharded_select(base_l, rows, _ties.ties_topk_count(density, d_global), d_global, w, group, kernels)
+    out = torch.empty_like(base_l)
+    if base_l.numel():
+        kernels.ties_build(base_l, rows, cut, _lib.MR_TIES_TRIMSUM, w=w, out=out)
+    return out
+
+
+def merge_task_vector_sharded(base_l: torch.Tensor, models_l, weights: Sequence[float], kernels=CudaKernels) -> torch.Tensor:
+    """This rank's columns of `merge_task_vector` (task_vector.py:13-34); columns are independent: no collective."""
+    rows = _local(models_l)
+    assert len(rows) == len(weights), "Number of models and weights should match."
+    if not base_l.numel():
+        return torch.empty_like(base_l)
+    return kernels.merge(base_l, rows, weights_tensor(weights, base_l.device), _lib.MR_ORDER_BASE_FIRST, True)
+
+
+def merge_linear_sharded(models_l, weights: Sequence[float], kernels=CudaKernels) -> torch.Tensor:
+    """This rank's columns of `merge_linear` (linear.py:8-27)."""
+    rows = _local(models_l)
+    assert len(rows) == len(weights), "Number of models and weights should match."
+    if not rows[0].numel():
+        return torch.empty_like(rows[0])
+    return kernels.merge(None, rows, weights_tensor(weights, rows[0].device), _lib.MR_ORDER_LINEAR, False)
+
+
+def gather_flat(local: torch.Tensor, d_global: int, group=None) -> torch.Tensor:
+    """All ranks' slices -> the full flat vector on every rank (one all-gather; slices padded to the largest)."""
+    world, rank = _world(group)
+    if world == 1:
+        return local
+    bounds = [flat_shard_bounds(d_global, world, r) for r in range(world)]
+    width = max(hi - lo for lo, hi in bounds)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[:local.numel()] = local
+    allp = _all_gather(padded, group)
+    return torch.cat([allp[r, :hi - lo] for r, (lo, hi) in enumerate(bounds)])
+
+
+class ShardedModelMerger(ModelMerger):
+    """`ModelMerger` (merger/merger.py:10-93) whose flat vectors are sharded over the ranks of `group`.  Same
+    constructor and `merge(merge_type, weights, **kwargs)` contract for "linear", "task_vector" and "ties"; the merged
+    state_dict returned on every rank is bit-identical to the single-GPU one."""
+
+    def __init__(self, models: Sequence[StateDict], base_model: Optional[StateDict] = None, align_key_order: bool = True,
+                 group=None):
+        super().__init__(models, base_model, align_key_order)
+        self.group = group
+        world, rank = _world(group)
+        self.d_global = self.models[0].numel()
+        lo, hi = flat_shard_bounds(self.d_global, world, rank)
+        self.bounds = (lo, hi)
+        self.models = [m[lo:hi].clone() for m in self.models]
+        if self.base_model is not None:
+            self.base_model = self.base_model[lo:hi].clone()
+
+    @torch.no_grad()
+    def merge(self, merge_type: str, weights, **kwargs) -> StateDict:
+        if isinstance(weights, float):
+            weights = [weights] * len(self.models)
+        elif not (isinstance(weights, list) and all(isinstance(w, float) for w in weights)):
+            raise ValueError("Weights should be a float or a list of floats.")
+        if merge_type in ("task_vector", "ties") and self.base_model is None:
+            raise ValueError(f"{'Task vector' if merge_type == 'task_vector' else 'TIES'} merge requires a base model.")
+        if merge_type == "linear":
+            local = merge_linear_sharded(self.models, weights)
+        elif merge_type == "task_vector":
+            local = merge_task_vector_sharded(self.base_model, self.models, weights)
+        elif merge_type == "ties":
+            local = merge_ties_sharded(self.base_model, self.models, weights, kwargs["density"], self.d_global, self.group)
+        elif merge_type in ("dare", "pcb"):
+            raise NotImplementedError(f"Merge type '{merge_type}' has no sharded implementation.")
+        else:
+            raise ValueError(f"Merge type '{merge_type}' is not supported.")
+        return unflatten_model(gather_flat(local, self.d_global, self.group), self.shape_dict)
