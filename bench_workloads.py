@@ -586,6 +586,108 @@ class CollabStepCfg3(Workload):
                 "sample": "the step's two merger passes only (lambda merge + lambda-gradient, full d, K=8), OpenMP C oracle port"}
 
 
+class TiesSharded(TiesCfg2):
+    """SURVEY.md section 8(e), merger row: the TIES merge of BASELINE config 2 with the flat vector SHARDED over the
+    ranks (d/G columns per GPU, 32-column aligned).  One step = global trim threshold (per-slice order statistic, then two
+    windowed radix levels of `mr_ties_mag_hist` with one NCCL all-reduce of K x 2049 int64 each + two all-gathers of K values), TIES build of
+    the local slice, task-wise lambda merge of the local slice.  Strong scaling: the whole job's algorithmic bytes
+    ((2K+1) + (K+2)) * d * 4 divided by the slowest rank's time.  Results are bit-identical to the single-GPU merge
+    (tests/test_sharded_merger_gpu.py)."""
+
+    name = "ties_sharded"
+    scaling = "strong"
+    launches_per_step = 14  # per-slice select (10), 2 x mag_hist, build, merge (plus torch's tiny histogram-walk ops and the collectives)
+
+    def config(self):
+        return {"workload": "TIES (density 0.2) of K=8 BLaIR-base models, flat vector sharded d/G per GPU; global trim via "
+                            "all-reduced radix histograms; local build + task-wise lambda merge",
+                "K": self.K, "d": self.d, "density": 0.2, "l2": "per-rank inputs (4.5 GB / G) exceed L2 for G <= 8",
+                "parallelism": f"flat dimension sharded x{self.world}, 2 all-reduces of 131 KB + 2 small all-gathers per step"
+                if self.world > 1 else "1 GPU (same code path, no collective)"}
+
+    def setup(self):
+        import torch.distributed as dist
+        from mergerec_b200.merger.layout import alloc_rows
+        from mergerec_b200.merger.sharded import flat_shard_bounds
+        g = torch.Generator(device=self.device).manual_seed(1234)    # same vectors on every rank, then keep the slice
+        d, K = self.d, self.K
+        lo, hi = flat_shard_bounds(d, self.world, self.rank)
+        self.lo, self.hi = lo, hi
+        base = torch.randn(d, generator=g, device=self.device) * 0.02
+        self.models = []
+        for _ in range(K):
+            self.models.append((base + 1e-3 * torch.randn(d, generator=g, device=self.device))[lo:hi].clone())
+        self.base = base[lo:hi].clone()
+        del base
+        self.group = dist.group.WORLD if self.world > 1 else None
+        self.That = alloc_rows(K, hi - lo, self.device)
+        self.Trows = list(self.That.unbind(0))
+        self.w = torch.full((1, K), 0.3, dtype=torch.float32, device=self.device)
+        self.out = torch.empty(hi - lo, dtype=torch.float32, device=self.device)
+
+    def _select(self):
+        from mergerec_b200.merger.sharded import sharded_select
+        return sharded_select(self.base, self.models, int(0.2 * self.d), self.d, None, self.group)
+
+    def _build(self, cut):
+        from mergerec_b200 import _lib
+        from mergerec_b200.merger.algorithms import ties as T
+        T._build(self.base, self.models, cut, _lib.MR_TIES_VECTORS, out=self.That, ldo=max(self.That.stride(0), self.hi - self.lo))
+
+    def _merge_only(self):
+        from mergerec_b200 import _lib
+        from mergerec_b200.merger.algorithms._common import merge_axpy
+        merge_axpy(self.base, self.Trows, self.w, _lib.MR_ORDER_SUM_FIRST, False, out=self.out)
+
+    def step(self):
+        self._build(self._select())
+        self._merge_only()
+
+    def units_per_step_all_ranks(self):
+        return self.bytes_per_step / GB      # strong scaling: one job, whatever the number of ranks
+
+    def setup_e2e(self):
+        n = self.hi - self.lo
+        self.h_base = _pinned(self.base.cpu())
+        self.h_models = [_pinned(m.cpu()) for m in self.models]
+        self.h_out = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        self.h2d_bytes = (self.K + 1) * n * 4
+        self.d2h_bytes = n * 4
+
+    def roofline(self, peaks):
+        from bench import event_time_ms
+        from mergerec_b200.merger.sharded import CudaKernels
+        n, K = self.hi - self.lo, self.K
+        cut = self._select()
+        hist = torch.zeros((K, 2048), dtype=torch.int64, device=self.device)
+        above = torch.zeros(K, dtype=torch.int64, device=self.device)
+        lo = ((cut >> 32) - (1 << 17)).clamp(min=0).to(torch.int32)          # the usual first window around the cut
+        sh = torch.full((K,), 7, dtype=torch.int32, device=self.device)
+        ms_hist = event_time_ms(lambda: CudaKernels.mag_hist(self.base, self.models, None, lo, sh, hist, above), 10)
+        ms_select = event_time_ms(self._select, 5)
+        ms_build = event_time_ms(lambda: self._build(cut), 10)
+        ms_merge = event_time_ms(self._merge_only, 10)
+        b_build, b_hist, b_merge = (2 * K + 1) * n * 4, (K + 1) * n * 4, (K + 2) * n * 4
+        ach = b_build / GB / (ms_build * 1e-3)
+        return {"bound": "hbm", "kernel": "mr::ties_build_kernel<8, VECTORS, vec4> on this rank's slice",
+                "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms_build,
+                "algorithmic_bytes_per_launch": b_build,
+                "other_kernels": {
+                    "mag_hist_kernel (one windowed radix level)": {"ms": ms_hist, "GB/s": b_hist / GB / (ms_hist * 1e-3), "bytes": b_hist},
+                    "sharded select (per-slice order statistic + 2 windowed levels + all-reduces + tie scan)": {"ms": ms_select},
+                    "lambda merge of the slice (merge_kernel)": {"ms": ms_merge, "GB/s": b_merge / GB / (ms_merge * 1e-3), "bytes": b_merge}}}
+
+    def extra(self):
+        # exact integer checksum of the merged vector's bit patterns, summed over the ranks: independent of the sharding
+        # because the sharded merge is bit-identical to the single-GPU one (compare the lines of different --gpus)
+        chk = self.out.view(torch.int32).to(torch.int64).sum().reshape(1)
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(chk, group=self.group)
+        return {"slice": [self.lo, self.hi], "merged_bits_checksum": int(chk.item())}
+
+
 class DistillStep(Workload):
     """The distillation half of a collaborative-merging step (reference:
     module/distiller/sequence/module.py:59-76 + loss_fn.py KD loss): catalogue logits of 16 pseudo-user representations
@@ -690,5 +792,5 @@ class DistillStep(Workload):
 
 
 WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8, TiesCfg2.name: TiesCfg2, EvalCatalog.name: EvalCatalog,
-             CollabStepCfg3.name: CollabStepCfg3, DistillStep.name: DistillStep}
+             CollabStepCfg3.name: CollabStepCfg3, DistillStep.name: DistillStep, TiesSharded.name: TiesSharded}
 DEFAULT_WORKLOAD = TiesCfg2.name

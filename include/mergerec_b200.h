@@ -266,13 +266,19 @@ int mr_pcb_vectors(const float* base, const float* const* models, int K, int64_t
 
 /* ------------------------------------------------------------------------------------------------
  * Sharded merger: the flat vector is split over ranks; the global TIES trim
- * (ref: merger/algorithms/ties.py:14-23, top-k over the WHOLE vector) is found by three radix passes over the
- * 31 magnitude bits.  hist[k, bin] += #{ j < d : |w_k (m_k[j] - base[j])| falls in `bin` }, bins of 11 / 10 / 10
- * bits (pass 0: bits >> 20; pass 1: (bits >> 10) & 1023 among bits >> 20 == prefix[k]; pass 2: bits & 1023 among
- * bits >> 10 == prefix[k]).  hist: dev int64 (K, 2048), accumulated; the caller zeroes it, all-reduces it over the
- * ranks and picks the bin (mergerec_b200/merger/sharded.py).  w: dev K floats or NULL. */
-int mr_ties_mag_hist(const float* base, const float* const* models, int K, int64_t d, const float* w, int pass,
-                     const uint32_t* prefix, int64_t* hist, mr_stream_t stream);
+ * (ref: merger/algorithms/ties.py:14-23, top-k over the WHOLE vector) is found by radix refinement of a window of
+ * magnitude bit patterns.  For model k and every j < d with bits = bits(|w_k (m_k[j] - base[j])|):
+ *   lo[k] <= bits < lo[k] + (2048 << shift[k])  ->  hist[k, (bits - lo[k]) >> shift[k]] += 1
+ *   bits >= lo[k] + (2048 << shift[k])          ->  above[k] += 1
+ * hist: dev int64 (K, 2048), above: dev int64 (K), both accumulated; the caller zeroes them, all-reduces them over the
+ * ranks and picks the bin (mergerec_b200/merger/sharded.py).  lo: dev uint32 (K), shift: dev int32 (K); lo = 0,
+ * shift = 20 covers every magnitude.  w: dev K floats or NULL.
+ * cand (optional, dev uint32 (K, cand_cap, 2)) / cand_count (dev uint32 (K), zeroed by the caller): for the models with
+ * shift[k] == 0, every in-window element also appends (bin, j); cand_count[k] may end above cand_cap (list truncated).
+ * The lists resolve equal magnitudes that straddle the cut (lowest index first) without another pass. */
+int mr_ties_mag_hist(const float* base, const float* const* models, int K, int64_t d, const float* w, const uint32_t* lo,
+                     const int32_t* shift, int64_t* hist, int64_t* above, uint32_t* cand, uint32_t* cand_count,
+                     int cand_cap, mr_stream_t stream);
 
 #ifdef __cplusplus
 }

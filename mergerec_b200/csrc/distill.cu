@@ -478,13 +478,14 @@ ds_loss_kernel(const __grid_constant__ DsLossArgs args, const float* __restrict_
     __shared__ double s_sum[(kDsLossThreads / 32) * 5];
     const int b = blockIdx.x;
     const int n = args.n[b];
-    const float* z = logits + (int64_t)b * ld;
-    const float* t = args.teacher[b];
-    float* g = gz ? gz + (int64_t)b * ldg : nullptr;
+    const float* __restrict__ z = logits + (int64_t)b * ld;
+    const float* __restrict__ t = args.teacher[b];
+    float* __restrict__ g = gz ? gz + (int64_t)b * ldg : nullptr;
     const bool has_t = (t != nullptr);
     if (n <= 0) { if (threadIdx.x == 0) loss[b] = 0.f; return; }
 
     ArgMax az{-INFINITY, 0x7fffffff}, at{-INFINITY, 0x7fffffff};
+#pragma unroll 4
     for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
         az = better(az, ArgMax{z[i], i});
         if (has_t) at = better(at, ArgMax{t[i], i});
@@ -494,14 +495,16 @@ ds_loss_kernel(const __grid_constant__ DsLossArgs args, const float* __restrict_
 
     if (mix.pairwise) {  // hinge on (best, second-best) teacher items
         ArgMax an{-INFINITY, 0x7fffffff};
-        for (int i = threadIdx.x; i < n; i += kDsLossThreads)
+    #pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += kDsLossThreads)
             if (i != at.i) an = better(an, ArgMax{t[i], i});
         an = block_argmax(an, s_am);
         const int neg = (an.i == 0x7fffffff) ? 0 : an.i;  // n == 1: argmax of an all -inf row is index 0
         const float h = margin - (z[at.i] - z[neg]);
         const bool active = h > 0.f;
         if (g) {
-            for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
+        #pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
                 float v = 0.f;
                 if (active) v = (i == at.i ? -1.f : 0.f) + (i == neg ? 1.f : 0.f);
                 g[i] = v;
@@ -516,6 +519,7 @@ ds_loss_kernel(const __grid_constant__ DsLossArgs args, const float* __restrict_
     // sums: [0] S1 = sum exp(z-mz); [1] ST = sum exp((z-mz)/T); [2] PT = sum e_t; [3] sum e_t ((t-mt)-(z-mz)); [4] sum (z-t)^2
     // (for ListNet [3] holds sum e_t (z-mz) instead)
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
     for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
         const float zc = z[i] - az.v;
         acc[0] += (double)expf(zc);
@@ -544,7 +548,8 @@ ds_loss_kernel(const __grid_constant__ DsLossArgs args, const float* __restrict_
     double hbar = 0.0;
     if (mix.cE != 0.f) {  // entropy of softmax(z) with the reference's +1e-8 inside the log (loss_fn.py:65-66)
         double e2[2] = {0.0, 0.0};
-        for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
+    #pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
             const float p = expf(z[i] - az.v) * inv_S1;
             const float lp = logf(p + 1e-8f);
             e2[0] += (double)p * (double)lp;
@@ -559,7 +564,8 @@ ds_loss_kernel(const __grid_constant__ DsLossArgs args, const float* __restrict_
     if (g) {
         const float kd_scale = mix.cK * T + mix.cL * invT;  // d/dz of T^2 KL(P || Q_T) is T (Q - P); ListNet: (Q - P)/T
         const float mse_scale = mix.cM * 2.0f / (float)n;
-        for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
+    #pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
             const float zc = z[i] - az.v;
             float v = 0.f;
             if (mix.cA != 0.f || mix.cE != 0.f) {

@@ -87,10 +87,23 @@ class CudaKernels:
     """The three kernel entry points the sharded path needs (the product path; tests may inject stand-ins)."""
 
     @staticmethod
-    def mag_hist(base, rows, w, p: int, prefix, hist) -> None:
+    def rows(models) -> List[torch.Tensor]:
+        return as_rows(models)          # raises for anything that is not an fp32 CUDA row: no CPU path
+
+    @staticmethod
+    def kth_largest_bits(base, rows, k: int, w) -> torch.Tensor:
+        """Bit pattern (int64 (K,)) of this slice's k-th largest magnitude -- the single-GPU selection kernels."""
+        return _ties.select_kth_largest(base, rows, k, w) >> 32
+
+    @staticmethod
+    def mag_hist(base, rows, w, lo, shift, hist, above, cand=None, cand_count=None) -> None:
+        """cand (K, cap, 2) int32 / cand_count (K) int32, optional: (bin, local index) of the in-window elements of
+        the models whose shift is 0."""
         d = base.numel()
-        rc = _lib.load().mr_ties_mag_hist(_lib.dptr(base, torch.float32), _lib.ptr_array(rows), len(rows), d, _lib.dptr(w), p,
-                                          _lib.dptr(prefix), _lib.dptr(hist), _lib.stream_handle())
+        rc = _lib.load().mr_ties_mag_hist(_lib.dptr(base, torch.float32), _lib.ptr_array(rows), len(rows), d, _lib.dptr(w),
+                                          _lib.dptr(lo, torch.int32), _lib.dptr(shift, torch.int32), _lib.dptr(hist),
+                                          _lib.dptr(above), _lib.dptr(cand), _lib.dptr(cand_count),
+                                          0 if cand is None else cand.shape[1], _lib.stream_handle())
         _lib.check(rc, "mr_ties_mag_hist")
 
     @staticmethod
@@ -117,36 +130,113 @@ def _tie_index(base, row, wk, mag: int, keep: int) -> int:
     return int(idx[keep - 1])
 
 
+MARGIN_BITS = 1 << 17      # widen the first window by ~1 % of a binade on both sides of the per-rank estimates
+FULL_SHIFT = 20            # lo = 0, shift = 20: 2048 bins of 2^20 cover all 31 magnitude bits
+CAND_CAP = 1 << 16         # per-model capacity of the (bin, index) list recorded at the last level
+
+
+def _ceil_log2(x: torch.Tensor) -> torch.Tensor:
+    """ceil(log2(x)) for int64 x >= 1 (exact: float64 holds 2^31)."""
+    return torch.ceil(torch.log2(x.to(torch.float64))).to(torch.int64)
+
+
 def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: int, d_global: int,
                    w: Optional[torch.Tensor] = None, group=None, kernels=CudaKernels) -> torch.Tensor:
     """Per-model cut keys FOR THIS RANK'S SLICE (int64 (K,), bit pattern of the uint64 `mr_ties_build` expects with
     LOCAL indices) such that, over all ranks, exactly the `k_cnt` largest `|w_k (m_k - base)|` of the whole vector
-    survive, equal magnitudes resolved towards the lowest global index."""
+    survive, equal magnitudes resolved towards the lowest global index.
+
+    1. every rank takes the proportional order statistic of ITS slice (the single-GPU select); the global cut lies
+       between the smallest and the largest of them, which gives a first window a few per cent wide;
+    2. windowed histogram of the slice (`mr_ties_mag_hist`) -> all-reduce -> walk from the top to the bin holding rank
+       k -> that bin becomes the next window, 11 bits finer; repeat until a bin is a single bit pattern (2 levels for
+       the usual window, 3 for the full range, which is also the fallback when a window misses);
+    3. all-gather of the per-rank counts AT the cut magnitude, exclusive scan in rank order: lowest global index first."""
     K, dev = len(rows_l), base_l.device
     world, rank = _world(group)
     if k_cnt <= 0:
         return torch.full((K,), -1, dtype=torch.int64, device=dev)          # 0xFFFF...: nothing survives
     if k_cnt >= d_global:
         return torch.zeros(K, dtype=torch.int64, device=dev)                # everything survives
-    left = torch.full((K,), int(k_cnt), dtype=torch.int64, device=dev)
-    prefix = None
-    local_last = None
-    chosen = None
-    for p in range(3):
-        hist = torch.zeros((K, BINS), dtype=torch.int64, device=dev)
-        if base_l.numel():
-            kernels.mag_hist(base_l, rows_l, w, p, None if prefix is None else prefix.to(torch.int32), hist)
-        if p == 2:
-            local_last = hist.clone()
-        hist = _all_reduce_sum(hist, group)
+    d_l = base_l.numel()
+    if d_l:
+        k_l = min(max(int(round(k_cnt * d_l / d_global)), 1), d_l)
+        est = kernels.kth_largest_bits(base_l, rows_l, k_l, w).to(torch.int64)
+    else:
+        est = torch.full((K,), -1, dtype=torch.int64, device=dev)           # an empty slice has no estimate
+    ests = _all_gather(est, group)                                           # (world, K)
+    valid = ests >= 0
+    big = torch.full_like(ests, 0x7FFFFFFF)
+    lo = (torch.where(valid, ests, big).min(0).values - MARGIN_BITS).clamp(min=0)
+    hi = (torch.where(valid, ests, torch.zeros_like(ests)).max(0).values + MARGIN_BITS).clamp(max=0x7FFFFFFF)
+    shift = (_ceil_log2(hi - lo + 1) - 11).clamp(min=0)
+    k_t = torch.full((K,), int(k_cnt), dtype=torch.int64, device=dev)
+    left = k_t.clone()
+    mag = torch.zeros(K, dtype=torch.int64, device=dev)
+    mine = torch.zeros(K, dtype=torch.int64, device=dev)
+    done = torch.zeros(K, dtype=torch.bool, device=dev)
+    tie_j = torch.full((K, CAND_CAP), 0x7FFFFFFF, dtype=torch.int64, device=dev)   # ascending local indices AT the cut
+    tie_ok = torch.ones(K, dtype=torch.bool, device=dev)                              # the list was not truncated
+    width = torch.full((K,), BINS, dtype=torch.int64, device=dev)    # bins of the current window that belong to the search
+    first = True
+    for _level in range(8):
+        both = torch.zeros((K, BINS + 1), dtype=torch.int64, device=dev)    # [:, :BINS] histogram, [:, BINS] above
+        hist_l, above_l = both[:, :BINS], both[:, BINS]
+        if d_l:
+            h = torch.zeros((K, BINS), dtype=torch.int64, device=dev)
+            a = torch.zeros(K, dtype=torch.int64, device=dev)
+            cand = cnt = None
+            if not first and bool(((shift == 0) & ~done).any()):           # a model resolves at this level
+                cand = torch.empty((K, CAND_CAP, 2), dtype=torch.int32, device=dev)
+                cnt = torch.zeros(K, dtype=torch.int32, device=dev)
+            kernels.mag_hist(base_l, rows_l, w, lo.to(torch.int32), shift.to(torch.int32), h, a, cand, cnt)
+            hist_l.copy_(h)
+            above_l.copy_(a)
+        else:
+            cand = cnt = None
+        local_hist = hist_l.clone()
+        both = _all_reduce_sum(both, group)
+        hist, above = both[:, :BINS], both[:, BINS]
+        if first:
+            # the window must contain global rank k_cnt; where it does not (adversarial shards) restart on the full range
+            miss = (above >= k_t) | (above + hist.sum(1) < k_t)
+            if bool(miss.any()):
+                lo = torch.where(miss, torch.zeros_like(lo), lo)
+                shift = torch.where(miss, torch.full_like(shift, FULL_SHIFT), shift)
+                if bool(miss.all()):
+                    continue
+                # models whose window was fine simply repeat the same level
+                continue
+            left = k_t - above
+            first = False
+        # a refined window may be wider than the bin it refines (2048 << shift' >= 1 << shift): ignore the excess bins,
+        # their elements were already counted as lying above
+        hist = torch.where(torch.arange(BINS, device=dev)[None, :] < width[:, None], hist, torch.zeros_like(hist))
         top = hist.flip(1).cumsum(1)                                         # top[:, i] = count in the i+1 highest bins
         i = (top < left[:, None]).sum(1).clamp(max=BINS - 1)                # first i with top[:, i] >= left
-        above = torch.where(i > 0, top.gather(1, (i - 1).clamp(min=0)[:, None]).squeeze(1), torch.zeros_like(left))
-        left = left - above
+        over = torch.where(i > 0, top.gather(1, (i - 1).clamp(min=0)[:, None]).squeeze(1), torch.zeros_like(left))
         chosen = (BINS - 1) - i
-        prefix = chosen if p == 0 else ((prefix << 10) | chosen)
-    mag = prefix                                                             # 31 magnitude bits of the cut
-    mine = local_last.gather(1, chosen[:, None]).squeeze(1)                  # my elements at exactly that magnitude
+        final = (shift == 0) & ~done
+        mag = torch.where(final, lo + chosen, mag)
+        mine = torch.where(final, local_hist.gather(1, chosen[:, None]).squeeze(1), mine)
+        if cand is not None:
+            # local indices of my elements at exactly the cut magnitude, ascending (others pushed to the end)
+            n_c = cnt.to(torch.int64).clamp(max=CAND_CAP)
+            slot = torch.arange(CAND_CAP, device=dev)[None, :]
+            hit = (slot < n_c[:, None]) & (cand[:, :, 0].to(torch.int64) == chosen[:, None])
+            j_sorted = torch.where(hit, cand[:, :, 1].to(torch.int64) & 0xFFFFFFFF, torch.full_like(tie_j, 1 << 40)).sort(1).values
+            tie_j = torch.where(final[:, None], j_sorted, tie_j)
+            tie_ok = torch.where(final, cnt.to(torch.int64) <= CAND_CAP, tie_ok)
+        left = torch.where(done, left, left - over)
+        lo = torch.where(done, lo, lo + (chosen << shift))
+        done = done | final
+        new_shift = torch.where(done, torch.zeros_like(shift), (shift - 11).clamp(min=0))
+        width = torch.where(done, torch.ones_like(width), (torch.ones_like(shift) << shift) >> new_shift)
+        shift = new_shift
+        if bool(done.all()):
+            break
+    else:
+        raise _lib.MergeRecLibraryError("sharded TIES select did not converge")
     counts = _all_gather(mine, group)                                        # (world, K)
     before = counts[:rank].sum(0) if rank > 0 else torch.zeros_like(mine)
     keep = torch.minimum((left - before).clamp(min=0), mine)                 # how many of MY ties survive
@@ -154,21 +244,26 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
     cut_none = (mag + 1) << 32                                               # none does
     cut = torch.where(keep >= mine, cut_all, cut_none)
     partial = (keep > 0) & (keep < mine)
-    if bool(partial.any()):
-        for k in torch.nonzero(partial).reshape(-1).tolist():
+    # the keep-th of my tied elements (ascending local index) is the last survivor: taken from the recorded list ...
+    j_keep = tie_j.gather(1, (keep - 1).clamp(min=0, max=CAND_CAP - 1)[:, None]).squeeze(1)
+    cut = torch.where(partial, (mag << 32) | (0xFFFFFFFF - j_keep), cut)
+    # ... unless that list was truncated or not recorded (millions of equal magnitudes; a first-window miss): rescan
+    redo = partial & (~tie_ok | (keep > CAND_CAP) | (j_keep >= (1 << 40)))
+    if bool(redo.any()):
+        for k in torch.nonzero(redo).reshape(-1).tolist():
             j = _tie_index(base_l, rows_l[k], None if w is None else w.reshape(-1)[k], int(mag[k]), int(keep[k]))
             cut[k] = (int(mag[k]) << 32) | (0xFFFFFFFF - j)
     return cut
 
 
-def _local(models) -> List[torch.Tensor]:
-    return as_rows(models)
+def _local(models, kernels) -> List[torch.Tensor]:
+    return kernels.rows(models)
 
 
 def get_ties_vectors_sharded(base_l: torch.Tensor, models_l, density: float, d_global: int, group=None,
                              kernels=CudaKernels) -> torch.Tensor:
     """This rank's columns of `get_ties_vectors` (ties.py:55-72) of the whole vector: (K, d_local)."""
-    rows = _local(models_l)
+    rows = _local(models_l, kernels)
     K, d = len(rows), base_l.numel()
     cut = sharded_select(base_l, rows, _ties.ties_topk_count(density, d_global), d_global, None, group, kernels)
     out = kernels.alloc_rows(K, d, base_l.device)
@@ -180,7 +275,7 @@ def get_ties_vectors_sharded(base_l: torch.Tensor, models_l, density: float, d_g
 def merge_ties_sharded(base_l: torch.Tensor, models_l, weights: Sequence[float], density: float, d_global: int,
                        group=None, kernels=CudaKernels) -> torch.Tensor:
     """This rank's columns of `merge_ties` (ties.py:75-83): weight, global trim, sum -- no election."""
-    rows = _local(models_l)
+    rows = _local(models_l, kernels)
     assert len(rows) == len(weights), "Number of models and weights should match."
     w = torch.tensor([float(x) for x in weights], dtype=torch.float32, device=base_l.device)
     cut = sharded_select(base_l, rows, _ties.ties_topk_count(density, d_global), d_global, w, group, kernels)
@@ -192,7 +287,7 @@ def merge_ties_sharded(base_l: torch.Tensor, models_l, weights: Sequence[float],
 
 def merge_task_vector_sharded(base_l: torch.Tensor, models_l, weights: Sequence[float], kernels=CudaKernels) -> torch.Tensor:
     """This rank's columns of `merge_task_vector` (task_vector.py:13-34); columns are independent: no collective."""
-    rows = _local(models_l)
+    rows = _local(models_l, kernels)
     assert len(rows) == len(weights), "Number of models and weights should match."
     if not base_l.numel():
         return torch.empty_like(base_l)
@@ -201,7 +296,7 @@ def merge_task_vector_sharded(base_l: torch.Tensor, models_l, weights: Sequence[
 
 def merge_linear_sharded(models_l, weights: Sequence[float], kernels=CudaKernels) -> torch.Tensor:
     """This rank's columns of `merge_linear` (linear.py:8-27)."""
-    rows = _local(models_l)
+    rows = _local(models_l, kernels)
     assert len(rows) == len(weights), "Number of models and weights should match."
     if not rows[0].numel():
         return torch.empty_like(rows[0])
