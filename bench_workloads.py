@@ -640,13 +640,22 @@ class TiesSharded(TiesCfg2):
         merge_axpy(self.base, self.Trows, self.w, _lib.MR_ORDER_SUM_FIRST, False, out=self.out)
 
     def step(self):
-        self._build(self._select())
+        self._cut = self._select()
+        self._build(self._cut)
         self._merge_only()
 
     def units_per_step_all_ranks(self):
         return self.bytes_per_step / GB      # strong scaling: one job, whatever the number of ranks
 
     def setup_e2e(self):
+        # (every rank passes here once, after the timed loop) exact integer checksum of the merged vector's bit
+        # patterns summed over the ranks: independent of the sharding because the sharded merge is bit-identical to
+        # the single-GPU one -- compare the lines of different --gpus
+        chk = self.out.view(torch.int32).to(torch.int64).sum().reshape(1)
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(chk, group=self.group)
+        self._checksum = int(chk.item())
         n = self.hi - self.lo
         self.h_base = _pinned(self.base.cpu())
         self.h_models = [_pinned(m.cpu()) for m in self.models]
@@ -658,13 +667,13 @@ class TiesSharded(TiesCfg2):
         from bench import event_time_ms
         from mergerec_b200.merger.sharded import CudaKernels
         n, K = self.hi - self.lo, self.K
-        cut = self._select()
+        cut = self._cut                      # rank 0 only from here on: kernels, no collectives
         hist = torch.zeros((K, 2048), dtype=torch.int64, device=self.device)
         above = torch.zeros(K, dtype=torch.int64, device=self.device)
         lo = ((cut >> 32) - (1 << 17)).clamp(min=0).to(torch.int32)          # the usual first window around the cut
         sh = torch.full((K,), 7, dtype=torch.int32, device=self.device)
         ms_hist = event_time_ms(lambda: CudaKernels.mag_hist(self.base, self.models, None, lo, sh, hist, above), 10)
-        ms_select = event_time_ms(self._select, 5)
+        ms_select = event_time_ms(self._select, 5) if self.world == 1 else None
         ms_build = event_time_ms(lambda: self._build(cut), 10)
         ms_merge = event_time_ms(self._merge_only, 10)
         b_build, b_hist, b_merge = (2 * K + 1) * n * 4, (K + 1) * n * 4, (K + 2) * n * 4
@@ -679,13 +688,7 @@ class TiesSharded(TiesCfg2):
                     "lambda merge of the slice (merge_kernel)": {"ms": ms_merge, "GB/s": b_merge / GB / (ms_merge * 1e-3), "bytes": b_merge}}}
 
     def extra(self):
-        # exact integer checksum of the merged vector's bit patterns, summed over the ranks: independent of the sharding
-        # because the sharded merge is bit-identical to the single-GPU one (compare the lines of different --gpus)
-        chk = self.out.view(torch.int32).to(torch.int64).sum().reshape(1)
-        if self.group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(chk, group=self.group)
-        return {"slice": [self.lo, self.hi], "merged_bits_checksum": int(chk.item())}
+        return {"slice": [self.lo, self.hi], "merged_bits_checksum": self._checksum}
 
 
 class DistillStep(Workload):
