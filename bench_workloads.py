@@ -32,6 +32,24 @@ class Workload:
         return {}
 
 
+def ncu_traffic(kernel: str):
+    """(bytes per launch, source file) of the committed ncu --set full capture of `kernel`, or (None, None)."""
+    import json
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            e = json.load(f).get(kernel)
+        return (e["bytes"], e["source"]) if e else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
+def _with_traffic(roof: Dict, kernel: str) -> Dict:
+    roof["traffic"], src = ncu_traffic(kernel)
+    if src:
+        roof["traffic_source"] = src
+    return roof
+
+
 def _pinned(t: torch.Tensor) -> torch.Tensor:
     out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     out.copy_(t)
@@ -104,10 +122,10 @@ class LambdaMergeK8(Workload):
         from bench import event_time_ms
         ms = event_time_ms(self.step, 20)
         achieved = self.bytes_per_step / GB / (ms * 1e-3)
-        return {"bound": "hbm", "kernel": "mr::merge_kernel<8, SUM_FIRST, segmented, vec4>", "achieved": achieved,
+        return _with_traffic({"bound": "hbm", "kernel": "mr::merge_kernel<8, SUM_FIRST, segmented, vec4>", "achieved": achieved,
                 "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
-                "algorithmic_bytes_per_launch": self.bytes_per_step}
+                "algorithmic_bytes_per_launch": self.bytes_per_step}, "merge_kernel")
 
     # -- CPU arms (oracle port of the reference algorithm)
     def _cpu_inputs(self, d):
@@ -235,7 +253,7 @@ class TiesCfg2(LambdaMergeK8):
         ms_fused = event_time_ms(self.step_fused, 5)
         ach = self.bytes_build / GB / (ms_build * 1e-3)
         sel_bytes = (K + 1) * d * 4
-        return {"bound": "hbm", "kernel": "mr::ties_build_kernel<8, VECTORS, vec4> (get_ties_vectors build pass)",
+        return _with_traffic({"bound": "hbm", "kernel": "mr::ties_build_kernel<8, VECTORS, vec4> (get_ties_vectors build pass)",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms_build,
                 "algorithmic_bytes_per_launch": self.bytes_build,
@@ -244,7 +262,7 @@ class TiesCfg2(LambdaMergeK8):
                     "lambda-gradient reduction (lambda_grad_kernel, incl. host pointer-table upload)": {"ms": ms_lgrad, "GB/s": lgrad_bytes / GB / (ms_lgrad * 1e-3), "bytes": lgrad_bytes},
                     "lambda merge (merge_kernel)": {"ms": ms_merge, "GB/s": self.bytes_merge / GB / (ms_merge * 1e-3), "bytes": self.bytes_merge},
                     "fused select + build + merge without materialising That (merge_ties_lambda)": {"ms": ms_fused, "GB/s": self.bytes_merge / GB / (ms_fused * 1e-3), "bytes": self.bytes_merge},
-                }}
+                }}, "ties_build_kernel")
 
     def extra(self):
         """The second hot path, reported beside the merger line: a short run of the evaluator workload
@@ -544,12 +562,12 @@ class CollabStepCfg3(Workload):
         ms_step = event_time_ms(self.step, 3)
         bytes_merge, bytes_grad = (self.K + 2) * self.d * 4, (self.K + 1) * self.d * 4
         ach = bytes_grad / GB / (ms_grad * 1e-3)
-        return {"bound": "hbm", "kernel": "mr::lg_partial_kernel<8> (+ finish): lambda-gradient reduction (A5)",
+        return _with_traffic({"bound": "hbm", "kernel": "mr::lg_partial_kernel<8> (+ finish): lambda-gradient reduction (A5)",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms_grad,
                 "algorithmic_bytes_per_launch": bytes_grad,
                 "other_kernels": {"lambda merge forward (merge_kernel, A4)": {"ms": ms_merge, "GB/s": bytes_merge / GB / (ms_merge * 1e-3), "bytes": bytes_merge}},
-                "step_ms": ms_step, "merge_plus_grad_share_of_step": (ms_merge + ms_grad) / ms_step}
+                "step_ms": ms_step, "merge_plus_grad_share_of_step": (ms_merge + ms_grad) / ms_step}, "lg_partial_kernel")
 
     def extra(self):
         return {"loss": None if self.loss is None else float(self.loss),
@@ -761,11 +779,11 @@ class DistillStep(Workload):
         ms = event_time_ms(lambda: distill_logits(rep, self.tables, self.dom, out=out), 20)
         ms_step = event_time_ms(self.step, 10)
         ach = self.bytes_tables / GB / (ms * 1e-3)
-        return {"bound": "hbm", "kernel": "mr::ds_logits_kernel<6, 2> (catalogue logits, every item table read once)",
+        return _with_traffic({"bound": "hbm", "kernel": "mr::ds_logits_kernel<6, 2> (catalogue logits, every item table read once)",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
                 "algorithmic_bytes_per_launch": self.bytes_tables, "step_ms": ms_step,
-                "step_GB/s (tables read twice)": 2 * self.bytes_tables / GB / (ms_step * 1e-3)}
+                "step_GB/s (tables read twice)": 2 * self.bytes_tables / GB / (ms_step * 1e-3)}, "ds_logits_kernel")
 
     def extra(self):
         return {"loss": None if self.loss is None else float(self.loss)}

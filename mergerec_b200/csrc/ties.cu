@@ -64,7 +64,7 @@ __device__ __forceinline__ int shift_for(u64 width /* hi - lo */) {
 }
 
 // ---- state init -----------------------------------------------------------------------------------
-__global__ void ties_init_kernel(TiesState* st, int K, u64* cut, int32_t* status, int64_t k_cnt, int64_t d) {
+static __global__ void ties_init_kernel(TiesState* st, int K, u64* cut, int32_t* status, int64_t k_cnt, int64_t d) {
     const int k = threadIdx.x;
     if (k >= K) return;
     TiesState s;
@@ -282,7 +282,7 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 }
 
 // ---- histogram of the keys collected by the full pass (replaces per-element histogram atomics in that pass) ----------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 ties_cand_hist_kernel(const TiesState* __restrict__ st, const uint32_t* __restrict__ cand_cnt,
                       const u64* __restrict__ cand_keys, int cand_cap, int n_lists, uint32_t* __restrict__ hist,
                       u64* __restrict__ above) {
@@ -321,7 +321,7 @@ ties_cand_hist_kernel(const TiesState* __restrict__ st, const uint32_t* __restri
 // rank_hi <= rank_lo are 1-based ranks (largest key = rank 1) in the population the pass visited.  The new
 // bracket spans the bins holding rank_hi .. rank_lo.  strict: both ranks must fall inside the old bracket
 // (exact passes, rank_hi == rank_lo == k_cnt); otherwise they are clamped to it (sample passes).
-__global__ void __launch_bounds__(kTiesBins)
+static __global__ void __launch_bounds__(kTiesBins)
 ties_pick_kernel(TiesState* st, const uint32_t* __restrict__ hist, const u64* __restrict__ above_ctr, int64_t rank_hi,
                  int64_t rank_lo, int strict, int32_t* status) {
     __shared__ u64 s_suffix[kTiesBins + 1];
@@ -394,7 +394,7 @@ ties_pick_kernel(TiesState* st, const uint32_t* __restrict__ hist, const u64* __
 }
 
 // ---- compact the candidates of the refined bracket ------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 ties_compact_kernel(TiesState* st, const uint32_t* __restrict__ cand_cnt, const u64* __restrict__ cand_keys,
                     int cand_cap, int n_lists, uint32_t* fin_cnt, u64* fin_keys, int32_t* status) {
     const int k = blockIdx.y;
@@ -419,7 +419,7 @@ ties_compact_kernel(TiesState* st, const uint32_t* __restrict__ cand_cnt, const 
 }
 
 // ---- final: sort the <= 4096 survivors in shared memory and read off the cut -------------------------------
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 ties_final_kernel(TiesState* st, const uint32_t* __restrict__ fin_cnt, const u64* __restrict__ fin_keys, int64_t k_cnt,
                   u64* cut, int32_t* status) {
     __shared__ u64 s_keys[kTiesFinalCap];
@@ -707,6 +707,56 @@ ties_build_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, 
     for (int64_t q = nq_hot + gtid; q < nq; q += gsz) ties_quad<K, MODE, VEC, MASKS, true>(base, models, d, q, cut, lo_ok, wk, a, fs, hint);
 }
 
+// ---- per-mode launchers of the build kernel ---------------------------------------------------------------------------
+// This file is compiled five times (Makefile): MR_TIES_PART = 0 holds the selection kernels and every C entry point,
+// MR_TIES_PART = 1..4 hold the 64 instantiations (K x alignment x masks) of the build kernel for ONE mode each, so that
+// `make -j` compiles them side by side instead of 256 kernels in one translation unit.
+#ifndef MR_TIES_PART
+#define MR_TIES_PART 0
+#endif
+struct BuildLaunch {
+    const float* base;
+    const float* const* models;
+    int K;
+    int64_t d;
+    const u64* cut;
+    BuildArgs a;
+    size_t smem;
+    int64_t blocks;
+    bool vec, masks;
+    cudaStream_t st;
+};
+int ties_build_launch_vectors(const BuildLaunch& L);
+int ties_build_launch_trimsum(const BuildLaunch& L);
+int ties_build_launch_fused(const BuildLaunch& L);
+int ties_build_launch_lns(const BuildLaunch& L);
+
+#if MR_TIES_PART >= 1
+template <int MODE>
+static int ties_build_launch_mode(const BuildLaunch& L) {
+#define MR_BUILD(VEC, MASKS) \
+    ties_build_kernel<KK, MODE, VEC, MASKS><<<(unsigned)L.blocks, kTiesThreads, L.smem, L.st>>>(L.base, pack, L.d, L.cut, L.a)
+    MR_DISPATCH_K(L.K, {
+        PtrPack<KK> pack;
+        for (int k = 0; k < KK; ++k) pack.p[k] = L.models[k];
+        if (L.vec) { if (L.masks) MR_BUILD(true, true); else MR_BUILD(true, false); }
+        else       { if (L.masks) MR_BUILD(false, true); else MR_BUILD(false, false); }
+    });
+#undef MR_BUILD
+    return MR_OK;
+}
+#if MR_TIES_PART == 1
+int ties_build_launch_vectors(const BuildLaunch& L) { return ties_build_launch_mode<TIES_MODE_VECTORS>(L); }
+#elif MR_TIES_PART == 2
+int ties_build_launch_trimsum(const BuildLaunch& L) { return ties_build_launch_mode<TIES_MODE_TRIMSUM>(L); }
+#elif MR_TIES_PART == 3
+int ties_build_launch_fused(const BuildLaunch& L) { return ties_build_launch_mode<TIES_MODE_FUSED_MERGE>(L); }
+#elif MR_TIES_PART == 4
+int ties_build_launch_lns(const BuildLaunch& L) { return ties_build_launch_mode<TIES_MODE_LNS>(L); }
+#endif
+#endif  // MR_TIES_PART >= 1
+
+#if MR_TIES_PART == 0
 // ---- host-side plumbing ---------------------------------------------------------------------------------------
 struct TiesWs {
     TiesState* st;
@@ -837,9 +887,11 @@ static int ties_check_args(const float* base, const float* const* models, int K,
     }
     return MR_OK;
 }
+#endif  // MR_TIES_PART == 0
 
 }  // namespace mr
 
+#if MR_TIES_PART == 0
 extern "C" int64_t mr_ties_workspace_bytes(int64_t d, int K) {
     if (d <= 0 || K < 1 || K > MR_MAX_K) return 256;
     return (int64_t)mr::ties_layout(nullptr, d, K).total;
@@ -945,23 +997,14 @@ extern "C" int mr_ties_build(const float* base, const float* const* models, int 
                 mode == TIES_MODE_FUSED_MERGE ? P : 1};
     size_t smem = 16;
     if (mode == TIES_MODE_FUSED_MERGE) smem = (((size_t)G * K * 4 + 15) & ~(size_t)15) + ((seg_end && seg_group) ? (size_t)P * 12 : 0) + 16;
-#define MR_BUILD(MODE, VEC, MASKS) \
-    ties_build_kernel<KK, MODE, VEC, MASKS><<<(unsigned)blocks, kTiesThreads, smem, st>>>(base, pack, d, reinterpret_cast<const u64*>(cut), a)
-#define MR_BUILD_VM(MODE)                                                        \
-    do {                                                                         \
-        if (vec) { if (masks) MR_BUILD(MODE, true, true); else MR_BUILD(MODE, true, false); }   \
-        else     { if (masks) MR_BUILD(MODE, false, true); else MR_BUILD(MODE, false, false); } \
-    } while (0)
-    MR_DISPATCH_K(K, {
-        PtrPack<KK> pack;
-        for (int k = 0; k < KK; ++k) pack.p[k] = models[k];
-        if (mode == TIES_MODE_VECTORS) MR_BUILD_VM(TIES_MODE_VECTORS);
-        else if (mode == TIES_MODE_LNS) MR_BUILD_VM(TIES_MODE_LNS);
-        else if (mode == TIES_MODE_TRIMSUM) MR_BUILD_VM(TIES_MODE_TRIMSUM);
-        else MR_BUILD_VM(TIES_MODE_FUSED_MERGE);
-    });
-#undef MR_BUILD_VM
-#undef MR_BUILD
+    BuildLaunch L{base, models, K, d, reinterpret_cast<const u64*>(cut), a, smem, blocks, vec, masks, st};
+    int rc = MR_OK;
+    if (mode == TIES_MODE_VECTORS) rc = ties_build_launch_vectors(L);
+    else if (mode == TIES_MODE_LNS) rc = ties_build_launch_lns(L);
+    else if (mode == TIES_MODE_TRIMSUM) rc = ties_build_launch_trimsum(L);
+    else rc = ties_build_launch_fused(L);
+    if (rc != MR_OK) return rc;
     MR_CUDA_LAUNCH_CHECK("mr_ties_build");
     return MR_OK;
 }
+#endif  // MR_TIES_PART == 0
