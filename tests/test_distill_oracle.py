@@ -83,3 +83,45 @@ def test_no_cpu_path_for_the_losses():
         pytest.skip("GPU present")
     with pytest.raises(_lib.MergeRecLibraryError):
         lf.DistillCELoss()(torch.zeros(1, 8), torch.zeros(1, 8))
+
+
+def test_item_encoding_callbacks_cpu():
+    """`encode_items` / `MultiDatasetItemEncodingCallback` (reference callbacks.py:18-50, 85-118): eval mode during the
+    encoding, training flag restored, one contiguous fp32 table per dataset, encoded once."""
+    import torch
+    from types import SimpleNamespace
+    from mergerec_b200.module.callbacks import ItemEncoderMixin, MultiDatasetItemEncodingCallback
+    from mergerec_b200.module.distiller import DistillSequenceModule
+    from mergerec_b200.module.recommender.loss_fn import DistillAdaMergingLoss
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(8, 8, bias=False)
+            self.drop = torch.nn.Dropout(0.5)
+
+        def forward(self, x):
+            return self.drop(self.lin(x))
+
+        def trainable_parameters(self, **_):
+            return list(self.parameters())
+
+    torch.manual_seed(0)
+    mod = DistillSequenceModule.__new__(DistillSequenceModule)      # the constructor moves teacher scores to the GPU
+    torch.nn.Module.__init__(mod)
+    mod.merged_model, mod.similarity, mod.item_embeddings = Enc(), "cosine", None
+    mod.loss_fn, mod.learning_rate, mod.trainable_args_kwargs = DistillAdaMergingLoss(), 1e-3, {}
+    mod.train()
+    loaders = [[SimpleNamespace(items=torch.randn(5, 8)), SimpleNamespace(items=torch.randn(3, 8))],
+               [SimpleNamespace(items=torch.randn(4, 8))]]
+    cb = MultiDatasetItemEncodingCallback(loaders)
+    cb.on_train_epoch_start(None, mod)
+    assert mod.training and len(mod.item_embeddings) == 2
+    assert mod.item_embeddings[0].shape == (8, 8) and mod.item_embeddings[1].shape == (4, 8)
+    assert not mod.item_embeddings[0].requires_grad and mod.item_embeddings[0].is_contiguous()
+    want = torch.nn.functional.normalize(mod.merged_model.lin(torch.cat([b.items for b in loaders[0]])), dim=-1)
+    assert torch.allclose(mod.item_embeddings[0], want, atol=1e-6)          # dropout was off: eval mode during encoding
+    first = mod.item_embeddings[0]
+    cb.on_train_epoch_start(None, mod)                                       # already injected: skipped
+    assert mod.item_embeddings[0] is first
+    assert ItemEncoderMixin.encode_items(loaders[1], mod).shape == (4, 8)
