@@ -559,7 +559,8 @@ class CollabStepCfg3(Workload):
         grad = torch.randn(self.d, device=self.device)
         grads = [grad[o:o + n] for o, n in zip(m._layout.offsets, m._layout.sizes)]
         ms_grad = event_time_ms(lambda: _lambda_grad(grads, m._layout, m._task_rows(), seg_group, len(keys)), 10)
-        ms_step = event_time_ms(self.step, 3)
+        # rank 0 only from here: with several ranks `step` holds an all-reduce, so time it only on one GPU
+        ms_step = event_time_ms(self.step, 3) if self.world == 1 else None
         bytes_merge, bytes_grad = (self.K + 2) * self.d * 4, (self.K + 1) * self.d * 4
         ach = bytes_grad / GB / (ms_grad * 1e-3)
         return _with_traffic({"bound": "hbm", "kernel": "mr::lg_partial_kernel<8> (+ finish): lambda-gradient reduction (A5)",
@@ -567,7 +568,7 @@ class CollabStepCfg3(Workload):
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms_grad,
                 "algorithmic_bytes_per_launch": bytes_grad,
                 "other_kernels": {"lambda merge forward (merge_kernel, A4)": {"ms": ms_merge, "GB/s": bytes_merge / GB / (ms_merge * 1e-3), "bytes": bytes_merge}},
-                "step_ms": ms_step, "merge_plus_grad_share_of_step": (ms_merge + ms_grad) / ms_step}, "lg_partial_kernel")
+                "step_ms": ms_step, "merge_plus_grad_share_of_step": None if ms_step is None else (ms_merge + ms_grad) / ms_step}, "lg_partial_kernel")
 
     def extra(self):
         return {"loss": None if self.loss is None else float(self.loss),

@@ -133,6 +133,7 @@ def _tie_index(base, row, wk, mag: int, keep: int) -> int:
 MARGIN_BITS = 1 << 17      # widen the first window by ~1 % of a binade on both sides of the per-rank estimates
 FULL_SHIFT = 20            # lo = 0, shift = 20: 2048 bins of 2^20 cover all 31 magnitude bits
 CAND_CAP = 1 << 16         # per-model capacity of the (bin, index) list recorded at the last level
+TIE_KEEP = 64              # how many of the lowest tied indices are extracted from that list (more: the slice is rescanned)
 
 
 def _ceil_log2(x: torch.Tensor) -> torch.Tensor:
@@ -175,7 +176,8 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
     mag = torch.zeros(K, dtype=torch.int64, device=dev)
     mine = torch.zeros(K, dtype=torch.int64, device=dev)
     done = torch.zeros(K, dtype=torch.bool, device=dev)
-    tie_j = torch.full((K, CAND_CAP), 0x7FFFFFFF, dtype=torch.int64, device=dev)   # ascending local indices AT the cut
+    n_tie = min(TIE_KEEP, CAND_CAP)
+    tie_j = torch.full((K, n_tie), 1 << 40, dtype=torch.int64, device=dev)           # ascending local indices AT the cut
     tie_ok = torch.ones(K, dtype=torch.bool, device=dev)                              # the list was not truncated
     width = torch.full((K,), BINS, dtype=torch.int64, device=dev)    # bins of the current window that belong to the search
     first = True
@@ -186,7 +188,7 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
             h = torch.zeros((K, BINS), dtype=torch.int64, device=dev)
             a = torch.zeros(K, dtype=torch.int64, device=dev)
             cand = cnt = None
-            if not first and bool(((shift == 0) & ~done).any()):           # a model resolves at this level
+            if not first:                                                   # some model may resolve at this level
                 cand = torch.empty((K, CAND_CAP, 2), dtype=torch.int32, device=dev)
                 cnt = torch.zeros(K, dtype=torch.int32, device=dev)
             kernels.mag_hist(base_l, rows_l, w, lo.to(torch.int32), shift.to(torch.int32), h, a, cand, cnt)
@@ -224,8 +226,9 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
             n_c = cnt.to(torch.int64).clamp(max=CAND_CAP)
             slot = torch.arange(CAND_CAP, device=dev)[None, :]
             hit = (slot < n_c[:, None]) & (cand[:, :, 0].to(torch.int64) == chosen[:, None])
-            j_sorted = torch.where(hit, cand[:, :, 1].to(torch.int64) & 0xFFFFFFFF, torch.full_like(tie_j, 1 << 40)).sort(1).values
-            tie_j = torch.where(final[:, None], j_sorted, tie_j)
+            j_all = torch.where(hit, cand[:, :, 1].to(torch.int64) & 0xFFFFFFFF, torch.full_like(hit, 1 << 40, dtype=torch.int64))
+            j_low = torch.topk(j_all, n_tie, dim=1, largest=False, sorted=True).values
+            tie_j = torch.where(final[:, None], j_low, tie_j)
             tie_ok = torch.where(final, cnt.to(torch.int64) <= CAND_CAP, tie_ok)
         left = torch.where(done, left, left - over)
         lo = torch.where(done, lo, lo + (chosen << shift))
@@ -245,10 +248,10 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
     cut = torch.where(keep >= mine, cut_all, cut_none)
     partial = (keep > 0) & (keep < mine)
     # the keep-th of my tied elements (ascending local index) is the last survivor: taken from the recorded list ...
-    j_keep = tie_j.gather(1, (keep - 1).clamp(min=0, max=CAND_CAP - 1)[:, None]).squeeze(1)
+    j_keep = tie_j.gather(1, (keep - 1).clamp(min=0, max=n_tie - 1)[:, None]).squeeze(1)
     cut = torch.where(partial, (mag << 32) | (0xFFFFFFFF - j_keep), cut)
     # ... unless that list was truncated or not recorded (millions of equal magnitudes; a first-window miss): rescan
-    redo = partial & (~tie_ok | (keep > CAND_CAP) | (j_keep >= (1 << 40)))
+    redo = partial & (~tie_ok | (keep > n_tie) | (j_keep >= (1 << 40)))
     if bool(redo.any()):
         for k in torch.nonzero(redo).reshape(-1).tolist():
             j = _tie_index(base_l, rows_l[k], None if w is None else w.reshape(-1)[k], int(mag[k]), int(keep[k]))

@@ -146,7 +146,7 @@ def test_truncated_tie_list_rescans(monkeypatch):
     calls = []
     orig = sh._tie_index
     monkeypatch.setattr(sh, "_tie_index", lambda *a: (calls.append(1), orig(*a))[1])
-    case = CASES[1]
+    case = CASES[2]                     # a handful of equal magnitudes at the cut: resolved from the recorded list
     base, models = _case_inputs(case)
     bl, ml = torch.from_numpy(base), [torch.from_numpy(m) for m in models]
     want = orc.ties_vectors(base, models, case["density"])
