@@ -126,10 +126,13 @@ extern "C" int mr_ties_mag_hist(const float* base, const float* const* models, i
         MR_REQUIRE(models[k] != nullptr, "mr_ties_mag_hist: models[%d] is NULL", k);
         vec = vec && host_aligned16(models[k]);
     }
-    int64_t blocks = ((d + 3) / 4 + kMhThreads - 1) / kMhThreads;
-    const int64_t cap = (int64_t)sm_count() * 4;
-    if (blocks > cap) blocks = cap;
     const size_t smem = (size_t)K * kMhBins * sizeof(uint32_t);
+    // exactly one resident wave: as many CTAs per SM as the shared-memory histograms allow (3 at K = 8), no tail wave
+    int per_sm = (int)((size_t)(200 * 1024) / smem);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    int64_t blocks = ((d + 3) / 4 + kMhThreads - 1) / kMhThreads;
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
     MR_DISPATCH_K(K, {
         PtrPack<KK> pk;
         for (int k = 0; k < KK; ++k) pk.p[k] = models[k];

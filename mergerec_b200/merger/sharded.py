@@ -130,7 +130,9 @@ def _tie_index(base, row, wk, mag: int, keep: int) -> int:
     return int(idx[keep - 1])
 
 
-MARGIN_BITS = 1 << 17      # widen the first window by ~1 % of a binade on both sides of the per-rank estimates
+MARGIN_BITS = 64           # widen the first window by a few bit patterns beyond the per-rank estimates (the proportional
+                           # ranks are rounded, so the cut may sit a handful of elements outside their span; a miss is
+                           # detected from the counts and falls back to the full range)
 FULL_SHIFT = 20            # lo = 0, shift = 20: 2048 bins of 2^20 cover all 31 magnitude bits
 CAND_CAP = 1 << 16         # per-model capacity of the (bin, index) list recorded at the last level
 TIE_KEEP = 64              # how many of the lowest tied indices are extracted from that list (more: the slice is rescanned)
@@ -168,9 +170,16 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
     ests = _all_gather(est, group)                                           # (world, K)
     valid = ests >= 0
     big = torch.full_like(ests, 0x7FFFFFFF)
-    lo = (torch.where(valid, ests, big).min(0).values - MARGIN_BITS).clamp(min=0)
-    hi = (torch.where(valid, ests, torch.zeros_like(ests)).max(0).values + MARGIN_BITS).clamp(max=0x7FFFFFFF)
-    shift = (_ceil_log2(hi - lo + 1) - 11).clamp(min=0)
+    est_lo = torch.where(valid, ests, big).min(0).values
+    est_hi = torch.where(valid, ests, torch.zeros_like(ests)).max(0).values
+    margin = MARGIN_BITS
+
+    def window(m):
+        lo_ = (est_lo - m).clamp(min=0)
+        hi_ = (est_hi + m).clamp(max=0x7FFFFFFF)
+        return lo_, (_ceil_log2(hi_ - lo_ + 1) - 11).clamp(min=0)
+
+    lo, shift = window(margin)
     k_t = torch.full((K,), int(k_cnt), dtype=torch.int64, device=dev)
     left = k_t.clone()
     mag = torch.zeros(K, dtype=torch.int64, device=dev)
@@ -180,40 +189,36 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
     tie_j = torch.full((K, n_tie), 1 << 40, dtype=torch.int64, device=dev)           # ascending local indices AT the cut
     tie_ok = torch.ones(K, dtype=torch.bool, device=dev)                              # the list was not truncated
     width = torch.full((K,), BINS, dtype=torch.int64, device=dev)    # bins of the current window that belong to the search
+    cand = torch.empty((K, CAND_CAP, 2), dtype=torch.int32, device=dev) if d_l else None
+    slot = torch.arange(CAND_CAP, device=dev)[None, :]
+    bins_idx = torch.arange(BINS, device=dev)[None, :]
     first = True
-    for _level in range(8):
-        both = torch.zeros((K, BINS + 1), dtype=torch.int64, device=dev)    # [:, :BINS] histogram, [:, BINS] above
-        hist_l, above_l = both[:, :BINS], both[:, BINS]
+    for _level in range(12):
+        h = torch.zeros((K, BINS), dtype=torch.int64, device=dev)
+        a = torch.zeros(K, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(K, dtype=torch.int32, device=dev) if d_l else None
         if d_l:
-            h = torch.zeros((K, BINS), dtype=torch.int64, device=dev)
-            a = torch.zeros(K, dtype=torch.int64, device=dev)
-            cand = cnt = None
-            if not first:                                                   # some model may resolve at this level
-                cand = torch.empty((K, CAND_CAP, 2), dtype=torch.int32, device=dev)
-                cnt = torch.zeros(K, dtype=torch.int32, device=dev)
             kernels.mag_hist(base_l, rows_l, w, lo.to(torch.int32), shift.to(torch.int32), h, a, cand, cnt)
-            hist_l.copy_(h)
-            above_l.copy_(a)
-        else:
-            cand = cnt = None
-        local_hist = hist_l.clone()
-        both = _all_reduce_sum(both, group)
+        local_hist = h
+        both = _all_reduce_sum(torch.cat([h, a[:, None]], dim=1), group)     # (K, BINS + 1): histogram | count above
         hist, above = both[:, :BINS], both[:, BINS]
         if first:
-            # the window must contain global rank k_cnt; where it does not (adversarial shards) restart on the full range
+            # the window must contain global rank k_cnt; where it does not (shards with different statistics, rounding of
+            # the proportional ranks) widen it 64-fold, finally to the full range, and repeat the level
             miss = (above >= k_t) | (above + hist.sum(1) < k_t)
             if bool(miss.any()):
-                lo = torch.where(miss, torch.zeros_like(lo), lo)
-                shift = torch.where(miss, torch.full_like(shift, FULL_SHIFT), shift)
-                if bool(miss.all()):
-                    continue
-                # models whose window was fine simply repeat the same level
+                margin *= 64
+                if margin <= (1 << 18):
+                    wlo, wsh = window(margin)
+                else:
+                    wlo, wsh = torch.zeros_like(lo), torch.full_like(shift, FULL_SHIFT)
+                lo, shift = torch.where(miss, wlo, lo), torch.where(miss, wsh, shift)
                 continue
             left = k_t - above
             first = False
         # a refined window may be wider than the bin it refines (2048 << shift' >= 1 << shift): ignore the excess bins,
         # their elements were already counted as lying above
-        hist = torch.where(torch.arange(BINS, device=dev)[None, :] < width[:, None], hist, torch.zeros_like(hist))
+        hist = torch.where(bins_idx < width[:, None], hist, torch.zeros_like(hist))
         top = hist.flip(1).cumsum(1)                                         # top[:, i] = count in the i+1 highest bins
         i = (top < left[:, None]).sum(1).clamp(max=BINS - 1)                # first i with top[:, i] >= left
         over = torch.where(i > 0, top.gather(1, (i - 1).clamp(min=0)[:, None]).squeeze(1), torch.zeros_like(left))
@@ -224,7 +229,6 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
         if cand is not None:
             # local indices of my elements at exactly the cut magnitude, ascending (others pushed to the end)
             n_c = cnt.to(torch.int64).clamp(max=CAND_CAP)
-            slot = torch.arange(CAND_CAP, device=dev)[None, :]
             hit = (slot < n_c[:, None]) & (cand[:, :, 0].to(torch.int64) == chosen[:, None])
             j_all = torch.where(hit, cand[:, :, 1].to(torch.int64) & 0xFFFFFFFF, torch.full_like(hit, 1 << 40, dtype=torch.int64))
             j_low = torch.topk(j_all, n_tie, dim=1, largest=False, sorted=True).values
