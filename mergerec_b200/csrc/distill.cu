@@ -17,6 +17,7 @@
 //                     that sums the per-CTA partials in a fixed order and applies the upstream gradient).
 // All reductions are deterministic (no atomics).  Arithmetic is fp32 with fp64 block sums in the loss kernel; the
 // contract is a floating-point tolerance (tests: 2e-5 relative against an fp64 oracle), not bit equality.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -26,7 +27,9 @@ namespace mr {
 constexpr int kDsThreads = 256;
 constexpr int kDsWarps = kDsThreads / 32;
 constexpr int kDsNB = 4;  // samples of one domain handled by one pass over its item table
-constexpr int kDsLossThreads = 512;
+constexpr int kDsLossThreads = 256;
+constexpr int kDsLossCluster = 8;  // CTAs (one thread-block cluster) sharing one sample
+namespace cg = cooperative_groups;
 
 struct DsGroup {
     const float* items;  // (rows, E) row-major
@@ -444,6 +447,33 @@ __device__ void block_sum(double (&v)[NV], double* s_tmp /* [warps][NV] */) {
     }
 }
 
+// cluster-wide versions: block result -> one slot per CTA in shared memory -> every CTA combines the eight slots over
+// distributed shared memory in rank order (deterministic)
+__device__ ArgMax cluster_argmax(ArgMax x, ArgMax* s_tmp, ArgMax* s_slot, cg::cluster_group& cl) {
+    x = block_argmax(x, s_tmp);
+    if (threadIdx.x == 0) *s_slot = x;
+    cl.sync();
+    ArgMax r = *cl.map_shared_rank(s_slot, 0);
+    for (int c = 1; c < kDsLossCluster; ++c) r = better(r, *cl.map_shared_rank(s_slot, c));
+    cl.sync();
+    return r;
+}
+template <int NV>
+__device__ void cluster_sum(double (&v)[NV], double* s_tmp, double* s_slot /* [NV] */, cg::cluster_group& cl) {
+    block_sum<NV>(v, s_tmp);
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s_slot[j] = v[j];
+    cl.sync();
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        double t = 0.0;
+        for (int c = 0; c < kDsLossCluster; ++c) t += cl.map_shared_rank(s_slot, c)[j];
+        v[j] = t;
+    }
+    cl.sync();
+}
+
 struct DsLossMix {  // loss = cA*CE(z, target) + cK*KD_T + cE*entropy(z) + cM*MSE + cL*ListNet_T  (or the pairwise hinge)
     float cA, cK, cE, cM, cL;
     int target_from_merged;  // CE target = argmax z (pseudo label of the merged model) instead of argmax t
@@ -469,48 +499,56 @@ static int ds_loss_mix(int type, float coef, DsLossMix* m) {
     return MR_OK;
 }
 
-// One CTA per sample.  z = merged-model logits, t = teacher logits (n each).  Streaming passes over the two rows
-// (they were just written / are L2-resident): maxima, sums, optional entropy pass, gradient write.
-__global__ void __launch_bounds__(kDsLossThreads)
+// One thread-block CLUSTER of eight CTAs per sample (a single CTA kept one SM busy for ~50 us on a 25,000-item row; the
+// expf / logf / fp64 work is what costs, not the bytes).  z = merged-model logits, t = teacher logits (n each).
+// Streaming passes over the two rows (just written / L2-resident): maxima, sums, optional entropy pass, gradient
+// write; between passes the CTAs exchange their partials through distributed shared memory.
+__global__ void __cluster_dims__(kDsLossCluster, 1, 1) __launch_bounds__(kDsLossThreads)
 ds_loss_kernel(const __grid_constant__ DsLossArgs args, const float* __restrict__ logits, int64_t ld, DsLossMix mix,
                float T, float margin, float* __restrict__ loss, float* __restrict__ gz, int64_t ldg) {
     __shared__ ArgMax s_am[kDsLossThreads / 32];
     __shared__ double s_sum[(kDsLossThreads / 32) * 5];
-    const int b = blockIdx.x;
+    __shared__ ArgMax s_am_slot;
+    __shared__ double s_sum_slot[5];
+    cg::cluster_group cl = cg::this_cluster();
+    const int b = blockIdx.y;
+    const int gt = (int)blockIdx.x * kDsLossThreads + (int)threadIdx.x;   // thread index inside the cluster
+    constexpr int GS = kDsLossCluster * kDsLossThreads;
+    const bool writer = (blockIdx.x == 0 && threadIdx.x == 0);
     const int n = args.n[b];
     const float* __restrict__ z = logits + (int64_t)b * ld;
     const float* __restrict__ t = args.teacher[b];
     float* __restrict__ g = gz ? gz + (int64_t)b * ldg : nullptr;
     const bool has_t = (t != nullptr);
-    if (n <= 0) { if (threadIdx.x == 0) loss[b] = 0.f; return; }
+    if (n <= 0) { if (writer) loss[b] = 0.f; return; }
 
     ArgMax az{-INFINITY, 0x7fffffff}, at{-INFINITY, 0x7fffffff};
 #pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
+    for (int i = gt; i < n; i += GS) {
         az = better(az, ArgMax{z[i], i});
         if (has_t) at = better(at, ArgMax{t[i], i});
     }
-    az = block_argmax(az, s_am);
-    if (has_t) at = block_argmax(at, s_am);
+    az = cluster_argmax(az, s_am, &s_am_slot, cl);
+    if (has_t) at = cluster_argmax(at, s_am, &s_am_slot, cl);
 
     if (mix.pairwise) {  // hinge on (best, second-best) teacher items
         ArgMax an{-INFINITY, 0x7fffffff};
     #pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += kDsLossThreads)
+    for (int i = gt; i < n; i += GS)
             if (i != at.i) an = better(an, ArgMax{t[i], i});
-        an = block_argmax(an, s_am);
+        an = cluster_argmax(an, s_am, &s_am_slot, cl);
         const int neg = (an.i == 0x7fffffff) ? 0 : an.i;  // n == 1: argmax of an all -inf row is index 0
         const float h = margin - (z[at.i] - z[neg]);
         const bool active = h > 0.f;
         if (g) {
         #pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
+    for (int i = gt; i < n; i += GS) {
                 float v = 0.f;
                 if (active) v = (i == at.i ? -1.f : 0.f) + (i == neg ? 1.f : 0.f);
                 g[i] = v;
             }
         }
-        if (threadIdx.x == 0) loss[b] = active ? h : 0.f;
+        if (writer) loss[b] = active ? h : 0.f;
         return;
     }
 
@@ -520,7 +558,7 @@ ds_loss_kernel(const __grid_constant__ DsLossArgs args, const float* __restrict_
     // (for ListNet [3] holds sum e_t (z-mz) instead)
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
+    for (int i = gt; i < n; i += GS) {
         const float zc = z[i] - az.v;
         acc[0] += (double)expf(zc);
         if (useT) {
@@ -535,7 +573,7 @@ ds_loss_kernel(const __grid_constant__ DsLossArgs args, const float* __restrict_
             acc[4] += (double)dlt * (double)dlt;
         }
     }
-    block_sum<5>(acc, s_sum);
+    cluster_sum<5>(acc, s_sum, s_sum_slot, cl);
     const double S1 = acc[0], ST = acc[1], PT = acc[2];
     double total = 0.0;
     const int target = mix.target_from_merged ? az.i : at.i;
@@ -549,23 +587,23 @@ ds_loss_kernel(const __grid_constant__ DsLossArgs args, const float* __restrict_
     if (mix.cE != 0.f) {  // entropy of softmax(z) with the reference's +1e-8 inside the log (loss_fn.py:65-66)
         double e2[2] = {0.0, 0.0};
     #pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
+    for (int i = gt; i < n; i += GS) {
             const float p = expf(z[i] - az.v) * inv_S1;
             const float lp = logf(p + 1e-8f);
             e2[0] += (double)p * (double)lp;
             e2[1] += (double)p * (double)(lp + p / (p + 1e-8f));
         }
-        block_sum<2>(e2, s_sum);
+        cluster_sum<2>(e2, s_sum, s_sum_slot, cl);
         total += (double)mix.cE * (-e2[0]);
         hbar = -e2[1];
     }
-    if (threadIdx.x == 0) loss[b] = (float)total;
+    if (writer) loss[b] = (float)total;
 
     if (g) {
         const float kd_scale = mix.cK * T + mix.cL * invT;  // d/dz of T^2 KL(P || Q_T) is T (Q - P); ListNet: (Q - P)/T
         const float mse_scale = mix.cM * 2.0f / (float)n;
     #pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += kDsLossThreads) {
+    for (int i = gt; i < n; i += GS) {
             const float zc = z[i] - az.v;
             float v = 0.f;
             if (mix.cA != 0.f || mix.cE != 0.f) {
@@ -675,7 +713,7 @@ extern "C" int mr_distill_loss(const float* logits, int64_t ld, const float* con
         args.teacher[b] = teacher_rows ? teacher_rows[b] : nullptr;
         MR_REQUIRE(!mix.needs_teacher || args.teacher[b], "mr_distill_loss: teacher row %d is NULL", b);
     }
-    ds_loss_kernel<<<B, kDsLossThreads, 0, (cudaStream_t)stream>>>(args, logits, ld, mix, usesT ? temperature : 1.0f, margin,
+    ds_loss_kernel<<<dim3(kDsLossCluster, B), kDsLossThreads, 0, (cudaStream_t)stream>>>(args, logits, ld, mix, usesT ? temperature : 1.0f, margin,
                                                                   loss, grad_logits, ldg);
     MR_CUDA_LAUNCH_CHECK("mr_distill_loss");
     return MR_OK;
