@@ -179,6 +179,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
+    if hasattr(wl, "finish"):
+        wl.finish()   # deferred host-side checks of the timed steps (e.g. the TIES select status word)
 
     # end to end through the public API: pinned host inputs -> H2D -> kernels -> D2H result, every step
     wl.setup_e2e()

