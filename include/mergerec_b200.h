@@ -280,6 +280,12 @@ int mr_ties_mag_hist(const float* base, const float* const* models, int K, int64
                      const int32_t* shift, int64_t* hist, int64_t* above, uint32_t* cand, uint32_t* cand_count,
                      int cand_cap, mr_stream_t stream);
 
+/* DARE merge with explicit keep masks.                       ref: merger/algorithms/dare.py:9-31 (+ torch dropout)
+ * out[j] = base[j] (+) sum in order k of fl( fl(w[k] * (models[k][j] - base[j])) * (keep[k, j] ? scale : 0) ),
+ * scale = 1 / (1 - p) in fp32.  keep: dev uint8, K rows of leading dimension ld_keep (1 = kept).  w: dev K floats. */
+int mr_merge_dare(const float* base, const float* const* models, int K, int64_t d, const float* w, const uint8_t* keep,
+                  int64_t ld_keep, float scale, float* out, mr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

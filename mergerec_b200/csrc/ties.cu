@@ -549,7 +549,9 @@ __device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_
             for (int k = 0; k < K; ++k) res[k] = div_by_count_fast(res[k], fc, inv);
         } else {
 #pragma unroll
-            for (int k = 0; k < K; ++k) res[k] = __fdiv_rn(res[k], fc);
+            // (+ 0.0f: the compiler may turn the `s < 0 ? s : 0` select above into a min, which keeps the sign of a
+            //  -0.0 update; the reference's torch.where yields +0.0 there.  The fast path maps -0.0 to +0.0 by itself.)
+            for (int k = 0; k < K; ++k) res[k] = __fadd_rn(__fdiv_rn(res[k], fc), 0.0f);
         }
     }
 }

@@ -9,12 +9,11 @@ from typing import List, Optional, Sequence, Union
 
 import torch
 
-from .algorithms import merge_linear, merge_pcb, merge_task_vector, merge_ties
+from .algorithms import merge_dare, merge_linear, merge_pcb, merge_task_vector, merge_ties
 from .types import FlattenedModel, ShapeDict, StateDict
 from .utils.model_operations import align_dict_key_order, check_model_shape, flatten_model, unflatten_model
 
 _NEEDS_BASE = {"task_vector": "Task vector", "ties": "TIES", "dare": "DARE", "pcb": "PCB"}
-_OUT_OF_SCOPE = {"dare"}  # needs torch's CPU dropout RNG stream to be reproducible; outside the hot paths
 
 
 class ModelMerger:
@@ -46,7 +45,7 @@ class ModelMerger:
 
         ``weights`` is a float (applied to every model) or a list of floats -- anything else raises
         ``ValueError`` exactly like the reference (merger.py:60-64).  Unknown merge types raise ``ValueError``
-        (merger.py:87-88); ``"dare"`` is recognised but outside this package's scope."""
+        (merger.py:87-88); ``"dare"`` draws its keep masks from torch's CUDA generator unless ``masks=`` is passed."""
         if isinstance(weights, float):
             weights = [weights] * len(self.models)
         elif not (isinstance(weights, list) and all(isinstance(w, float) for w in weights)):
@@ -63,9 +62,8 @@ class ModelMerger:
             flat = merge_ties(**call)
         elif merge_type == "pcb":
             flat = merge_pcb(**call)
-        elif merge_type in _OUT_OF_SCOPE:
-            raise NotImplementedError(
-                f"Merge type '{merge_type}' is a baseline outside the merger hot path this package implements.")
+        elif merge_type == "dare":
+            flat = merge_dare(**call)
         else:
             raise ValueError(f"Merge type '{merge_type}' is not supported.")
         return unflatten_model(flat, self.shape_dict)

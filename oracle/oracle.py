@@ -516,3 +516,24 @@ def merge_pcb(base, models, weights: Sequence[float], density: float = 0.2) -> n
     for i in range(len(models)):
         acc = (acc + (np.float32(weights[i]) * vec[i]).astype(np.float32)).astype(np.float32)
     return acc
+
+
+# ---- DARE (merger/algorithms/dare.py:9-31) with explicit keep masks --------------------------------------------------
+def merge_dare(base, models, weights: Sequence[float], density: float, masks) -> np.ndarray:
+    """merged = base; merged += fl(fl(w_i * (m_i - base)) * noise_i), noise = keep / (1 - p) in fp32 (torch's CPU dropout:
+    `input * bernoulli_(1 - p).div_(1 - p)`; p == 0 returns the input, p == 1 multiplies by zeros)."""
+    assert len(models) == len(weights), "Number of models and weights should match."
+    base = _f32(base)
+    p = float(density)
+    masks = np.asarray(masks).astype(bool)
+    acc = base.copy()
+    for i, m in enumerate(models):
+        update = (np.float32(weights[i]) * (_f32(m) - base).astype(np.float32)).astype(np.float32)
+        if p == 1.0:
+            noise = np.zeros_like(update)
+        elif p == 0.0:
+            noise = np.ones_like(update)
+        else:
+            noise = (masks[i].astype(np.float32) / np.float32(1.0 - p)).astype(np.float32)
+        acc = (acc + (update * noise).astype(np.float32)).astype(np.float32)
+    return acc

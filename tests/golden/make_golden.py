@@ -307,12 +307,28 @@ def gen_pcb():
     save("pcb", **out)
 
 
+def gen_dare():
+    from rec_retrieval.merger.algorithms.dare import merge_dare
+    from torch.nn.functional import dropout
+    out = {}
+    for case in gc.DARE_CASES:
+        base, models = synth.make_flat(case["d"], case["K"], seed=case["seed"])
+        tb, tm = T(base), [T(m) for m in models]
+        torch.manual_seed(case["torch_seed"])
+        out[f"{case['name']}/merged"] = merge_dare(tb, tm, case["weights"], density=case["density"]).numpy()
+        # replay the generator: the mask of a dropout call depends on the shape and the RNG state only
+        torch.manual_seed(case["torch_seed"])
+        masks = np.stack([(dropout(torch.ones(case["d"]), p=case["density"], training=True) != 0).numpy() for _ in range(case["K"])])
+        out[f"{case['name']}/masks"] = np.packbits(masks, axis=1)
+    save("dare", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
     only = set(sys.argv[1:])   # e.g. `make_golden.py lns` regenerates one file
     for name, fn in [("merge_flat", gen_merge_flat), ("model_merger", gen_model_merger), ("lambda_merge", gen_lambda),
                      ("ties", gen_ties), ("lns", gen_lns), ("evaluator", gen_evaluator), ("evaluator_bf16", gen_evaluator_bf16),
-                     ("module_e2e", gen_module_e2e), ("distill", gen_distill), ("pcb", gen_pcb)]:
+                     ("module_e2e", gen_module_e2e), ("distill", gen_distill), ("pcb", gen_pcb), ("dare", gen_dare)]:
         if not only or name in only:
             fn()

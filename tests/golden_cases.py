@@ -79,3 +79,12 @@ PCB_CASES = [
     dict(name="k5_d10007", K=5, d=10007, seed=93, density=0.1, weights=[1.0, 0.5, 0.25, 2.0, 1.5]),
     dict(name="k2_d40000", K=2, d=40000, seed=94, density=0.5, weights=[0.6, 0.4]),
 ]
+
+# DARE: the reference draws its dropout masks from torch's CPU generator; the golden file stores those masks (replayed
+# from the same seed) next to the merged vector.
+DARE_CASES = [
+    dict(name="k3_d4099", K=3, d=4099, seed=101, density=0.2, weights=[0.3, 0.7, -0.123456789], torch_seed=7),
+    dict(name="k8_d4165", K=8, d=4165, seed=102, density=0.9, weights=[0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], torch_seed=8),
+    dict(name="k2_p0", K=2, d=1000, seed=103, density=0.0, weights=[0.5, 0.5], torch_seed=9),
+    dict(name="k2_p1", K=2, d=1000, seed=104, density=1.0, weights=[0.5, 0.5], torch_seed=10),
+]

@@ -89,8 +89,6 @@ def test_model_merger_pcb_and_module_factory():
     torch.manual_seed(0)
     mod = load_merging_module(MergeType.PCB, LearnType.TASK_WISE, ToyEncoder(), pre, fts, ignore_keys=set(), ties_density=0.2)
     assert mod.task_vectors.shape[0] == 3 if hasattr(mod, "task_vectors") else True
-    with pytest.raises(NotImplementedError):
-        merger.merge("dare", 0.3, density=0.2)
 
 
 def test_pcb_full_size_properties():

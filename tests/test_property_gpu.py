@@ -4,7 +4,7 @@ are not multiples of 4 / 32, pointers off the 16-byte grid, ragged block tables 
 import numpy as np
 import pytest
 import torch
-from hypothesis import HealthCheck, given, settings, strategies as st
+from hypothesis import HealthCheck, example, given, settings, strategies as st
 
 from helpers import assert_bit_equal
 from mergerec_b200 import _lib
@@ -107,6 +107,7 @@ def test_lambda_merge_ragged_blocks(K, d, seed, layer_wise):
 @settings(**SETTINGS)
 @given(K=st.integers(1, 16), d=st.integers(40, 4000), shift=st.integers(0, 3), seed=st.integers(0, 2 ** 31 - 1),
        density=st.sampled_from([0.0, 0.001, 0.05, 0.2, 0.5, 0.999, 1.0]), quant=st.booleans(), specials=st.booleans())
+@example(K=6, d=40, shift=0, seed=0, density=0.999, quant=False, specials=True)   # kept -0.0 updates under a minus election
 def test_ties_family(K, d, shift, seed, density, quant, specials):
     rng = np.random.Generator(np.random.PCG64(seed))
     base, models = make_inputs(rng, K, d, specials, quant)
