@@ -15,7 +15,11 @@ from mergerec_b200.merger.algorithms.ties import merge_ties_lambda
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
-SETTINGS = dict(deadline=None, max_examples=40, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+import os
+
+# MR_HYPOTHESIS_EXAMPLES=1000 turns the suite into a soak test (the default keeps `pytest -m gpu` under a minute)
+SETTINGS = dict(deadline=None, max_examples=int(os.environ.get("MR_HYPOTHESIS_EXAMPLES", "40")),
+                suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 
 
 def dev(a):
@@ -126,7 +130,7 @@ def test_ties_family(K, d, shift, seed, density, quant, specials):
                      "localize-and-stitch vectors")
 
 
-@settings(**dict(SETTINGS, max_examples=30))
+@settings(**dict(SETTINGS, max_examples=max(30, SETTINGS["max_examples"] // 4)))
 @given(Q=st.integers(1, 600), N=st.integers(1, 3000), e4=st.integers(1, 33), k=st.integers(1, 128),
        id_base=st.integers(0, 2_000_000_000), seed=st.integers(0, 2 ** 31 - 1), cg=st.sampled_from([1, 2]),
        mode=st.sampled_from([0, 1, 2]), splits=st.sampled_from([0, 1, 2, 5]))
@@ -156,3 +160,37 @@ def test_fused_scoring_topk(Q, N, e4, k, id_base, seed, cg, mode, splits):
     ov, oi = orc.topk_rows(scores, k, id_base=id_base)
     assert np.array_equal(host(i), oi), "ids"
     assert_bit_equal(host(v), ov, "scores")
+
+
+_DISTILL_LOSSES = [("CE", {}), ("KD", dict(temperature=2.0)), ("KD", dict(temperature=0.1)), ("MSE", {}), ("ADAMERGING", {}),
+                   ("ADAMERGING_KD", dict(temperature=0.5, coefficient=0.3)), ("SINGLE_PSEUDO_LABEL_KD", dict(temperature=1.0, coefficient=0.5)),
+                   ("LISTNET", dict(temperature=0.3))]
+
+
+@settings(**dict(SETTINGS, max_examples=max(25, SETTINGS["max_examples"] // 8)))
+@given(B=st.integers(1, 20), e4=st.integers(1, 256), D=st.integers(1, 5), seed=st.integers(0, 2 ** 31 - 1),
+       loss=st.sampled_from(_DISTILL_LOSSES), big=st.booleans())
+def test_distill_step(B, e4, D, seed, loss, big):
+    """Distillation step (logits -> loss -> representation gradient) on ragged tables, every embedding width that is a
+    multiple of 4 up to 1024, 1..20 samples spread over 1..5 domains (so groups of 1..4 samples and repeated passes over
+    a table): 2e-5 of the largest magnitude against the fp64 oracle.  (The losses whose label is an argmax of the merged
+    model's own logits, and the hinge, are discontinuous in the logits and stay with the golden-vector tests.)"""
+    from mergerec_b200.module.distiller.sequence.module import fused_distill_losses
+    from test_distill_gpu import loss_object
+    rng = np.random.Generator(np.random.PCG64(seed))
+    E = 4 * e4
+    rows = [int(rng.integers(1, 2000 if big else 200)) for _ in range(D)]
+    tables = [(rng.standard_normal((n, E)) / np.sqrt(E)).astype(np.float32) for n in rows]
+    dom = [int(x) for x in rng.integers(0, D, size=B)]
+    rep = rng.standard_normal((B, E)).astype(np.float32)
+    teacher = [(tables[d] @ rep[b] + 0.5 * rng.standard_normal(rows[d])).astype(np.float32) for b, d in enumerate(dom)]
+    lname, kw = loss
+    spec = loss_object(lname, kw).spec
+    t_dev = [dev(t) for t in teacher]
+    r = dev(rep).requires_grad_(True)
+    losses = fused_distill_losses(r, [dev(t) for t in tables], dom, [t.data_ptr() for t in t_dev], spec)
+    losses.mean().backward()
+    o_losses, _, o_grad = orc.distill_step(rep, tables, dom, teacher, lname, **kw)
+    scale_l = max(np.abs(o_losses).max(), 1e-3)
+    assert np.abs(host(losses) - o_losses).max() <= 2e-5 * scale_l, (lname, rows, dom)
+    assert np.abs(host(r.grad) - o_grad).max() <= 2e-5 * max(np.abs(o_grad).max(), 1e-6), (lname, rows, dom)
