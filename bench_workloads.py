@@ -740,9 +740,12 @@ class TiesSharded(TiesCfg2):
         cut = self._cut                      # rank 0 only from here on: kernels, no collectives
         hist = torch.zeros((K, 2048), dtype=torch.int64, device=self.device)
         above = torch.zeros(K, dtype=torch.int64, device=self.device)
-        lo = ((cut >> 32) - (1 << 17)).clamp(min=0).to(torch.int32)          # the usual first window around the cut
-        sh = torch.full((K,), 7, dtype=torch.int32, device=self.device)
+        lo = ((cut >> 32) - 64).clamp(min=0).to(torch.int32)                  # the first window of this (iid) workload
+        sh = torch.zeros(K, dtype=torch.int32, device=self.device)
         ms_hist = event_time_ms(lambda: CudaKernels.mag_hist(self.base, self.models, None, lo, sh, hist, above), 10)
+        lo_w = ((cut >> 32) - (1 << 17)).clamp(min=0).to(torch.int32)         # a wide window (shards with different statistics)
+        sh_w = torch.full((K,), 7, dtype=torch.int32, device=self.device)
+        ms_hist_wide = event_time_ms(lambda: CudaKernels.mag_hist(self.base, self.models, None, lo_w, sh_w, hist, above), 10)
         ms_select = event_time_ms(self._select, 5) if self.world == 1 else None
         ms_build = event_time_ms(lambda: self._build(cut), 10)
         ms_merge = event_time_ms(self._merge_only, 10)
@@ -754,7 +757,8 @@ class TiesSharded(TiesCfg2):
                 "algorithmic_bytes_per_launch": b_build,
                 "other_kernels": {
                     "mag_hist_kernel (one windowed radix level)": {"ms": ms_hist, "GB/s": b_hist / GB / (ms_hist * 1e-3), "bytes": b_hist},
-                    "sharded select (per-slice order statistic + 2 windowed levels + all-reduces + tie scan)": {"ms": ms_select},
+                    "mag_hist_kernel, window 2^18 bit patterns wide (1.3 % of the elements inside)": {"ms": ms_hist_wide, "GB/s": b_hist / GB / (ms_hist_wide * 1e-3)},
+                    "sharded select (per-slice order statistic + windowed level(s) + all-reduce + tie scan)": {"ms": ms_select},
                     "lambda merge of the slice (merge_kernel)": {"ms": ms_merge, "GB/s": b_merge / GB / (ms_merge * 1e-3), "bytes": b_merge}}}
 
     def extra(self):

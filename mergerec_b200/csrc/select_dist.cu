@@ -25,7 +25,7 @@ struct MhCand {           // optional: (bin, local index) of every in-window ele
     uint32_t cap;
 };
 
-template <int K>
+template <int K, bool COUNT_ABOVE>
 __device__ __forceinline__ void mh_one(float b, const float (&x)[K], const float* s_w, bool weighted, const uint32_t* s_lo,
                                        const int* s_sh, uint32_t* s_hist, uint32_t (&above)[K], const MhCand& cand,
                                        int64_t j) {
@@ -45,7 +45,7 @@ __device__ __forceinline__ void mh_one(float b, const float (&x)[K], const float
                         cand.list[((size_t)k * cand.cap + pos) * 2 + 1] = (uint32_t)j;
                     }
                 }
-            } else {
+            } else if (COUNT_ABOVE) {
                 ++above[k];
             }
         }
@@ -75,6 +75,13 @@ mag_hist_kernel(const float* __restrict__ base, PtrPack<K> m, int64_t d, const f
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
     if (VEC) {
+        // hot loop: branch-free classification of the 4 x K elements of a quad (count what lies above the window, note
+        // whether anything lies inside); the rare quad with an in-window element is redone by the scalar routine
+        uint32_t lo_r[K];
+        int sh_r[K];
+        float w_r[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { lo_r[k] = s_lo[k]; sh_r[k] = s_sh[k]; w_r[k] = s_w[k]; }
         const int64_t n4 = d >> 2;
         for (int64_t v = gtid; v < n4; v += gsz) {
             const float4 xb = ldg_stream4(base + 4 * v);
@@ -82,12 +89,43 @@ mag_hist_kernel(const float* __restrict__ base, PtrPack<K> m, int64_t d, const f
 #pragma unroll
             for (int k = 0; k < K; ++k) xs[k] = ldg_stream4(m.p[k] + 4 * v);
             const float bx[4] = {xb.x, xb.y, xb.z, xb.w};
+            unsigned long long hit = 0;   // bit 4k + c: element c of model k lies inside its window
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float x[K];
+            for (int k = 0; k < K; ++k) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) x[k] = reinterpret_cast<const float*>(&xs[k])[c];
-                mh_one<K>(bx[c], x, s_w, weighted, s_lo, s_sh, s_hist, above, cand, 4 * v + c);
+                for (int c = 0; c < 4; ++c) {
+                    float u = __fsub_rn(reinterpret_cast<const float*>(&xs[k])[c], bx[c]);
+                    if (weighted) u = __fmul_rn(u, w_r[k]);
+                    const uint32_t bits = __float_as_uint(u) & 0x7fffffffu;
+                    const bool ge = bits >= lo_r[k];
+                    const bool inw = ge && (((bits - lo_r[k]) >> sh_r[k]) < (uint32_t)kMhBins);
+                    above[k] += (ge && !inw) ? 1u : 0u;
+                    hit |= (unsigned long long)(inw ? 1u : 0u) << (4 * k + c);
+                }
+            }
+            if (hit) {   // work proportional to the number of in-window elements, static register indexing
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t mk = (uint32_t)(hit >> (4 * k)) & 0xFu;
+                    if (mk) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if ((mk >> c) & 1u) {
+                                float u = __fsub_rn(reinterpret_cast<const float*>(&xs[k])[c], bx[c]);
+                                if (weighted) u = __fmul_rn(u, w_r[k]);
+                                const uint32_t bin = ((__float_as_uint(u) & 0x7fffffffu) - lo_r[k]) >> sh_r[k];
+                                atomicAdd(&s_hist[k * kMhBins + bin], 1u);
+                                if (cand.list && sh_r[k] == 0) {
+                                    const uint32_t pos = atomicAdd(&cand.count[k], 1u);
+                                    if (pos < cand.cap) {
+                                        cand.list[((size_t)k * cand.cap + pos) * 2] = bin;
+                                        cand.list[((size_t)k * cand.cap + pos) * 2 + 1] = (uint32_t)(4 * v + c);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
             }
         }
     }
@@ -95,7 +133,7 @@ mag_hist_kernel(const float* __restrict__ base, PtrPack<K> m, int64_t d, const f
         float x[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) x[k] = m.p[k][j];
-        mh_one<K>(base[j], x, s_w, weighted, s_lo, s_sh, s_hist, above, cand, j);
+        mh_one<K, true>(base[j], x, s_w, weighted, s_lo, s_sh, s_hist, above, cand, j);
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {

@@ -91,9 +91,12 @@ class CudaKernels:
         return as_rows(models)          # raises for anything that is not an fp32 CUDA row: no CPU path
 
     @staticmethod
-    def kth_largest_bits(base, rows, k: int, w) -> torch.Tensor:
-        """Bit pattern (int64 (K,)) of this slice's k-th largest magnitude -- the single-GPU selection kernels."""
-        return _ties.select_kth_largest(base, rows, k, w) >> 32
+    def kth_largest_bits(base, rows, k: int, w):
+        """(bit pattern (int64 (K,)) of this slice's k-th largest magnitude, status word) -- the single-GPU selection
+        kernels, stream-ordered; the status is checked together with the other flags at the end of the select (a
+        failed estimate only widens the search: the windows are verified against the global counts anyway)."""
+        cut, status = _ties.select_kth_largest(base, rows, k, w, defer_status=True)
+        return cut >> 32, status
 
     @staticmethod
     def mag_hist(base, rows, w, lo, shift, hist, above, cand=None, cand_count=None) -> None:
@@ -164,7 +167,8 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
     d_l = base_l.numel()
     if d_l:
         k_l = min(max(int(round(k_cnt * d_l / d_global)), 1), d_l)
-        est = kernels.kth_largest_bits(base_l, rows_l, k_l, w).to(torch.int64)
+        est, _est_status = kernels.kth_largest_bits(base_l, rows_l, k_l, w)
+        est = est.to(torch.int64).clamp(min=0, max=0x7FFFFFFF)
     else:
         est = torch.full((K,), -1, dtype=torch.int64, device=dev)           # an empty slice has no estimate
     ests = _all_gather(est, group)                                           # (world, K)

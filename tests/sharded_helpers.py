@@ -28,7 +28,7 @@ class OracleKernels:
         for i, r in enumerate(rows):
             bits = OracleKernels._bits(base, r, w, i)
             out.append(int(np.partition(bits, bits.size - k)[bits.size - k]))
-        return torch.tensor(out, dtype=torch.int64)
+        return torch.tensor(out, dtype=torch.int64), None
 
     @staticmethod
     def mag_hist(base, rows, w, lo, shift, hist, above, cand=None, cand_count=None):

@@ -30,7 +30,7 @@ def test_mag_hist_matches_numpy(K, d, w):
     base, models = synth.make_flat(d, K, seed=5, quantize=2.5e-4)
     wt = torch.linspace(0.1, 0.9, K) if w else None
     rng = np.random.default_rng(1)
-    med = OracleKernels.kth_largest_bits(torch.from_numpy(base), [torch.from_numpy(m) for m in models], d // 5, wt)
+    med, _ = OracleKernels.kth_largest_bits(torch.from_numpy(base), [torch.from_numpy(m) for m in models], d // 5, wt)
     for lo, shift in ((torch.zeros(K, dtype=torch.int64), torch.full((K,), 20)),                 # full range
                       ((med - (1 << 17)).clamp(min=0), torch.full((K,), 7)),                      # the usual first window
                       (med, torch.zeros(K, dtype=torch.int64)),                                   # single bit patterns

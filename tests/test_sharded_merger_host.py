@@ -123,12 +123,12 @@ def test_window_miss_falls_back_to_the_full_range():
     class BadLow(OracleKernels):
         @staticmethod
         def kth_largest_bits(base, rows, k, w):
-            return torch.zeros(len(rows), dtype=torch.int64)
+            return torch.zeros(len(rows), dtype=torch.int64), None
 
     class BadHigh(OracleKernels):
         @staticmethod
         def kth_largest_bits(base, rows, k, w):
-            return torch.full((len(rows),), 0x7F000000, dtype=torch.int64)
+            return torch.full((len(rows),), 0x7F000000, dtype=torch.int64), None
 
     for case in CASES[:2]:
         base, models = _case_inputs(case)
