@@ -257,12 +257,14 @@ int mr_normalize_rows(const float* x, int64_t rows, int E, float* out, mr_stream
  * inter-balancing weights of pcb.py:44-53.  clamp_lo / clamp_hi (dev, K floats) are the int(d*0.01)-th and
  * int(d*0.99 - 1)-th smallest |tau_k| (pcb.py:17-27; obtained with mr_ties_select on the magnitudes);
  * q_index = int(d * (1 - density)) is the ascending rank of the lower clamp of the balancing weights, found here
- * exactly with three histogram passes.  task_out (K rows, ldo) / thr_out (K x {q, max}) are optional diagnostics.
- * exp / tanh are CUDA's: values agree with torch's CPU kernels to ~1 ulp (floating-point contract, not bit-exact). */
+ * exactly: dense = 1 runs three full histogram passes; dense = 0 runs them on a 1/32 sample, then two windowed passes
+ * over everything around the sample's quantile, and reports per model in status (dev int32 K) 1 = exact result,
+ * 0 = the window missed (call again with dense = 1).  task_out (K rows, ldo) / thr_out (K x {q, max}) are optional
+ * diagnostics.  exp / tanh are CUDA's: values agree with torch's CPU kernels to ~1 ulp (floating-point contract). */
 int64_t mr_pcb_workspace_bytes(int K);
 int mr_pcb_vectors(const float* base, const float* const* models, int K, int64_t d, const float* clamp_lo,
-                   const float* clamp_hi, int64_t q_index, float* out, int64_t ldo, float* task_out, float* thr_out,
-                   void* ws, int64_t ws_bytes, mr_stream_t stream);
+                   const float* clamp_hi, int64_t q_index, int dense, int32_t* status, float* out, int64_t ldo,
+                   float* task_out, float* thr_out, void* ws, int64_t ws_bytes, mr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sharded merger: the flat vector is split over ranks; the global TIES trim

@@ -32,7 +32,7 @@ def _magnitude_of(cut: torch.Tensor) -> torch.Tensor:
 
 
 def get_pcb_vectors(base_model: FlattenedModel, models: List[FlattenedModel], density: float = 0.2,
-                    return_diagnostics: bool = False, **__):
+                    return_diagnostics: bool = False, force_dense: bool = False, **__):
     lib = _lib.load()
     rows = as_rows(models)
     K, d = len(rows), base_model.numel()
@@ -48,10 +48,18 @@ def get_pcb_vectors(base_model: FlattenedModel, models: List[FlattenedModel], de
     thr = torch.empty((K, 2), dtype=torch.float32, device=dev) if return_diagnostics else None
     ws_bytes = int(lib.mr_pcb_workspace_bytes(K))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    rc = lib.mr_pcb_vectors(_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(lo), _lib.dptr(hi),
-                            q_index, _lib.dptr(out), ldo, _lib.dptr(task), _lib.dptr(thr), _lib.dptr(ws), ws_bytes,
-                            _lib.stream_handle())
-    _lib.check(rc, "mr_pcb_vectors")
+    status = torch.zeros(K, dtype=torch.int32, device=dev)
+    for dense in ((1,) if force_dense else (0, 1)):
+        # fast path: dense radix passes on a 1/32 sample, then two windowed passes over everything; a window that misses
+        # the wanted rank is reported in `status` and the three dense passes over the whole vector run instead
+        rc = lib.mr_pcb_vectors(_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(lo), _lib.dptr(hi),
+                                q_index, dense, _lib.dptr(status), _lib.dptr(out), ldo, _lib.dptr(task), _lib.dptr(thr),
+                                _lib.dptr(ws), ws_bytes, _lib.stream_handle())
+        _lib.check(rc, "mr_pcb_vectors")
+        if bool((status.cpu() == 1).all()):
+            break
+    else:
+        raise _lib.MergeRecLibraryError("PCB quantile search failed")
     if return_diagnostics:
         return out, task, thr, lo, hi
     return out

@@ -111,3 +111,22 @@ def test_pcb_full_size_properties():
         tau = models[k] - base
         assert bool(((out[k, :d] == 0) | (torch.sign(out[k, :d]) == torch.sign(tau))).all())
     assert bool(torch.isfinite(out[:, :d]).all())
+
+
+def test_fast_and_dense_quantile_paths_agree():
+    """d large enough for the sampled + windowed search (d / 32 >= 4096): its quantile must be the exact order statistic
+    (host sort of the kernel's own balancing weights) and the vectors must equal those of the three dense passes bit for
+    bit."""
+    K, d, density = 5, 600_011, 0.2
+    base, models = synth.make_flat(d, K, seed=97)
+    tb, tm = dev(base), [dev(m) for m in models]
+    fast, task, thr, lo, hi = get_pcb_vectors(tb, tm, density=density, return_diagnostics=True)
+    dense, task_d, thr_d, *_ = get_pcb_vectors(tb, tm, density=density, return_diagnostics=True, force_dense=True)
+    assert torch.equal(thr, thr_d) and torch.equal(fast[:, :d], dense[:, :d])
+    srt = np.sort(task[:, :d].cpu().numpy(), axis=1)
+    assert np.array_equal(thr[:, 0].cpu().numpy(), srt[:, int(d * (1 - density))])
+    assert np.array_equal(thr[:, 1].cpu().numpy(), srt[:, -1])
+    for dens in (0.001, 0.9):            # quantiles in the tails
+        a, _, ta, *_ = get_pcb_vectors(tb, tm, density=dens, return_diagnostics=True)
+        b, _, tb2, *_ = get_pcb_vectors(tb, tm, density=dens, return_diagnostics=True, force_dense=True)
+        assert torch.equal(ta, tb2) and torch.equal(a[:, :d], b[:, :d]), dens
