@@ -7,13 +7,13 @@ away from exact threshold ties the results are bit-identical to the reference.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import torch
 
 from ... import _lib
 from ..layout import alloc_rows
-from ..types import FlattenedModel, FlattenedModel2D
+from ..types import FlattenedModel
 from ._common import as_rows
 
 

@@ -2,7 +2,7 @@
 (reference: rec_retrieval/merger/weight_learning/utils.py)."""
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 
