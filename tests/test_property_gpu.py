@@ -128,6 +128,11 @@ def test_ties_family(K, d, shift, seed, density, quant, specials):
     assert_bit_equal(host(fused), orc.lambda_merge(base, oT, lam), "fused TIES + lambda merge")
     assert_bit_equal(host(get_localize_and_stitch_vectors(tb, tm, density)), orc.lns_vectors(base, models, density),
                      "localize-and-stitch vectors")
+    # the sharded merger's select (per-slice estimate + windowed radix levels + tie scan) on a single rank
+    from mergerec_b200.merger.sharded import get_ties_vectors_sharded, merge_ties_sharded
+    assert_bit_equal(host(get_ties_vectors_sharded(tb, tm, density, d, None))[:, :d], oT, "sharded-path TIES vectors")
+    assert_bit_equal(host(merge_ties_sharded(tb, tm, w, density, d, None)), orc.merge_ties(base, models, w, density),
+                     "sharded-path merge_ties")
 
 
 @settings(**dict(SETTINGS, max_examples=max(30, SETTINGS["max_examples"] // 4)))
@@ -194,3 +199,26 @@ def test_distill_step(B, e4, D, seed, loss, big):
     scale_l = max(np.abs(o_losses).max(), 1e-3)
     assert np.abs(host(losses) - o_losses).max() <= 2e-5 * scale_l, (lname, rows, dom)
     assert np.abs(host(r.grad) - o_grad).max() <= 2e-5 * max(np.abs(o_grad).max(), 1e-6), (lname, rows, dom)
+
+
+@settings(**dict(SETTINGS, max_examples=max(20, SETTINGS["max_examples"] // 10)))
+@given(K=st.integers(2, 16), d=st.integers(500, 6000), seed=st.integers(0, 2 ** 31 - 1),
+       density=st.sampled_from([0.05, 0.2, 0.5, 0.9]), shift=st.integers(0, 3))
+def test_pcb_vectors(K, d, seed, density, shift):
+    """PCB vectors on random K / d / density and unaligned pointers: exact clamps and quantile, vectors within 2e-6 of the
+    row scale outside the columns whose balancing weight sits within 1e-3 relative of the clamp (see tests/test_pcb_gpu.py)."""
+    from hypothesis import assume
+    from mergerec_b200.merger.algorithms.pcb import get_pcb_vectors
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base, models = make_inputs(rng, K, d, False, False)
+    o_vec, o_task, o_q, o_max, o_lo, o_hi = orc.pcb_vectors(base, models, density, return_task=True)
+    assume(np.isfinite(o_vec).all() and (o_hi > o_lo).all() and (o_max > o_q).all())
+    tb, tm = shifted(base, shift, d), [shifted(m, shift, d) for m in models]
+    out, task, thr, lo, hi = get_pcb_vectors(tb, tm, density=density, return_diagnostics=True)
+    out, task, thr = host(out)[:, :d], host(task)[:, :d], host(thr)
+    assert np.array_equal(host(lo), o_lo) and np.array_equal(host(hi), o_hi)
+    srt = np.sort(task, axis=1)
+    assert np.array_equal(thr[:, 0], srt[:, int(d * (1 - density))]) and np.array_equal(thr[:, 1], srt[:, -1])
+    near = (np.abs(o_task - o_q[:, None]) <= 1e-3 * np.abs(o_q[:, None])).any(axis=0)
+    err = np.abs(out - o_vec) / np.abs(o_vec).max(axis=1, keepdims=True)
+    assert err[:, ~near].max() < 2e-6
