@@ -435,12 +435,14 @@ ties_final_kernel(TiesState* st, const uint32_t* __restrict__ fin_cnt, const u64
         if (threadIdx.x == 0) { st[k].status = err; status[k] = err; }
         return;
     }
-    for (int i = threadIdx.x; i < kTiesFinalCap; i += blockDim.x)
+    int cap2 = 2;                                  // sort only as many slots as the survivors need (block-uniform)
+    while (cap2 < (int)n) cap2 <<= 1;
+    for (int i = threadIdx.x; i < cap2; i += blockDim.x)
         s_keys[i] = (i < (int)n) ? fin_keys[(size_t)k * kTiesFinalCap + i] : 0;  // real keys are > 0 ... or equal 0 only
     __syncthreads();                                                              // for (mag 0, j = 2^32-1): harmless
-    for (int size = 2; size <= kTiesFinalCap; size <<= 1) {      // bitonic sort, descending
+    for (int size = 2; size <= cap2; size <<= 1) {               // bitonic sort, descending
         for (int strd = size >> 1; strd > 0; strd >>= 1) {
-            for (int i = threadIdx.x; i < kTiesFinalCap / 2; i += blockDim.x) {
+            for (int i = threadIdx.x; i < cap2 / 2; i += blockDim.x) {
                 const int a = 2 * i - (i & (strd - 1));
                 const int b = a + strd;
                 const bool desc = ((a & size) == 0);
