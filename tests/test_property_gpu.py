@@ -18,7 +18,10 @@ pytestmark = pytest.mark.gpu
 import os
 
 # MR_HYPOTHESIS_EXAMPLES=1000 turns the suite into a soak test (the default keeps `pytest -m gpu` under a minute)
+# Without the variable the examples are derived from the test body (derandomize): `pytest -m gpu` is reproducible; the
+# soak run draws fresh random examples.
 SETTINGS = dict(deadline=None, max_examples=int(os.environ.get("MR_HYPOTHESIS_EXAMPLES", "40")),
+                derandomize="MR_HYPOTHESIS_EXAMPLES" not in os.environ,
                 suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 
 
@@ -175,6 +178,7 @@ _DISTILL_LOSSES = [("CE", {}), ("KD", dict(temperature=2.0)), ("KD", dict(temper
 @settings(**dict(SETTINGS, max_examples=max(25, SETTINGS["max_examples"] // 8)))
 @given(B=st.integers(1, 20), e4=st.integers(1, 256), D=st.integers(1, 5), seed=st.integers(0, 2 ** 31 - 1),
        loss=st.sampled_from(_DISTILL_LOSSES), big=st.booleans())
+@example(B=1, e4=222, D=1, seed=2_147_483_646, loss=("KD", {"temperature": 0.1}), big=False)   # student ~ teacher: gradient cancels
 def test_distill_step(B, e4, D, seed, loss, big):
     """Distillation step (logits -> loss -> representation gradient) on ragged tables, every embedding width that is a
     multiple of 4 up to 1024, 1..20 samples spread over 1..5 domains (so groups of 1..4 samples and repeated passes over
@@ -198,7 +202,11 @@ def test_distill_step(B, e4, D, seed, loss, big):
     o_losses, _, o_grad = orc.distill_step(rep, tables, dom, teacher, lname, **kw)
     scale_l = max(np.abs(o_losses).max(), 1e-3)
     assert np.abs(host(losses) - o_losses).max() <= 2e-5 * scale_l, (lname, rows, dom)
-    assert np.abs(host(r.grad) - o_grad).max() <= 2e-5 * max(np.abs(o_grad).max(), 1e-6), (lname, rows, dom)
+    # the gradient is sum_n gz[n] * items[n] with |gz| up to ~max(1, T, 1/T): when student and teacher nearly agree it
+    # cancels to ~0, so the tolerance is anchored to the size of the terms as well as to the result
+    T = kw.get("temperature", 1.0)
+    term = max(1.0, T, 1.0 / T) * max(np.abs(t).max() for t in tables) / B
+    assert np.abs(host(r.grad) - o_grad).max() <= 2e-5 * np.abs(o_grad).max() + 2e-7 * term, (lname, rows, dom)
 
 
 @settings(**dict(SETTINGS, max_examples=max(20, SETTINGS["max_examples"] // 10)))
