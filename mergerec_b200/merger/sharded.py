@@ -152,11 +152,14 @@ def sharded_select(base_l: torch.Tensor, rows_l: Sequence[torch.Tensor], k_cnt: 
     LOCAL indices) such that, over all ranks, exactly the `k_cnt` largest `|w_k (m_k - base)|` of the whole vector
     survive, equal magnitudes resolved towards the lowest global index.
 
-    1. every rank takes the proportional order statistic of ITS slice (the single-GPU select); the global cut lies
-       between the smallest and the largest of them, which gives a first window a few per cent wide;
-    2. windowed histogram of the slice (`mr_ties_mag_hist`) -> all-reduce -> walk from the top to the bin holding rank
-       k -> that bin becomes the next window, 11 bits finer; repeat until a bin is a single bit pattern (2 levels for
-       the usual window, 3 for the full range, which is also the fallback when a window misses);
+    1. every rank takes the proportional order statistic of ITS slice (the single-GPU select, no host sync); the global
+       cut lies between the smallest and the largest of them up to the rounding of the ranks, so the first window of
+       magnitude bit patterns is their span plus a small margin;
+    2. windowed histogram of the slice (`mr_ties_mag_hist`) -> all-reduce -> the window must hold global rank k (else it
+       is widened 64-fold, finally to the full range, and the level repeats) -> walk from the top to the bin holding
+       rank k -> that bin becomes the next window, 11 bits finer; repeat until a bin is a single bit pattern (one level
+       when the shards have the same statistics, up to three for the full range); the last level also records
+       (bin, index) of its in-window elements;
     3. all-gather of the per-rank counts AT the cut magnitude, exclusive scan in rank order: lowest global index first."""
     K, dev = len(rows_l), base_l.device
     world, rank = _world(group)
