@@ -323,12 +323,66 @@ def gen_dare():
     save("dare", **out)
 
 
+def collab_distill_inputs(case):
+    """Seeded inputs shared with tests/test_collab_distill_gpu.py."""
+    rng = np.random.Generator(np.random.PCG64(case["seed"] + 9))
+    D, E, B, steps, n_seq = len(case["rows"]), 24, 6, 3, 5
+    tables = [rng.standard_normal((n, E), dtype=np.float32) for n in case["rows"]]
+    tables = [(t / np.linalg.norm(t, axis=-1, keepdims=True)).astype(np.float32) for t in tables]
+    t_items = [rng.standard_normal((n, E), dtype=np.float32) for n in case["rows"]]
+    t_seqs = [rng.standard_normal((n_seq, E), dtype=np.float32) for _ in case["rows"]]
+    ids = rng.integers(0, 37, size=(steps, B, 5)).astype(np.int64)
+    dom = rng.integers(0, D, size=(steps, B)).astype(np.int64)
+    seq = rng.integers(0, n_seq, size=(steps, B)).astype(np.int64)
+    return tables, t_items, t_seqs, ids, dom, seq
+
+
+def gen_collab_distill():
+    """The reference's load_merging_module + its loss classes + the `_forward_distill` loop (sequence/module.py:59-76,
+    cosine similarity) + Adam on lambda, three steps on the toy encoder: lambda trajectory and losses."""
+    from toy_model import ToyEncoder, make_toy_state_dicts
+    lf = _load_reference_loss_fn()
+    out = {}
+    for case in gc.COLLAB_DISTILL_CASES:
+        pre, fts = make_toy_state_dicts(case["K"], seed=case["seed"])
+        torch.manual_seed(1234)
+        mod = load_merging_module(MergeType.TASK_VECTOR, LearnType[case["learn_type"]], ToyEncoder(), pre, fts,
+                                  ignore_keys=set(), initial_per_weight=0.3, disable_softmax=True)
+        tables, t_items, t_seqs, ids, dom, seq = collab_distill_inputs(case)
+        score_embeddings = []
+        for ie, se in zip(t_items, t_seqs):
+            ie, se = T(ie), T(se)
+            ie = ie / ie.norm(dim=-1, keepdim=True)
+            se = se / se.norm(dim=-1, keepdim=True)
+            score_embeddings.append(se @ ie.T)
+        item_embeddings = [T(t) for t in tables]
+        loss_fn = reference_loss(lf, case["loss"], case["kw"])
+        opt = torch.optim.Adam(mod.trainable_parameters(True, True, False), lr=1e-2, weight_decay=0.0)
+        traj, losses = [], []
+        for step in range(ids.shape[0]):
+            opt.zero_grad()
+            rep = torch.nn.functional.normalize(mod.forward(T(ids[step])), p=2, dim=-1)
+            per = []
+            for i, (d_i, s_i) in enumerate(zip(dom[step].tolist(), seq[step].tolist())):
+                merged_model_logit = rep[i] @ item_embeddings[d_i].T
+                single_model_logit = score_embeddings[d_i][s_i]
+                per.append(loss_fn(merged_model_logit.unsqueeze(0), single_model_logit.unsqueeze(0)))
+            loss = torch.stack(per).mean()
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+            traj.append(np.stack([mod.per_weights[k].detach().numpy().copy() for k in mod.per_weights.keys()]))
+        out[f"{case['name']}/per_weights_traj"] = np.stack(traj)
+        out[f"{case['name']}/losses"] = np.asarray(losses, np.float64)
+    save("collab_distill", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
     only = set(sys.argv[1:])   # e.g. `make_golden.py lns` regenerates one file
     for name, fn in [("merge_flat", gen_merge_flat), ("model_merger", gen_model_merger), ("lambda_merge", gen_lambda),
                      ("ties", gen_ties), ("lns", gen_lns), ("evaluator", gen_evaluator), ("evaluator_bf16", gen_evaluator_bf16),
-                     ("module_e2e", gen_module_e2e), ("distill", gen_distill), ("pcb", gen_pcb), ("dare", gen_dare)]:
+                     ("module_e2e", gen_module_e2e), ("distill", gen_distill), ("pcb", gen_pcb), ("dare", gen_dare), ("collab_distill", gen_collab_distill)]:
         if not only or name in only:
             fn()

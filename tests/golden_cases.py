@@ -88,3 +88,9 @@ DARE_CASES = [
     dict(name="k2_p0", K=2, d=1000, seed=103, density=0.0, weights=[0.5, 0.5], torch_seed=9),
     dict(name="k2_p1", K=2, d=1000, seed=104, density=1.0, weights=[0.5, 0.5], torch_seed=10),
 ]
+
+# Stack B end to end: load_merging_module -> encoder -> distillation loss -> lambda-gradient -> Adam (3 steps).
+COLLAB_DISTILL_CASES = [
+    dict(name="layerwise_kd", K=3, seed=55, learn_type="LAYER_WISE", loss="KD", kw=dict(temperature=2.0), rows=[17, 40, 33]),
+    dict(name="taskwise_ce", K=4, seed=56, learn_type="TASK_WISE", loss="CE", kw={}, rows=[25, 64]),
+]
