@@ -202,3 +202,24 @@ def test_full_size_properties():
         n = teacher[b].shape[0]
         assert abs(gz[b, :n].double().sum().item()) < 1e-4
     assert torch.isfinite(l1).all() and (l1 >= -1e-5).all()      # KL divergence is non-negative
+
+
+def test_item_distill_module_shares_the_step():
+    """`DistillModule` (reference item/module.py): same kernels, item-side batch fields (`items`, `item_ids`)."""
+    from mergerec_b200.module.distiller import BatchDistillationItem, DistillModule
+    case = gc.DISTILL_CASES[0]
+    c = synth.make_distill_case(case["B"], case["E"], case["rows"], case["n_seq"], case["seed"], planted=case["scale"])
+    torch.manual_seed(3)
+    enc = _ToyEncoder(case["E"]).cuda()
+    teacher = TeacherScores([dev(t) for t in c["teacher_items"]], [dev(t) for t in c["teacher_seqs"]])
+    seq_mod = DistillSequenceModule(enc, teacher, lf.DistillKDLoss(2.0), similarity="cosine")
+    item_mod = DistillModule(enc, teacher, lf.DistillKDLoss(2.0), similarity="cosine")
+    seq_mod.item_embeddings = item_mod.item_embeddings = [dev(t) for t in c["tables"]]
+    a = seq_mod(BatchDistillationSequence(sequence=dev(c["rep"]), dataset_indexes=c["dataset_indexes"], sequence_ids=c["sequence_ids"]))
+    b = item_mod(BatchDistillationItem(items=dev(c["rep"]), dataset_indexes=c["dataset_indexes"], item_ids=c["sequence_ids"]))
+    assert torch.equal(a, b)
+    from types import SimpleNamespace
+    enc_only = item_mod(SimpleNamespace(items=dev(c["rep"])))
+    assert enc_only.shape == (case["B"], case["E"]) and torch.allclose(enc_only.norm(dim=-1), torch.ones(case["B"], device="cuda"), atol=1e-5)
+    with pytest.raises(ValueError):
+        item_mod(object())
