@@ -144,95 +144,188 @@ def event_time_ms(fn, iters: int) -> float:
 from bench_workloads import WORKLOADS, DEFAULT_WORKLOAD  # noqa: E402
 
 
-def run_ours(args):
-    rank, local_rank, world = dist_env()
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
-    torch.cuda.set_device(local_rank)
+def measure_tf32_peak(device) -> dict:
+    """cuBLAS TF32 GEMM (torch.matmul on fp32 operands with allow_tf32) at 8192^3: best of 10 (burst) and back to back
+    for ~2 s (sustained, under the power cap) -- the tensor-pipe denominators of the evaluator's roofline, measured in
+    this run on this GPU instead of derived from the bf16 figure."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=device)
+        b = torch.randn(n, n, device=device)
+        c = torch.empty(n, n, device=device)
+        flops = 2.0 * n ** 3
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e30
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(10):
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(2000.0 / best))
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        sustained = e0.elapsed_time(e1) / reps
+        return {"tf32_tflops": flops / (best * 1e-3) / 1e12, "tf32_tflops_sustained": flops / (sustained * 1e-3) / 1e12,
+                "how": f"torch.matmul fp32 with allow_tf32 (cuBLAS TF32), {n}^3: best of 10 / {reps} back to back"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+_L2_FLUSH = None
+
+
+def flush_l2(device):
+    """Write a 512 MB buffer (4x the 126 MB L2) so the next step starts from a cold cache."""
+    global _L2_FLUSH
+    if _L2_FLUSH is None or _L2_FLUSH.device != device:
+        _L2_FLUSH = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    _L2_FLUSH.fill_(1)
+
+
+def measure(wl, steps: int, warmup: int, rank: int, world: int, local_rank: int, cpu_arm: bool, sample_clocks: bool):
+    """One workload through the bench contract: W untimed warm-up steps, exactly K timed steps between barrier +
+    synchronize pairs (CUDA events, max over ranks), the end-to-end arm (pinned host inputs, host<->device copies in
+    the timed region), the roofline of the dominant kernel and the CPU arm.  Returns the JSON line (rank 0) or None."""
     import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = WORKLOADS[args.workload](rank=rank, world=world, device=torch.device("cuda", local_rank))
-    wl.setup()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl.setup()
     # clocks are sampled from the first warm-up step to the end of the last measured loop (the timed region
     # itself can be a few ms, shorter than one nvidia-smi sample period)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+    if sampler:
         sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         wl.step()
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        wl.step()
-    ev1.record()
-    barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
+    if getattr(wl, "l2_flush", False):
+        # inputs that fit L2: flush between the timed steps and time every step with its own event pair
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush_l2(wl.device)
+            a.record()
+            wl.step()
+            b.record()
+        barrier()
+        total_ms = reduce_max(sum(a.elapsed_time(b) for a, b in evs))
+    else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            wl.step()
+        ev1.record()
+        barrier()
+        total_ms = reduce_max(ev0.elapsed_time(ev1))
     if hasattr(wl, "finish"):
-        wl.finish()   # deferred host-side checks of the timed steps (e.g. the TIES select status word)
+        wl.finish()   # deferred host-side checks of the timed steps, checksums, stage timings (every rank)
 
     # end to end through the public API: pinned host inputs -> H2D -> kernels -> D2H result, every step
     wl.setup_e2e()
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(min(warmup, 2)):
         wl.step_e2e()
     barrier()
+    e2e_steps = max(1, min(steps, wl.e2e_steps_cap))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, wl.e2e_steps_cap))
     ev0.record()
     for _ in range(e2e_steps):
         wl.step_e2e()
     ev1.record()
     barrier()
     e2e_wall = time.perf_counter() - t0
-    ms2 = torch.tensor([max(ev0.elapsed_time(ev1), e2e_wall * 1e3)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(ms2.item()) / e2e_steps
+    e2e_ms = reduce_max(max(ev0.elapsed_time(ev1), e2e_wall * 1e3)) / e2e_steps
+    if hasattr(wl, "teardown_e2e"):
+        wl.teardown_e2e()
 
     roof = wl.roofline(measured_peaks()) if rank == 0 else None
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and cpu_arm:
         use_all_host_threads()
         cpu = wl.cpu_baseline()
+    if rank != 0:
+        return None
+    ms_per_step = total_ms / steps
+    units = wl.units_per_step_all_ranks()
+    line = {
+        "metric": wl.metric, "value": units / (ms_per_step * 1e-3), "unit": wl.unit, "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+        "config": wl.config(),
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": wl.h2d_bytes,
+                "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": e2e_ms, "steps": e2e_steps},
+        "gpu_launches": wl.launches_per_step * steps,
+        "roofline": roof,
+    }
+    if clocks is not None:
+        line["clocks"] = clocks
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    line.update(wl.extra())
+    if hasattr(wl, "Q"):
+        line["eval_seqs_per_s"] = wl.Q / (ms_per_step * 1e-3)
+    return line
 
+
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    cpu_arm = world == 1 and not args.no_cpu_baseline
+    wl = WORKLOADS[args.workload](rank=rank, world=world, device=device)
+    line = measure(wl, args.steps, args.warmup, rank, world, local_rank, cpu_arm, sample_clocks=True)
+    # the other hot path, carried beside the headline: the merger at the size BASELINE.json quotes it on (single GPU)
+    # or its sharded form (several GPUs) -- a complete nested line with its own roofline / e2e / cpu_baseline
+    comp_cls = None if args.no_companion else wl.companion()
+    if comp_cls is not None:
+        wl.release()
+        del wl
+        torch.cuda.empty_cache()
+        comp = comp_cls(rank=rank, world=world, device=device)
+        try:
+            sub = measure(comp, min(args.steps, 20), max(3, min(args.warmup, 5)), rank, world, local_rank, cpu_arm,
+                          sample_clocks=False)
+        except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
+            if world > 1:
+                raise
+            sub = {"error": repr(e)}
+        if rank == 0:
+            line[comp.companion_key] = sub
     if rank == 0:
-        ms_per_step = total_ms / args.steps
-        units = wl.units_per_step_all_ranks()
-        line = {
-            "metric": wl.metric, "value": units / (ms_per_step * 1e-3), "unit": wl.unit, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-            "config": wl.config(), "clocks": clocks,
-            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": wl.h2d_bytes,
-                    "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": e2e_ms, "steps": e2e_steps},
-            "gpu_launches": wl.launches_per_step * args.steps,
-            "roofline": roof,
-        }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
-        line.update(wl.extra())
-        if hasattr(wl, "Q"):
-            line["eval_seqs_per_s"] = wl.Q / (ms_per_step * 1e-3)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def run_reference(args):
-    """The reference's own CPU implementation of the path (the oracle port of it: the reference is pure
-    Python/torch and does not travel to the GPU box), all host threads, same metric/config."""
+    """The reference's own CPU implementation of the path on the box's host cores, all host threads, same metric /
+    config: the UNMODIFIED reference packages from baseline/_ref when they are installed (`kind: "reference"`), else the
+    oracle port (`kind: "port"`).  Every step is a bounded sample of the workload, actually run W + K times."""
     rank, _, world = dist_env()
     if rank != 0:
         return
@@ -243,7 +336,7 @@ def run_reference(args):
         "impl": "reference", "metric": wl.metric, "value": res["value"], "unit": wl.unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
-        "cpu_baseline": {"value": res["value"], "unit": wl.unit, "cores": res["cores"], "kind": "port",
+        "cpu_baseline": {"value": res["value"], "unit": wl.unit, "cores": res["cores"], "kind": res.get("kind", "port"),
                          "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -265,6 +358,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-companion", action="store_true", help="skip the nested merger line of the evaluator workloads")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: fewer than 3 warm-up steps requested; the timing rules ask for >= 3")

@@ -28,8 +28,46 @@ class Workload:
     def __init__(self, rank: int, world: int, device: Optional[torch.device]):
         self.rank, self.world, self.device = rank, world, device
 
+    companion_key = "merger"
+
     def extra(self) -> Dict:
         return {}
+
+    def companion(self):
+        """Workload class of the OTHER hot path to carry beside this line (nested, complete), or None."""
+        return None
+
+    def release(self) -> None:
+        """Drop every device tensor (called before a companion workload is set up)."""
+        for name in list(vars(self)):
+            if name not in ("rank", "world", "device"):
+                delattr(self, name)
+
+
+def reference_package():
+    """The unmodified reference hot-path packages installed under baseline/_ref (baseline/install_ref.py), or None."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("mr_install_ref", os.path.join(here, "baseline", "install_ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        return mod.load()
+    except Exception as e:  # noqa: BLE001 -- a broken copy falls back to the port, and says so
+        print(f"[bench] baseline/_ref could not be imported ({type(e).__name__}: {e}); using the oracle port", file=__import__("sys").stderr)
+        return None
+
+
+def timed_steps(fn, steps: int, warmup: int):
+    """Run fn() warmup + steps times; (mean seconds per timed step, list of step times)."""
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), ts
 
 
 def ncu_traffic(kernel: str):
@@ -76,7 +114,7 @@ class LambdaMergeK8(Workload):
         return {"workload": "BLaIR-base (RoBERTa-base, d=124,645,632, P=199) K=8 per-layer lambda merge (G=13) "
                             "from stored task vectors; merge half of BASELINE config 2",
                 "K": self.K, "d": self.d, "G": 13, "l2": "inputs (4.5 GB) exceed L2, no flush needed",
-                "parallelism": f"replicas x{self.world}" if self.world > 1 else "1 GPU"}
+                "parallelism": "single GPU (one merge is a few ms; the multi-GPU form is --workload ties_sharded)"}
 
     # -- device-resident arm
     def setup(self):
@@ -100,7 +138,7 @@ class LambdaMergeK8(Workload):
         merge_axpy(self.base, self.rows, self.w, _lib.MR_ORDER_SUM_FIRST, False, self.seg_end, self.seg_group, out=self.out)
 
     def units_per_step_all_ranks(self):
-        return self.bytes_per_step * self.world / GB
+        return self.bytes_per_step / GB     # one job; with several ranks every rank repeats it (no "x N" credit)
 
     # -- end-to-end arm: pinned host flat vectors in, merged flat vector out
     def setup_e2e(self):
@@ -155,7 +193,7 @@ class LambdaMergeK8(Workload):
                 "seconds_per_step": t}
 
     def reference_arm(self, steps, warmup):
-        t, cores = self._cpu_time(max(1, min(steps, 5)))
+        t, cores = self._cpu_time(max(1, steps))
         return {"value": self.bytes_per_step / GB / t, "ms_per_step": t * 1e3, "cores": cores,
                 "sample": f"full workload (d={self.d}, K={self.K}) per step, OpenMP C oracle port"}
 
@@ -179,9 +217,9 @@ class TiesCfg2(LambdaMergeK8):
                             "of K=8 BLaIR-base (RoBERTa-base, d=124,645,632, P=199) domain models + per-layer "
                             "lambda merge (G=13)",
                 "K": self.K, "d": self.d, "G": 13, "density": 0.2,
-                "l2": "inputs (4.5 GB) exceed L2, no flush needed", "cuda_graph": getattr(self, "graph", None) is not None,
+                "l2": "inputs (4.5 GB) exceed L2, no flush needed",
                 "select_status": "checked on the host after the timed loop (stream-ordered step)",
-                "parallelism": f"replicas x{self.world}" if self.world > 1 else "1 GPU"}
+                "parallelism": "single GPU (one merge is a few ms; the multi-GPU form is --workload ties_sharded)"}
 
     def setup(self):
         super().setup()
@@ -313,135 +351,237 @@ class TiesCfg2(LambdaMergeK8):
                 }}, "ties_build_kernel")
 
     def extra(self):
-        """The second hot path, reported beside the merger line: a short run of the evaluator workload
-        (`--workload eval_cfg5` is the full bench of it).  Single GPU only; failures are reported, not raised."""
-        if self.world != 1 or self.rank != 0 or os.environ.get("MR_BENCH_SKIP_EVAL_EXTRA"):
-            return {}
-        try:
-            from bench import event_time_ms, measured_peaks
-            for name in ("base", "models", "That", "Trows", "out"):   # free the merger's 9 GB first
-                if hasattr(self, name):
-                    delattr(self, name)
-            torch.cuda.empty_cache()
-            ev = EvalCatalog(0, 1, self.device)   # BASELINE config 5 at full size (about 0.4 s per step)
-            ev.setup()
-            ev.step()
-            torch.cuda.synchronize()
-            ms = event_time_ms(ev.step, 3)
-            roof = ev.roofline(measured_peaks())
-            return {"evaluator": {"metric": ev.metric, "value": ev.Q * ev.N / (ms * 1e-3), "unit": ev.unit,
-                                  "eval_seqs_per_s": ev.Q / (ms * 1e-3), "ms_per_step": ms, "config": ev.config(),
-                                  "metrics": ev.last, "roofline": roof}}
-        except Exception as e:  # noqa: BLE001
-            return {"evaluator": {"error": repr(e)}}
+        return {"cuda_graph": getattr(self, "graph", None) is not None}
 
     def _merge_only(self):
         from mergerec_b200 import _lib
         from mergerec_b200.merger.algorithms._common import merge_axpy
         merge_axpy(self.base, self.Trows, self.w, _lib.MR_ORDER_SUM_FIRST, False, self.seg_end, self.seg_group, out=self.out)
 
-    def _cpu_time(self, reps):
-        """Oracle port on a bounded sample: the full K = 8 but a prefix of the flat vector (the select is global
-        over whatever vector it is given, so the per-element work is the same)."""
-        from oracle import oracle as orc
-        frac = 8
-        d = self.d // frac
+    # -- CPU arms.  Port: the OpenMP C oracle at the FULL size of the workload (about 2 s per step).  Reference: the
+    #    unmodified `get_ties_vectors` + `TaskVectorMergingModuleLayerWise._merge_task_vectors` from baseline/_ref on a
+    #    RoBERTa-shaped slice (12 layers, hidden 64: same P = 199 tensors and G = 13 groups, d = 3.85 M) -- at full
+    #    size the reference needs minutes per step (single-threaded torch.topk over 1.2e8 elements per model).
+    def _port_inputs(self):
         rng = np.random.Generator(np.random.PCG64(7))
+        d = self.d
         base = rng.standard_normal(d, dtype=np.float32) * np.float32(0.02)
         models = [base + np.float32(1e-3) * rng.standard_normal(d, dtype=np.float32) for _ in range(self.K)]
-        w = rng.uniform(0.1, 0.5, size=(1, self.K)).astype(np.float32)
-        ts = []
-        for _ in range(reps):
-            t0 = time.perf_counter()
+        from oracle import oracle as orc
+        sb, se, sg, keys = orc.segment_table(self.shapes, layer_wise=True)
+        w = rng.uniform(0.1, 0.5, size=(len(keys), self.K)).astype(np.float32)
+        return base, models, w, sb, se, sg
+
+    def _port_step_fn(self):
+        from oracle import oracle as orc
+        base, models, w, sb, se, sg = self._port_inputs()
+
+        def step():
             That = orc.ties_vectors(base, models, 0.2)
-            orc.lambda_merge(base, That, w)
-            ts.append(time.perf_counter() - t0)
-        self._cpu_sample = f"d/{frac} = {d} flat elements of the K={self.K} workload (select is global over the sample), OpenMP C oracle port"
-        return float(np.median(ts)) * frac, orc.max_threads()
+            orc.lambda_merge(base, That, w, sb, se, sg)
+        return step, self.bytes_per_step, (f"full workload (d={self.d}, K={self.K}): ties_vectors + per-layer lambda merge, "
+                                           "OpenMP C oracle port")
+
+    def _reference_step_fn(self):
+        ref = reference_package()
+        if ref is None:
+            return None
+        from rec_retrieval.merger.algorithms.ties import get_ties_vectors
+        from rec_retrieval.merger.weight_learning.module.layer_wise import TaskVectorMergingModuleLayerWise
+        shapes = synth.roberta_shapes(hidden=64, ffn=256)
+        d = synth.total_numel(shapes)
+        g = torch.Generator().manual_seed(7)
+        base = torch.randn(d, generator=g) * 0.02
+        models = [base + 1e-3 * torch.randn(d, generator=g) for _ in range(self.K)]
+        shape_dict = {k: torch.Size(v) for k, v in shapes.items()}
+
+        class _NoModel(torch.nn.Module):
+            def forward(self, x):
+                return x
+
+        def step():
+            That = get_ties_vectors(base, models, 0.2)
+            mod = TaskVectorMergingModuleLayerWise(base, That, _NoModel(), shape_dict, disable_softmax=True)
+            with torch.no_grad():
+                mod._merge_task_vectors()
+        nbytes = ((2 * self.K + 1) + (self.K + 2)) * d * 4
+        return step, nbytes, (f"UNMODIFIED reference (get_ties_vectors + TaskVectorMergingModuleLayerWise._merge_task_vectors) on a "
+                              f"RoBERTa-shaped slice: 12 layers, hidden 64, P=199, G=13, d={d}, K={self.K}, density 0.2")
 
     def cpu_baseline(self):
-        t, cores = self._cpu_time(2)
-        return {"value": self.bytes_per_step / GB / t, "unit": self.unit, "cores": cores, "kind": "port",
-                "sample": self._cpu_sample + "; time scaled x8 to the full vector", "seconds_per_step": t}
+        from oracle import oracle as orc
+        fn, nbytes, sample = self._port_step_fn()
+        t, ts = timed_steps(fn, 3, 1)
+        t = float(np.median(ts))
+        out = {"value": nbytes / GB / t, "unit": self.unit, "cores": orc.max_threads(), "kind": "port",
+               "sample": sample + "; median of 3 after 1 warm-up", "seconds_per_step": t}
+        r = self._reference_step_fn()
+        if r is not None:
+            rfn, rbytes, rsample = r
+            rt, rts = timed_steps(rfn, 2, 1)
+            rt = float(np.median(rts))
+            out["reference"] = {"value": rbytes / GB / rt, "unit": self.unit, "cores": torch.get_num_threads(), "kind": "reference",
+                                "sample": rsample + "; median of 2 after 1 warm-up", "seconds_per_step": rt}
+        return out
 
     def reference_arm(self, steps, warmup):
-        t, cores = self._cpu_time(max(1, min(steps, 3)))
-        return {"value": self.bytes_per_step / GB / t, "ms_per_step": t * 1e3, "cores": cores,
-                "sample": self._cpu_sample + "; time scaled x8 to the full vector"}
+        from oracle import oracle as orc
+        r = self._reference_step_fn()
+        if r is not None:
+            fn, nbytes, sample = r
+            t, _ = timed_steps(fn, steps, warmup)
+            return {"value": nbytes / GB / t, "ms_per_step": t * 1e3, "cores": torch.get_num_threads(), "kind": "reference",
+                    "sample": sample + " per step"}
+        fn, nbytes, sample = self._port_step_fn()
+        t, _ = timed_steps(fn, steps, warmup)
+        return {"value": nbytes / GB / t, "ms_per_step": t * 1e3, "cores": orc.max_threads(), "kind": "port",
+                "sample": sample + " per step"}
 
 
 class EvalCatalog(Workload):
     """BASELINE config 5 (evaluator): full-catalog scoring of Q query embeddings against an N-item table (E = 768),
     fused per-row top-100, label rank and Recall/NDCG.  The item table is sharded over the ranks (N / world rows
-    each, strong scaling); every rank scores all queries against its shard, the per-rank top-K lists are
-    allgathered over NCCL and merged.  One step = one pass of all Q queries over the whole catalog.
+    each, strong scaling); every rank scores all queries against its shard, the per-rank top-K lists are exchanged by
+    ONE NCCL all-gather and merged.  One step = one pass of all Q queries over the whole catalog.
 
-    Default sizes are config 5 itself: Q = 65,536 queries, N = 1,000,000 items, E = 768, top-100 (1.0e14 multiply-adds
-    worth of logical FLOPs, x3 tensor passes); MR_BENCH_EVAL_Q / _N / _K / _E override them."""
+    Default sizes are config 5 itself: Q = 65,536 queries, N = 1,000,000 items, E = 768, top-100 (1.0e14 logical FLOP,
+    x3 tensor passes); MR_BENCH_EVAL_Q / _N / _K / _E override them (for debugging only)."""
 
     name = "eval_cfg5"
+    label = "BASELINE config 5"
     metric = "catalog scores/sec (Q*N / time, fused scoring + top-K + Recall/NDCG)"
     unit = "scores/s"
     dtype = "tf32x3 (fp32-faithful split, fp32 accumulate)"
     scaling = "strong"
     e2e_steps_cap = 3
+    sizes = dict(Q=65536, N=1_000_000, E=768, K=100)
+    ks_low = 10
+    cpu_sample = dict(Q=128)          # queries per CPU step (full catalog width)
+    accuracy_rows = 2048
 
     def __init__(self, rank, world, device):
         super().__init__(rank, world, device)
-        self.Q = int(os.environ.get("MR_BENCH_EVAL_Q", 65536))
-        self.N = int(os.environ.get("MR_BENCH_EVAL_N", 1_000_000))
-        self.E = int(os.environ.get("MR_BENCH_EVAL_E", 768))
-        self.K = int(os.environ.get("MR_BENCH_EVAL_K", 100))
+        self.Q = int(os.environ.get("MR_BENCH_EVAL_Q", self.sizes["Q"]))
+        self.N = int(os.environ.get("MR_BENCH_EVAL_N", self.sizes["N"]))
+        self.E = int(os.environ.get("MR_BENCH_EVAL_E", self.sizes["E"]))
+        self.K = int(os.environ.get("MR_BENCH_EVAL_K", self.sizes["K"]))
         self.mode = int(os.environ.get("MR_BENCH_EVAL_MODE", 0))
+        self.ks = sorted({min(self.ks_low, self.K), self.K})
         self.flops = 2.0 * self.Q * self.N * self.E
-        self.launches_per_step = 4 if world == 1 else 5  # split_tf32(users), score_topk, topk_merge, [shard merge], label_rank
+        self.l2_flush = (self.Q + self.N) * self.E * 8 < (256 << 20)   # hi + lo operands smaller than 2x L2: flush
+        # split is part of the operand format (prepared once); per step: score_topk, its list merge, [all-gather is
+        # NCCL's], shard merge, label_rank
+        self.launches_per_step = 3 if world == 1 else 4
+        self._stage = None
+        self._checksum = None
+        self._accuracy = None
+
+    def companion(self):
+        return TiesCfg2 if self.world == 1 else TiesSharded
 
     def config(self):
-        return {"workload": f"BASELINE config 5: {self.Q} query seqs x {self.N}-item catalog, E={self.E}, "
-                            f"top-{self.K}, Recall/NDCG@{{10,{self.K}}}; item table sharded over {self.world} GPU(s), "
-                            "NCCL allgather of per-GPU top-K + merge",
+        return {"workload": f"{self.label}: {self.Q} query seqs x {self.N}-item catalog, E={self.E}, "
+                            f"top-{self.K}, Recall/NDCG@{{{','.join(str(k) for k in self.ks)}}}; item table row-sharded over the GPUs, "
+                            "one NCCL all-gather of the per-GPU top-K lists + merge",
                 "Q": self.Q, "N": self.N, "E": self.E, "K": self.K, "mode": "tf32x3" if self.mode == 0 else "tf32x1",
-                "l2": "item table (3.1 GB x2 hi/lo at N=1M) exceeds L2, no flush needed",
-                "parallelism": f"item-sharded x{self.world}" if self.world > 1 else "1 GPU"}
+                "l2": ("operands fit L2: a 512 MB buffer is written between timed steps (flush)" if self.l2_flush else
+                       f"item table ({self.N * self.E * 8 / 1e9:.1f} GB as hi/lo operands) exceeds L2, no flush needed"),
+                "parallelism": "item table sharded N/G rows per GPU, queries replicated (strong scaling)"}
+
+    # ---------------------------------------------------------------------------------------------- inputs
+    def _make_inputs(self, device, lo, hi):
+        """Same queries / labels on every rank; the item table generated chunk by chunk (seeded per chunk) so that every
+        rank sees the same catalog and keeps rows [lo, hi).  Half of the queries are planted near their label item so
+        Recall / NDCG are non-trivial."""
+        g = torch.Generator(device=device).manual_seed(99)
+        users = torch.randn(self.Q, self.E, generator=g, device=device)
+        labels = torch.randint(0, self.N, (self.Q,), generator=g, device=device)
+        planted = torch.rand(self.Q, generator=g, device=device) < 0.5
+        items = torch.empty(hi - lo, self.E, device=device)
+        label_rows = torch.empty(self.Q, self.E, device=device)
+        chunk = 65536
+        for c0 in range(0, self.N, chunk):
+            c1 = min(self.N, c0 + chunk)
+            gi = torch.Generator(device=device).manual_seed(1000 + c0 // chunk)
+            rows = torch.nn.functional.normalize(torch.randn(c1 - c0, self.E, generator=gi, device=device), dim=-1)
+            a, b = max(c0, lo), min(c1, hi)
+            if a < b:
+                items[a - lo:b - lo] = rows[a - c0:b - c0]
+            sel = (labels >= c0) & (labels < c1)
+            if bool(sel.any()):
+                label_rows[sel] = rows[labels[sel] - c0]
+        users = torch.where(planted[:, None], label_rows + 0.5 * users / self.E ** 0.5, users)
+        return torch.nn.functional.normalize(users, dim=-1), items, labels
 
     def setup(self):
         import torch.distributed as dist
         from mergerec_b200.evaluator import Evaluator, ShardedItemTable, shard_bounds
-        # every rank generates the same full table chunk by chunk (seeded), keeps its own rows and the rows of the
-        # labels: half of the queries are planted near their label item so Recall / NDCG are non-trivial
-        g = torch.Generator(device=self.device).manual_seed(99)       # same queries and labels on every rank
-        users = torch.randn(self.Q, self.E, generator=g, device=self.device)
-        self.labels = torch.randint(0, self.N, (self.Q,), generator=g, device=self.device)
-        planted = torch.rand(self.Q, generator=g, device=self.device) < 0.5
         lo, hi = shard_bounds(self.N, self.world, self.rank)
-        self.items = torch.empty(hi - lo, self.E, device=self.device)
-        label_rows = torch.empty(self.Q, self.E, device=self.device)
-        chunk = 65536
-        for c0 in range(0, self.N, chunk):
-            c1 = min(self.N, c0 + chunk)
-            gi = torch.Generator(device=self.device).manual_seed(1000 + c0 // chunk)
-            rows = torch.nn.functional.normalize(torch.randn(c1 - c0, self.E, generator=gi, device=self.device), dim=-1)
-            a, b = max(c0, lo), min(c1, hi)
-            if a < b:
-                self.items[a - lo:b - lo] = rows[a - c0:b - c0]
-            sel = (self.labels >= c0) & (self.labels < c1)
-            if bool(sel.any()):
-                label_rows[sel] = rows[self.labels[sel] - c0]
-        users = torch.where(planted[:, None], label_rows + 0.5 * users / self.E ** 0.5, users)
-        self.users = torch.nn.functional.normalize(users, dim=-1)
-        del label_rows, users
+        self.users, self.items, self.labels = self._make_inputs(self.device, lo, hi)
         self.lo = lo
         self.group = dist.group.WORLD if self.world > 1 else None
         self.table = ShardedItemTable(self.items, id_base=lo, n_total=self.N, group=self.group)
-        self.ev = Evaluator(["RECALL", "NDCG"], [10, self.K])
+        self.ev = Evaluator(["RECALL", "NDCG"], self.ks)
+        self.queries = self.ev.prepare_queries(self.users)      # operand format of the kernel: split once, reused
         self.last = None
 
     def step(self):
-        self.last = self.ev.evaluate_embeddings(self.users, self.table, self.labels, mode=self.mode)
+        self.last = self.ev.evaluate_embeddings(self.queries, self.table, self.labels, mode=self.mode)
 
     def units_per_step_all_ranks(self):
         return float(self.Q) * float(self.N)
 
+    # ---------------------------------------------------------------------------------------------- after the loop
+    def finish(self):
+        """Every rank: (1) checksums of the merged top-K lists -- integers that must not depend on the number of GPUs;
+        (2) the step cut into stages with CUDA events / host clocks (where the non-kernel time goes)."""
+        import torch.distributed as dist
+        from mergerec_b200.evaluator.evaluator import score_topk
+        from mergerec_b200.evaluator.metrics import label_rank
+        from mergerec_b200.evaluator.sharded import exchange_packed, new_packed_list
+        vals, ids = self.ev.topk_embeddings(self.queries, self.table, self.K, mode=self.mode)
+        pos = torch.arange(1, self.K + 1, device=self.device, dtype=torch.int64)
+        self._checksum = {
+            "topk_ids": int(((ids.to(torch.int64) + 1) * pos).sum().item()),
+            "topk_score_bits": int((vals.view(torch.int32).to(torch.int64) * pos).sum().item()),
+            "note": "sum over (q, r) of (id + 1) * (r + 1) and of score bits * (r + 1): equal for every --gpus N"}
+        del vals, ids
+
+        def ev_ms(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            b.synchronize()
+            return a.elapsed_time(b) / reps
+
+        Q, K = self.Q, self.K
+        local, lv, li = new_packed_list(Q, K, self.device)
+        st = {"score_topk_kernel_plus_split_merge": ev_ms(lambda: score_topk(self.queries.hi, self.queries.lo, self.table, K, self.mode, out=(lv, li)), 2)}
+        if self.world > 1:
+            gathered = self.table.gather_buffer(Q, K)
+            dist.barrier()
+            st["all_gather_plus_shard_merge"] = ev_ms(lambda: exchange_packed(local, K, self.group, gathered=gathered))
+            st["all_gather_alone"] = ev_ms(lambda: dist.all_gather_into_tensor(gathered.view(self.world * 2 * Q, K), local.view(2 * Q, K), group=self.group))
+            ids = exchange_packed(local, K, self.group, gathered=gathered)[1]
+        else:
+            ids = li
+        st["label_rank_kernel"] = ev_ms(lambda: label_rank(ids, self.labels))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            self.ev.metrics_from_ids(ids, self.labels)
+        st["label_rank_d2h_and_host_metrics_wall"] = (time.perf_counter() - t0) / 3 * 1e3
+        if self.world > 1:
+            t = torch.tensor([st[k] for k in sorted(st)], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            st = {k: float(v) for k, v in zip(sorted(st), t.tolist())}
+        self._stage = st
+
+    # ---------------------------------------------------------------------------------------------- end to end
     def setup_e2e(self):
         self.h_users = _pinned(self.users.cpu())
         self.h_items = _pinned(self.items.cpu())
@@ -450,65 +590,187 @@ class EvalCatalog(Workload):
         self.d2h_bytes = self.Q * 4          # the rank of each label; the metric floats are finished on the host
 
     def step_e2e(self):
+        """Host embeddings in, metric floats out: H2D of queries / this rank's item rows / labels, operand split of both,
+        fused scoring + top-K, exchange, label rank, D2H of the ranks, host finalisation."""
         from mergerec_b200.evaluator import ShardedItemTable
         users = self.h_users.to(self.device, non_blocking=True)
         items = self.h_items.to(self.device, non_blocking=True)
         labels = self.h_labels.to(self.device, non_blocking=True)
         table = ShardedItemTable(items, id_base=self.lo, n_total=self.N, group=self.group)
+        table._ws, table._gathered = self.table._ws, self.table._gathered     # scratch is reused, data is not
         self.last = self.ev.evaluate_embeddings(users, table, labels, mode=self.mode)
 
+    def teardown_e2e(self):
+        del self.h_users, self.h_items, self.h_labels
+
+    # ---------------------------------------------------------------------------------------------- roofline
     def roofline(self, peaks):
-        from bench import event_time_ms
+        from bench import event_time_ms, measure_tf32_peak
         from mergerec_b200.evaluator.evaluator import score_topk
-        from mergerec_b200.evaluator.sharded import split_tf32
-        u_hi, u_lo = split_tf32(self.users)
-        ms = event_time_ms(lambda: score_topk(u_hi, u_lo, self.table, self.K, self.mode), 2)
+        ms = event_time_ms(lambda: score_topk(self.queries.hi, self.queries.lo, self.table, self.K, self.mode), 2)
         passes = 3 if self.mode == 0 else 1
         local_flops = 2.0 * self.Q * self.table.n_local * self.E
         ach = passes * local_flops / (ms * 1e-3) / 1e12
-        # a launch of a few ms runs at boost clocks (burst peak); one of hundreds of ms sits at the 1 kW power cap
-        # like the driver's sustained cuBLAS loop (sustained peak).  TF32 runs at half the bf16 rate.
+        # a launch of a few ms runs at boost clocks (burst peak); one of hundreds of ms sits at the 1 kW power cap like
+        # a back-to-back cuBLAS loop (sustained peak).  Both TF32 peaks are measured here with cuBLAS; the figures
+        # derived from MEASURED_PEAKS.json's bf16 numbers (/ 2) are listed beside them.
+        tf32 = measure_tf32_peak(self.device)
         sustained = ms > 100.0
-        peak = (peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]) / 2
-        return {"bound": "tensor", "kernel": "mr::st::score_topk_kernel<2, 32> (tcgen05.mma kind::tf32, cta_group::2) + list merge",
+        peak = tf32["tf32_tflops_sustained"] if sustained else tf32["tf32_tflops"]
+        roof = {"bound": "tensor", "kernel": "mr::st::score_topk_kernel<2, 32> (tcgen05.mma kind::tf32, cta_group::2) + list merge",
                 "achieved": ach, "peak": peak,
-                "peak_source": peaks["source"] + (": sustained" if sustained else ": burst") + " bf16 cuBLAS / 2 (tf32 runs at half the bf16 rate)",
+                "peak_source": "cuBLAS TF32 GEMM 8192^3 measured in this run (" + ("sustained, back to back for ~2 s" if sustained else "burst, best of 10") + ")",
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms_per_launch": ms,
                 "tensor_passes": passes, "logical_tflops": local_flops / (ms * 1e-3) / 1e12,
                 "algorithmic_flops_per_launch": passes * local_flops,
-                "frac_of_burst_peak": ach / (peaks["bf16_tflops"] / 2),
-                "frac_of_sustained_peak": ach / (peaks["bf16_tflops_sustained"] / 2)}
+                "tf32_peak_measured": tf32,
+                "frac_of_measured_burst": ach / tf32["tf32_tflops"], "frac_of_measured_sustained": ach / tf32["tf32_tflops_sustained"],
+                "frac_of_bf16_derived_burst": ach / (peaks["bf16_tflops"] / 2),
+                "frac_of_bf16_derived_sustained": ach / (peaks["bf16_tflops_sustained"] / 2)}
+        if self.world == 1 and not os.environ.get("MR_BENCH_SKIP_ACCURACY"):
+            try:
+                self._accuracy = self.accuracy()
+            except Exception as e:  # noqa: BLE001 -- the accuracy figure is reported, never fatal
+                self._accuracy = {"error": repr(e)}
+        return roof
+
+    def accuracy(self):
+        """Parity figure of the 3xTF32 path AT THIS SCALE on Gaussian (non-grid) inputs: the top-K of a slice of the
+        queries against the whole catalog, compared with (a) plain fp32 CUDA-core scoring (`mr_scores_fp32`: one fp32
+        FMA chain per score) + `mr_topk_rows` and (b) an fp64 ranking (torch fp64 matmul + stable sort by
+        (score desc, id asc))."""
+        from mergerec_b200 import _lib
+        from mergerec_b200.evaluator.evaluator import topk_rows
+        from mergerec_b200.evaluator.metrics import label_rank, ndcg_from_ranks, recall_from_ranks
+        lib = _lib.load()
+        Qs, K, N, E = min(self.accuracy_rows, self.Q), self.K, self.table.n_local, self.E
+        users = self.users[:Qs].contiguous()
+        v3, i3 = self.ev.topk_embeddings(users, self.table, K, mode=self.mode)
+        # (a) fp32 CUDA-core scores, materialised in row chunks
+        i32 = torch.empty((Qs, K), dtype=torch.int32, device=self.device)
+        v32 = torch.empty((Qs, K), dtype=torch.float32, device=self.device)
+        i64 = torch.empty((Qs, K), dtype=torch.int32, device=self.device)
+        v64 = torch.empty((Qs, K), dtype=torch.float64, device=self.device)
+        rows = max(1, min(Qs, (8 << 30) // (N * 8)))
+        items64 = self.items.double()
+        for q0 in range(0, Qs, rows):
+            q1 = min(Qs, q0 + rows)
+            sc = torch.empty((q1 - q0, N), dtype=torch.float32, device=self.device)
+            _lib.check(lib.mr_scores_fp32(_lib.dptr(users[q0:q1]), q1 - q0, _lib.dptr(self.items), N, E, _lib.dptr(sc), N,
+                                          _lib.stream_handle()), "mr_scores_fp32")
+            v, i = topk_rows(sc, K)
+            v32[q0:q1], i32[q0:q1] = v, i
+            del sc
+            s64 = users[q0:q1].double() @ items64.T
+            v, i = torch.topk(s64, K + 8, dim=1)                 # a few extra, then the canonical order among equal scores
+            order = torch.argsort(i, dim=1, stable=True)
+            v, i = torch.gather(v, 1, order), torch.gather(i, 1, order)
+            order = torch.argsort(v, dim=1, descending=True, stable=True)
+            v, i = torch.gather(v, 1, order)[:, :K], torch.gather(i, 1, order)[:, :K]
+            v64[q0:q1], i64[q0:q1] = v, i.to(torch.int32)
+            del s64
+        del items64
+
+        def cmp_ids(a, b):
+            diff = a != b
+            rows_diff = diff.any(dim=1)
+            first = torch.where(rows_diff, diff.to(torch.int32).argmax(dim=1), torch.full_like(rows_diff, K, dtype=torch.int64))
+            same_set = (torch.sort(a, dim=1).values == torch.sort(b, dim=1).values).all(dim=1)
+            return {"rows_differing": int(rows_diff.sum()), "rows": int(a.shape[0]),
+                    "first_differing_rank_min": int(first.min()) if bool(rows_diff.any()) else None,
+                    "rows_with_different_id_SET": int((~same_set).sum())}
+
+        labels = self.labels[:Qs]
+
+        def mets(ids):
+            r = label_rank(ids, labels).cpu().numpy()
+            return {f"Recall@{k}": recall_from_ranks(r, k) for k in self.ks} | {f"NDCG@{k}": ndcg_from_ranks(r, k) for k in self.ks}
+
+        m3, m32, m64 = mets(i3), mets(i32), mets(i64)
+        # smallest fp64 gap between neighbours of the fp64 list: what a swap has to overcome
+        gaps = (v64[:, :-1] - v64[:, 1:])
+        res = {"slice": f"first {Qs} queries x all {N} items, top-{K}, unit-norm Gaussian embeddings (half of the queries planted near their label)",
+               "tf32x3_vs_fp64": cmp_ids(i3, i64), "tf32x3_vs_fp32_cuda_cores": cmp_ids(i3, i32), "fp32_cuda_cores_vs_fp64": cmp_ids(i32, i64),
+               "max_abs_score_error_vs_fp64_at_equal_ids": {
+                   "tf32x3": float(((v3.double() - v64).abs() * (i3 == i64)).max()),
+                   "fp32_cuda_cores": float(((v32.double() - v64).abs() * (i32 == i64)).max())},
+               "fp64_neighbour_gap": {"min": float(gaps.min()), "median": float(gaps.median())},
+               "metrics_tf32x3": m3, "metrics_fp32": m32, "metrics_fp64": m64,
+               "metrics_identical_to_fp64": m3 == m64, "metrics_identical_to_fp32": m3 == m32}
+        return res
 
     def extra(self):
-        return {"metrics": self.last}
+        out = {"metrics": self.last, "checksum": self._checksum, "stage_ms": self._stage}
+        if self._accuracy is not None:
+            out["accuracy"] = self._accuracy
+        return out
 
-    # -- CPU arms: fp32 sgemm + canonical top-K + metrics (oracle port of module.py:137 + evaluator.py:31-49)
-    def _cpu_time(self, reps):
-        from oracle import oracle as orc
-        Qs, Ns = min(self.Q, 256), min(self.N, 100_000)
+    # ---------------------------------------------------------------------------------------------- CPU arms
+    # One CPU step = `cpu_sample["Q"]` queries against the WHOLE catalog: scores = U @ I.T (module.py:137) followed by
+    # Evaluator(["RECALL", "NDCG"], ks)(scores, labels) (evaluator.py:31-49).  Reference = the unmodified
+    # rec_retrieval.evaluator from baseline/_ref (torch CPU matmul + torch.topk + the python metric loops); port = numpy
+    # BLAS sgemm + the OpenMP C top-K + python metric loops of oracle/.
+    def _cpu_inputs(self):
+        Qs = min(self.Q, self.cpu_sample["Q"])
         rng = np.random.Generator(np.random.PCG64(7))
         users = rng.standard_normal((Qs, self.E), dtype=np.float32)
-        items = rng.standard_normal((Ns, self.E), dtype=np.float32)
-        labels = rng.integers(0, Ns, size=Qs)
-        ts = []
-        for _ in range(reps + 1):
-            t0 = time.perf_counter()
+        items = rng.standard_normal((self.N, self.E), dtype=np.float32)
+        labels = rng.integers(0, self.N, size=Qs)
+        return users, items, labels, Qs
+
+    def _port_step_fn(self):
+        from oracle import oracle as orc
+        users, items, labels, Qs = self._cpu_inputs()
+        ks = [min(k, self.N) for k in self.ks]
+
+        def step():
             scores = orc.scores_f32(users, items)
-            orc.evaluate(scores, labels, ["RECALL", "NDCG"], [10, min(self.K, Ns)])
-            ts.append(time.perf_counter() - t0)
-        t = float(np.median(ts[1:]))
-        self._cpu_sample = (f"{Qs} queries x {Ns} items (E={self.E}) of the workload: numpy/BLAS sgemm + OpenMP C top-K + "
-                            "python metric loops (oracle port); rate scaled linearly")
-        return t, Qs * Ns, max(orc.max_threads(), os.cpu_count() or 1)
+            orc.evaluate(scores, labels, ["RECALL", "NDCG"], ks)
+        return step, float(Qs) * self.N, (f"{Qs} queries x the whole {self.N}-item catalog (E={self.E}), top-{ks[-1]}: numpy/BLAS sgemm + "
+                                          "OpenMP C top-K + python metric loops (oracle port)")
+
+    def _reference_step_fn(self):
+        if reference_package() is None:
+            return None
+        from rec_retrieval.evaluator import Evaluator as RefEvaluator
+        users, items, labels, Qs = self._cpu_inputs()
+        tu, ti, tl = torch.from_numpy(users), torch.from_numpy(items), torch.from_numpy(labels)
+        ev = RefEvaluator(["RECALL", "NDCG"], [min(k, self.N) for k in self.ks])
+
+        def step():
+            scores = tu @ ti.T
+            ev(scores, tl)
+        return step, float(Qs) * self.N, (f"UNMODIFIED reference: scores = U @ I.T (torch CPU fp32) + rec_retrieval.evaluator.Evaluator on "
+                                          f"{Qs} queries x the whole {self.N}-item catalog (E={self.E}), top-{self.ks[-1]}")
 
     def cpu_baseline(self):
-        t, n, cores = self._cpu_time(2)
-        return {"value": n / t, "unit": self.unit, "cores": cores, "kind": "port", "sample": self._cpu_sample,
-                "seconds_per_sample": t}
+        from oracle import oracle as orc
+        fn, units, sample = self._port_step_fn()
+        _, ts = timed_steps(fn, 3, 1)
+        t = float(np.median(ts))
+        port = {"value": units / t, "unit": self.unit, "cores": max(orc.max_threads(), torch.get_num_threads()), "kind": "port",
+                "sample": sample + "; median of 3 after 1 warm-up", "seconds_per_step": t}
+        r = self._reference_step_fn()
+        if r is None:
+            return port
+        rfn, runits, rsample = r
+        _, rts = timed_steps(rfn, 3, 1)
+        rt = float(np.median(rts))
+        return {"value": runits / rt, "unit": self.unit, "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": rsample + "; median of 3 after 1 warm-up", "seconds_per_step": rt, "port": port}
 
     def reference_arm(self, steps, warmup):
-        t, n, cores = self._cpu_time(max(1, min(steps, 3)))
-        return {"value": n / t, "ms_per_step": t * 1e3, "cores": cores, "sample": self._cpu_sample}
+        from oracle import oracle as orc
+        r = self._reference_step_fn()
+        if r is not None:
+            fn, units, sample = r
+            t, _ = timed_steps(fn, steps, warmup)
+            return {"value": units / t, "ms_per_step": t * 1e3, "cores": torch.get_num_threads(), "kind": "reference",
+                    "sample": sample + " per step"}
+        fn, units, sample = self._port_step_fn()
+        t, _ = timed_steps(fn, steps, warmup)
+        return {"value": units / t, "ms_per_step": t * 1e3, "cores": max(orc.max_threads(), torch.get_num_threads()), "kind": "port",
+                "sample": sample + " per step"}
 
 
 class CollabStepCfg3(Workload):
@@ -538,8 +800,7 @@ class CollabStepCfg3(Workload):
                             "layer-wise lambda (G=13), batch 16 x 512 tokens, Adam(lr 1e-3) on lambda",
                 "K": self.K, "d": self.d, "batch": self.B, "seq_len": self.L,
                 "l2": "4.5 GB of task vectors per merge / gradient pass exceed L2",
-                "parallelism": f"data-parallel replicas x{self.world} (lambda-gradient all-reduce of G x K floats)"
-                if self.world > 1 else "1 GPU"}
+                "parallelism": "data-parallel replicas, one all-reduce of the G x K lambda-gradient per step (SURVEY.md 8(e))"}
 
     def setup(self):
         import torch.distributed as dist
@@ -648,7 +909,7 @@ class CollabStepCfg3(Workload):
                 "seconds_per_step": t}
 
     def reference_arm(self, steps, warmup):
-        t, cores = self._cpu_time(max(1, min(steps, 3)))
+        t, cores = self._cpu_time(max(1, steps))
         return {"value": 1.0 / t, "ms_per_step": t * 1e3, "cores": cores,
                 "sample": "the step's two merger passes only (lambda merge + lambda-gradient, full d, K=8), OpenMP C oracle port"}
 
@@ -669,8 +930,8 @@ class TiesSharded(TiesCfg2):
         return {"workload": "TIES (density 0.2) of K=8 BLaIR-base models, flat vector sharded d/G per GPU; global trim via "
                             "all-reduced radix histograms; local build + task-wise lambda merge",
                 "K": self.K, "d": self.d, "density": 0.2, "l2": "per-rank inputs (4.5 GB / G) exceed L2 for G <= 8",
-                "parallelism": f"flat dimension sharded x{self.world}, 2 all-reduces of 131 KB + 2 small all-gathers per step"
-                if self.world > 1 else "1 GPU (same code path, no collective)"}
+                "parallelism": "flat dimension sharded d/G per GPU (strong scaling); per select level one all-reduce of "
+                               "K x 2049 int64 + small all-gathers; the same code path without collectives on 1 GPU"}
 
     def setup(self):
         import torch.distributed as dist
@@ -783,8 +1044,8 @@ class DistillStep(Workload):
         return {"workload": "distillation step: 16 samples over 8 domains x 25,000 items, E=768, KD loss (T=2), "
                             "teacher logits device-resident (512 sequences per domain)",
                 "B": self.B, "domains": self.D, "items_per_domain": self.N, "E": self.E,
-                "l2": "item tables (614 MB) exceed L2", "cuda_graph": getattr(self, "graph", None) is not None,
-                "parallelism": f"data-parallel replicas x{self.world}" if self.world > 1 else "1 GPU"}
+                "l2": "item tables (614 MB) exceed L2",
+                "parallelism": "independent replicas (no collective on this path)"}
 
     def setup(self):
         from mergerec_b200.module.distiller import TeacherScores
@@ -878,7 +1139,7 @@ class DistillStep(Workload):
                 "step_GB/s (tables read twice)": 2 * self.bytes_tables / GB / (ms_step * 1e-3)}, "ds_logits_kernel")
 
     def extra(self):
-        return {"loss": None if self.loss is None else float(self.loss)}
+        return {"loss": None if self.loss is None else float(self.loss), "cuda_graph": getattr(self, "graph", None) is not None}
 
     def _cpu_time(self, reps):
         from oracle import oracle as orc
@@ -899,11 +1160,297 @@ class DistillStep(Workload):
                 "sample": "the full step (16 samples, 8 x 25,000 x 768 tables), numpy fp64 oracle port (BLAS threads)", "seconds_per_step": t}
 
     def reference_arm(self, steps, warmup):
-        t, cores = self._cpu_time(max(1, min(steps, 3)))
+        t, cores = self._cpu_time(max(1, steps))
         return {"value": self.B / t, "ms_per_step": t * 1e3, "cores": cores,
                 "sample": "the full step (16 samples, 8 x 25,000 x 768 tables), numpy fp64 oracle port"}
 
 
+class TaskArithCfg1(LambdaMergeK8):
+    """Merger half of BASELINE config 1: task-arithmetic merge of K = 3 BLaIR-base domain models, lambda = 0.3
+    (`ModelMerger.merge("task_vector", 0.3)`, merger.py:71-74 -> task_vector.py:13-34).  Algorithmic bytes per step:
+    (K+2) * d * 4.  The end-to-end arm is the public API itself: host state_dicts -> `ModelMerger` (flatten into HBM) ->
+    merge -> merged flat vector back to the host."""
+
+    name = "task_arith_cfg1"
+    K = 3
+
+    def config(self):
+        return {"workload": "BASELINE config 1 (merger half): task-arithmetic merge of K=3 BLaIR-base (RoBERTa-base, "
+                            "d=124,645,632, P=199) domain models, lambda=0.3",
+                "K": self.K, "d": self.d, "l2": "inputs (2 GB) exceed L2, no flush needed",
+                "parallelism": "single GPU"}
+
+    def setup(self):
+        g = torch.Generator(device=self.device).manual_seed(1234)
+        d, K = self.d, self.K
+        self.base = torch.randn(d, generator=g, device=self.device) * 0.02
+        self.models = [self.base + 1e-3 * torch.randn(d, generator=g, device=self.device) for _ in range(K)]
+        self.w = torch.full((1, K), 0.3, dtype=torch.float32, device=self.device)
+        self.out = torch.empty(d, dtype=torch.float32, device=self.device)
+
+    def step(self):
+        from mergerec_b200 import _lib
+        from mergerec_b200.merger.algorithms._common import merge_axpy
+        merge_axpy(self.base, self.models, self.w, _lib.MR_ORDER_BASE_FIRST, True, out=self.out)
+
+    def setup_e2e(self):
+        from mergerec_b200.merger.layout import FlatLayout
+        layout = FlatLayout.from_shape_dict(self.shapes)
+        self.h_flat = [_pinned(t.cpu()) for t in [self.base] + self.models]
+        self.h_dicts = [layout.views(f) for f in self.h_flat]          # host state_dicts (views of pinned flat buffers)
+        self.h_out = torch.empty(self.d, dtype=torch.float32, pin_memory=True)
+        self.h2d_bytes = (self.K + 1) * self.d * 4
+        self.d2h_bytes = self.d * 4
+        del self.base, self.models
+        torch.cuda.empty_cache()
+
+    def step_e2e(self):
+        from mergerec_b200.merger import ModelMerger
+        merger = ModelMerger(self.h_dicts[1:], self.h_dicts[0], align_key_order=False)
+        merged = merger.merge("task_vector", 0.3)
+        first = next(iter(merged.values()))
+        flat = first.reshape(-1)
+        # the merged state_dict's tensors are views of one flat device vector in layout order: copy it back whole
+        self.h_out.copy_(torch.as_strided(flat, (self.d,), (1,), first.storage_offset()), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def teardown_e2e(self):
+        g = torch.Generator(device=self.device).manual_seed(1234)
+        d, K = self.d, self.K
+        self.base = torch.randn(d, generator=g, device=self.device) * 0.02
+        self.models = [self.base + 1e-3 * torch.randn(d, generator=g, device=self.device) for _ in range(K)]
+        del self.h_flat, self.h_dicts
+
+    def roofline(self, peaks):
+        from bench import event_time_ms
+        ms = event_time_ms(self.step, 20)
+        achieved = self.bytes_per_step / GB / (ms * 1e-3)
+        return _with_traffic({"bound": "hbm", "kernel": "mr::merge_kernel<3, BASE_FIRST, src_is_model, vec4>", "achieved": achieved,
+                "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
+                "algorithmic_bytes_per_launch": self.bytes_per_step}, "merge_kernel")
+
+    # -- CPU arms at FULL size: the unmodified ModelMerger.merge("task_vector", 0.3) (reference) / oracle port
+    def _host_models(self):
+        base, models = synth.make_state_dicts(self.shapes, self.K, seed=0, sigma=1e-3)
+        return base, models
+
+    def _reference_step_fn(self):
+        if reference_package() is None:
+            return None
+        from rec_retrieval.merger import ModelMerger as RefMerger
+        base, models = self._host_models()
+        t0 = time.perf_counter()
+        merger = RefMerger([{k: torch.from_numpy(v) for k, v in m.items()} for m in models],
+                           {k: torch.from_numpy(v) for k, v in base.items()})
+        t_flat = time.perf_counter() - t0
+        del base, models
+        return (lambda: merger.merge("task_vector", 0.3)), self.bytes_per_step, (
+            f"UNMODIFIED reference ModelMerger.merge('task_vector', 0.3) at the full size (K={self.K}, d={self.d}); the "
+            f"constructor's flatten_model x{self.K + 1} took {t_flat:.2f} s and is not in the step")
+
+    def _port_step_fn(self):
+        from oracle import oracle as orc
+        rng = np.random.Generator(np.random.PCG64(7))
+        base = rng.standard_normal(self.d, dtype=np.float32) * np.float32(0.02)
+        models = [base + np.float32(1e-3) * rng.standard_normal(self.d, dtype=np.float32) for _ in range(self.K)]
+        return (lambda: orc.merge_task_vector(base, models, [0.3] * self.K)), self.bytes_per_step, (
+            f"full size (K={self.K}, d={self.d}) merge_task_vector, OpenMP C oracle port")
+
+    cpu_baseline = TiesCfg2.cpu_baseline
+    reference_arm = TiesCfg2.reference_arm
+
+
+class MergeCfg4(TiesCfg2):
+    """Merger half of BASELINE config 4: K = 8 Recformer-large (Longformer-large, d = 433,610,754, P = 535) domain models.
+    One step = task-arithmetic merge from the models (A1) + `get_ties_vectors(density 0.2)` (A6-A8) + task-wise lambda
+    merge of the TIES vectors (A3).  Algorithmic bytes per step: (K+2)*d*4 + (2K+1)*d*4 + (K+2)*d*4 = 64.2 GB."""
+
+    name = "merge_cfg4"
+    launches_per_step = 13
+    e2e_steps_cap = 2
+
+    def __init__(self, rank, world, device):
+        Workload.__init__(self, rank, world, device)
+        self.shapes = synth.recformer_shapes()
+        self.d = synth.total_numel(self.shapes)
+        self.bytes_arith = (self.K + 2) * self.d * 4
+        self.bytes_build = (2 * self.K + 1) * self.d * 4
+        self.bytes_merge = (self.K + 2) * self.d * 4
+        self.bytes_per_step = self.bytes_arith + self.bytes_build + self.bytes_merge
+
+    def config(self):
+        return {"workload": "BASELINE config 4 (merger half): K=8 Recformer-large (Longformer-large, d=433,610,754, P=535; flat "
+                            "offsets after position_ids are 2 mod 4): task-arithmetic merge + TIES vectors (density 0.2, global "
+                            "trim, election, disjoint mean) + task-wise lambda merge",
+                "K": self.K, "d": self.d, "density": 0.2, "l2": "inputs (15.6 GB) exceed L2, no flush needed",
+                "select_status": "checked on the host after the timed loop (stream-ordered step)",
+                "parallelism": "single GPU"}
+
+    def setup(self):
+        from mergerec_b200.merger.layout import alloc_rows
+        g = torch.Generator(device=self.device).manual_seed(4321)
+        d, K = self.d, self.K
+        self.base = torch.randn(d, generator=g, device=self.device) * 0.02
+        self.models = []
+        for _ in range(K):
+            m = torch.randn(d, generator=g, device=self.device)
+            m.mul_(1e-3).add_(self.base)
+            self.models.append(m)
+        self.w_arith = torch.full((1, K), 0.3, dtype=torch.float32, device=self.device)
+        rng = np.random.Generator(np.random.PCG64(5))
+        self.w = torch.from_numpy(rng.uniform(0.1, 0.5, size=(1, K)).astype(np.float32)).to(self.device)
+        self.out = torch.empty(d, dtype=torch.float32, device=self.device)
+        self.out_arith = torch.empty(d, dtype=torch.float32, device=self.device)
+        self.That = alloc_rows(K, d, self.device)
+        self.Trows = list(self.That.unbind(0))
+        self.seg_end = self.seg_group = None
+        self._status = None
+        self.graph = None
+
+    def _arith(self):
+        from mergerec_b200 import _lib
+        from mergerec_b200.merger.algorithms._common import merge_axpy
+        merge_axpy(self.base, self.models, self.w_arith, _lib.MR_ORDER_BASE_FIRST, True, out=self.out_arith)
+
+    def _eager_step(self, defer=True):
+        self._arith()
+        TiesCfg2._eager_step(self, defer)
+
+    def step(self):
+        self._eager_step()
+
+    def step_fused(self):
+        from mergerec_b200.merger.algorithms import ties as T
+        T.merge_ties_lambda(self.base, self.models, 0.2, self.w, out=self.out)
+
+    def setup_e2e(self):
+        self.h_base = _pinned(self.base.cpu())
+        self.h_models = [_pinned(m.cpu()) for m in self.models]
+        self.h_out = torch.empty(self.d, dtype=torch.float32, pin_memory=True)
+        self.h_out_arith = torch.empty(self.d, dtype=torch.float32, pin_memory=True)
+        self.h2d_bytes = (self.K + 1) * self.d * 4
+        self.d2h_bytes = 2 * self.d * 4
+
+    def step_e2e(self):
+        self.base.copy_(self.h_base, non_blocking=True)
+        for m, h in zip(self.models, self.h_models):
+            m.copy_(h, non_blocking=True)
+        self._eager_step(defer=False)
+        self.h_out_arith.copy_(self.out_arith, non_blocking=True)
+        self.h_out.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def teardown_e2e(self):
+        del self.h_base, self.h_models, self.h_out, self.h_out_arith
+
+    def roofline(self, peaks):
+        from bench import event_time_ms
+        from mergerec_b200 import _lib
+        from mergerec_b200.merger.algorithms import ties as T
+        cut = T.ties_select(self.base, self.models, 0.2)
+        K, d = self.K, self.d
+        ms_build = event_time_ms(lambda: T._build(self.base, self.models, cut, _lib.MR_TIES_VECTORS, out=self.That, ldo=self.That.stride(0)), 5)
+        ms_select = event_time_ms(lambda: T.select_kth_largest(self.base, self.models, int(0.2 * d), None, defer_status=True), 5)
+        ms_merge = event_time_ms(self._merge_only, 5)
+        ms_arith = event_time_ms(self._arith, 5)
+        ms_fused = event_time_ms(self.step_fused, 3)
+        ach = self.bytes_build / GB / (ms_build * 1e-3)
+        sel_bytes = (K + 1) * d * 4
+        return {"bound": "hbm", "kernel": "mr::ties_build_kernel<8, VECTORS, vec4> at d=433,610,754 (get_ties_vectors build pass)",
+                "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms_build,
+                "algorithmic_bytes_per_launch": self.bytes_build,
+                "other_kernels": {
+                    "task-arithmetic merge from models (merge_kernel, A1)": {"ms": ms_arith, "GB/s": self.bytes_arith / GB / (ms_arith * 1e-3), "bytes": self.bytes_arith},
+                    "ties_select (sample + 1 full pass + finish)": {"ms": ms_select, "GB/s": sel_bytes / GB / (ms_select * 1e-3), "bytes": sel_bytes},
+                    "task-wise lambda merge of That (merge_kernel, A3)": {"ms": ms_merge, "GB/s": self.bytes_merge / GB / (ms_merge * 1e-3), "bytes": self.bytes_merge},
+                    "fused select + build + merge without materialising That (merge_ties_lambda)": {"ms": ms_fused, "GB/s": self.bytes_merge / GB / (ms_fused * 1e-3), "bytes": self.bytes_merge},
+                }}
+
+    def extra(self):
+        return {}
+
+    # -- CPU arms on bounded samples (the full size needs ~45 GB of host temporaries and minutes per step on the CPU)
+    def _port_step_fn(self):
+        from oracle import oracle as orc
+        frac = 8
+        d = self.d // frac
+        rng = np.random.Generator(np.random.PCG64(7))
+        base = rng.standard_normal(d, dtype=np.float32) * np.float32(0.02)
+        models = [base + np.float32(1e-3) * rng.standard_normal(d, dtype=np.float32) for _ in range(self.K)]
+        w = rng.uniform(0.1, 0.5, size=(1, self.K)).astype(np.float32)
+
+        def step():
+            orc.merge_task_vector(base, models, [0.3] * self.K)
+            That = orc.ties_vectors(base, models, 0.2)
+            orc.lambda_merge(base, That, w)
+        nbytes = ((self.K + 2) + (2 * self.K + 1) + (self.K + 2)) * d * 4
+        return step, nbytes, (f"a flat prefix of d/{frac} = {d} elements, K={self.K}: merge_task_vector + ties_vectors + task-wise "
+                              "lambda merge, OpenMP C oracle port")
+
+    def _reference_step_fn(self):
+        if reference_package() is None:
+            return None
+        from rec_retrieval.merger.algorithms.task_vector import merge_task_vector
+        from rec_retrieval.merger.algorithms.ties import get_ties_vectors
+        from rec_retrieval.merger.weight_learning.module.task_wise import TaskVectorMergingModuleTaskWise
+        shapes = synth.recformer_shapes(hidden=64, ffn=256)
+        d = synth.total_numel(shapes)
+        g = torch.Generator().manual_seed(7)
+        base = torch.randn(d, generator=g) * 0.02
+        models = [base + 1e-3 * torch.randn(d, generator=g) for _ in range(self.K)]
+        shape_dict = {k: torch.Size(v) for k, v in shapes.items()}
+
+        class _NoModel(torch.nn.Module):
+            def forward(self, x):
+                return x
+
+        def step():
+            merge_task_vector(base, models, [0.3] * self.K)
+            That = get_ties_vectors(base, models, 0.2)
+            mod = TaskVectorMergingModuleTaskWise(base, That, _NoModel(), shape_dict, disable_softmax=True)
+            with torch.no_grad():
+                mod._merge_task_vectors()
+        nbytes = ((self.K + 2) + (2 * self.K + 1) + (self.K + 2)) * d * 4
+        return step, nbytes, ("UNMODIFIED reference (merge_task_vector + get_ties_vectors + TaskVectorMergingModuleTaskWise."
+                              f"_merge_task_vectors) on a Recformer-shaped slice: 24 layers, hidden 64, P=535, d={d}, K={self.K}")
+
+
+class EvalCfg1(EvalCatalog):
+    """BASELINE config 1: Recall@10 / NDCG@10 of 256 query sequences against a 20,000-item catalog, E = 768 (the
+    reference's own CPU-runnable case), with the K = 3 task-arithmetic merge carried as the `merger` object.  The CPU arms
+    run at the FULL size of the configuration."""
+
+    name = "cfg1"
+    label = "BASELINE config 1"
+    sizes = dict(Q=256, N=20_000, E=768, K=10)
+    ks_low = 10
+    cpu_sample = dict(Q=256)
+    accuracy_rows = 256
+    e2e_steps_cap = 10
+
+    def companion(self):
+        return TaskArithCfg1 if self.world == 1 else None
+
+
+class EvalCfg4(EvalCatalog):
+    """BASELINE config 4: evaluation over the 8-domain union catalog -- 200,000 items, E = 1024 (Recformer-large),
+    Q = 32,768 query sequences, top-50 (the reference default max(ks), configs/base.py:46-48) -- with the Recformer-large
+    K = 8 merge carried as the `merger` object."""
+
+    name = "cfg4"
+    label = "BASELINE config 4"
+    sizes = dict(Q=32768, N=200_000, E=1024, K=50)
+    ks_low = 10
+    cpu_sample = dict(Q=512)
+    accuracy_rows = 2048
+
+    def companion(self):
+        return MergeCfg4 if self.world == 1 else None
+
+
 WORKLOADS = {LambdaMergeK8.name: LambdaMergeK8, TiesCfg2.name: TiesCfg2, EvalCatalog.name: EvalCatalog,
-             CollabStepCfg3.name: CollabStepCfg3, DistillStep.name: DistillStep, TiesSharded.name: TiesSharded}
-DEFAULT_WORKLOAD = TiesCfg2.name
+             CollabStepCfg3.name: CollabStepCfg3, DistillStep.name: DistillStep, TiesSharded.name: TiesSharded,
+             TaskArithCfg1.name: TaskArithCfg1, MergeCfg4.name: MergeCfg4, EvalCfg1.name: EvalCfg1, EvalCfg4.name: EvalCfg4}
+DEFAULT_WORKLOAD = EvalCatalog.name

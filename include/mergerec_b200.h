@@ -158,6 +158,13 @@ int mr_topk_rows(const float* scores, int64_t Q, int64_t N, int64_t ld, int K, i
 int mr_topk_merge(const float* vals, const int32_t* ids, int L, int64_t Q, int K_in, int K_out, float* out_val,
                   int32_t* out_id, mr_stream_t stream);
 
+/* The same merge over the sharded evaluator's exchange buffer: packed = dev L blocks of (2, Q, K_in) 32-bit words,
+ * block l = rank l's list with plane 0 the fp32 scores and plane 1 the int32 global ids -- what ONE
+ * ncclAllGather of every rank's (2, Q, K_in) buffer leaves behind (no reference
+ * counterpart, the reference is single-GPU).  L * K_in <= 8192. */
+int mr_topk_merge_packed(const void* packed, int L, int64_t Q, int K_in, int K_out, float* out_val, int32_t* out_id,
+                         mr_stream_t stream);
+
 /* rank[q] = position of labels[q] in ids[q, :K], or -1          ref: evaluator/metrics.py:51-59, 79-84 */
 int mr_label_rank(const int32_t* ids, int64_t Q, int K, const int64_t* labels, int32_t* rank, mr_stream_t stream);
 

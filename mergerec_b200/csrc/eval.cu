@@ -91,10 +91,11 @@ topk_rows_kernel(const float* __restrict__ scores, int64_t Q, int64_t N, int64_t
 }
 
 // ---- merge L top-K lists per row (the multi-GPU / multi-split exchange step) -----------------------------------
-// vals / ids: (L, Q, K_in); entries with id < 0 are empty.  Output (Q, K_out) sorted by (score desc, id asc).
+// vals / ids: L lists of (Q, K_in), list l starting `list_stride` elements after list l - 1; entries with id < 0 are
+// empty.  Output (Q, K_out) sorted by (score desc, id asc).
 __global__ void __launch_bounds__(256)
-topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ ids, int L, int64_t Q, int K_in, int K_out,
-                  int NP, float* __restrict__ out_val, int32_t* __restrict__ out_id) {
+topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ ids, int64_t list_stride, int L, int64_t Q,
+                  int K_in, int K_out, int NP, float* __restrict__ out_val, int32_t* __restrict__ out_id) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* s_keys = reinterpret_cast<u64*>(smem_raw);
     for (int64_t q = blockIdx.x; q < Q; q += gridDim.x) {
@@ -103,7 +104,7 @@ topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ id
             u64 key = 0;
             if (i < total) {
                 const int l = i / K_in, e = i - l * K_in;
-                const int64_t src = ((int64_t)l * Q + q) * K_in + e;
+                const int64_t src = (int64_t)l * list_stride + q * K_in + e;
                 const int32_t id = ids[src];
                 if (id >= 0) key = topk_key(vals[src], (uint32_t)id);
             }
@@ -224,23 +225,39 @@ extern "C" int mr_topk_rows(const float* scores, int64_t Q, int64_t N, int64_t l
     return MR_OK;
 }
 
-extern "C" int mr_topk_merge(const float* vals, const int32_t* ids, int L, int64_t Q, int K_in, int K_out,
-                             float* out_val, int32_t* out_id, mr_stream_t stream) {
+static int topk_merge_launch(const float* vals, const int32_t* ids, int64_t list_stride, int L, int64_t Q, int K_in,
+                             int K_out, float* out_val, int32_t* out_id, mr_stream_t stream, const char* who) {
     using namespace mr;
-    MR_REQUIRE(L >= 1 && Q >= 0 && K_in >= 1 && K_out >= 1, "mr_topk_merge: need L, K_in, K_out >= 1 and Q >= 0");
-    MR_REQUIRE(K_out <= MR_MAX_TOPK, "mr_topk_merge: K_out=%d exceeds %d", K_out, MR_MAX_TOPK);
+    MR_REQUIRE(L >= 1 && Q >= 0 && K_in >= 1 && K_out >= 1, "%s: need L, K_in, K_out >= 1 and Q >= 0", who);
+    MR_REQUIRE(K_out <= MR_MAX_TOPK, "%s: K_out=%d exceeds %d", who, K_out, MR_MAX_TOPK);
     int NP = 1;
     while (NP < L * K_in) NP <<= 1;
-    MR_REQUIRE(NP <= 8192, "mr_topk_merge: L*K_in=%d candidates per row exceed 8192", L * K_in);
+    MR_REQUIRE(NP <= 8192, "%s: L*K_in=%d candidates per row exceed 8192", who, L * K_in);
     if (Q == 0) return MR_OK;
-    MR_REQUIRE(vals && ids && out_val && out_id, "mr_topk_merge: null pointer");
+    MR_REQUIRE(vals && ids && out_val && out_id, "%s: null pointer", who);
     const size_t smem = (size_t)NP * 8;
     if (smem > 48 * 1024) cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t cap = (int64_t)sm_count() * 8;
     const unsigned blocks = (unsigned)(Q < cap ? Q : cap);
-    topk_merge_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(vals, ids, L, Q, K_in, K_out, NP, out_val, out_id);
-    MR_CUDA_LAUNCH_CHECK("mr_topk_merge");
+    topk_merge_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(vals, ids, list_stride, L, Q, K_in, K_out, NP, out_val, out_id);
+    MR_CUDA_LAUNCH_CHECK(who);
     return MR_OK;
+}
+
+extern "C" int mr_topk_merge(const float* vals, const int32_t* ids, int L, int64_t Q, int K_in, int K_out,
+                             float* out_val, int32_t* out_id, mr_stream_t stream) {
+    return topk_merge_launch(vals, ids, Q * (int64_t)K_in, L, Q, K_in, K_out, out_val, out_id, stream, "mr_topk_merge");
+}
+
+// Same merge over the exchange buffer of the sharded evaluator: L blocks of (2, Q, K_in) 32-bit words, block l = one
+// rank's list -- plane 0 the fp32 scores, plane 1 the int32 global ids -- exactly what ONE all-gather of every rank's
+// (2, Q, K_in) buffer produces.
+extern "C" int mr_topk_merge_packed(const void* packed, int L, int64_t Q, int K_in, int K_out, float* out_val,
+                                    int32_t* out_id, mr_stream_t stream) {
+    const float* vals = reinterpret_cast<const float*>(packed);
+    const int32_t* ids = packed ? reinterpret_cast<const int32_t*>(packed) + Q * (int64_t)K_in : nullptr;
+    return topk_merge_launch(vals, ids, 2 * Q * (int64_t)K_in, L, Q, K_in, K_out, out_val, out_id, stream,
+                             "mr_topk_merge_packed");
 }
 
 extern "C" int mr_label_rank(const int32_t* ids, int64_t Q, int K, const int64_t* labels, int32_t* rank,

@@ -18,8 +18,8 @@ import torch
 from .. import _lib
 from .enums import MetricType
 from .metrics import label_rank
-from .sharded import (MAX_FUSED_TOPK, MR_SCORE_BF16, MR_SCORE_TF32X3, ShardedItemTable, exchange_topk, split_tf32,
-                      to_bf16)
+from .sharded import (MAX_FUSED_TOPK, MR_SCORE_BF16, MR_SCORE_TF32X3, ShardedItemTable, exchange_packed,
+                      new_packed_list, split_tf32, to_bf16)
 
 MAX_TOPK = 1024
 
@@ -49,23 +49,44 @@ def topk_rows(scores: torch.Tensor, k: int, id_base: int = 0) -> Tuple[torch.Ten
 
 
 def score_topk(user_hi: torch.Tensor, user_lo: Optional[torch.Tensor], table: ShardedItemTable, k: int,
-               mode: int = MR_SCORE_TF32X3) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Local fused scoring + top-k of pre-split queries against this rank's shard (`mr_score_topk`)."""
+               mode: int = MR_SCORE_TF32X3, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Local fused scoring + top-k of pre-split queries against this rank's shard (`mr_score_topk`).  `out` =
+    (values (Q, k) fp32, ids (Q, k) int32) to write into (e.g. the planes of the exchange buffer)."""
     dev = _lib.require_cuda()
     lib = _lib.load()
     Q, E = user_hi.shape
     if E != table.dim:
         raise ValueError(f"embedding dims differ: queries {E}, items {table.dim}")
-    out_v = torch.empty((Q, k), dtype=torch.float32, device=dev)
-    out_i = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    if out is None:
+        out_v = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    else:
+        out_v, out_i = out
     ws_bytes = int(lib.mr_score_topk_workspace_bytes(Q, table.n_local, E, k))
     if ws_bytes < 0:
         _lib.check(ws_bytes, "mr_score_topk_workspace_bytes")
-    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    ws = table.workspace(ws_bytes)
     _lib.check(lib.mr_score_topk(_lib.dptr(user_hi), _lib.dptr(user_lo), Q, _lib.dptr(table.hi), _lib.dptr(table.lo),
                                  table.n_local, E, k, table.id_base, mode, _lib.dptr(out_v), _lib.dptr(out_i),
                                  _lib.dptr(ws), ws_bytes, _lib.stream_handle()), "mr_score_topk")
     return out_v, out_i
+
+
+class PreparedQueries:
+    """Query embeddings in the operand format of the scoring kernel ((hi, lo) TF32 split, or bf16), prepared once and
+    reusable against any number of item tables / evaluations (`Evaluator.prepare_queries`)."""
+
+    def __init__(self, user_emb: torch.Tensor, normalize: bool = False, bf16: bool = False):
+        dev = _lib.require_cuda()
+        users = user_emb.to(device=dev, dtype=torch.float32)
+        if users.dim() != 2:
+            raise ValueError("query embeddings must be (Q, E)")
+        if normalize:
+            users = torch.nn.functional.normalize(users, p=2, dim=-1)   # module/recommender/module.py:74-77
+        self.bf16 = bool(bf16)
+        self.hi, self.lo = (to_bf16(users), None) if self.bf16 else split_tf32(users)
+        self.shape = tuple(users.shape)
 
 
 class Evaluator:
@@ -87,7 +108,7 @@ class Evaluator:
         return self.metrics_from_ids(ids, labels, metric_prefix)
 
     # ------------------------------------------------------------------ fused additions
-    def topk_embeddings(self, user_emb: torch.Tensor, item_emb: Union[torch.Tensor, ShardedItemTable],
+    def topk_embeddings(self, user_emb: Union[torch.Tensor, PreparedQueries], item_emb: Union[torch.Tensor, ShardedItemTable],
                         k: Optional[int] = None, normalize: bool = False,
                         mode: int = MR_SCORE_TF32X3) -> Tuple[torch.Tensor, torch.Tensor]:
         """Top-k (values fp32, global ids int32), both (Q, k), of ``user_emb @ item_emb.T`` without the matrix.
@@ -101,23 +122,30 @@ class Evaluator:
         k = self._max_k if k is None else k
         if k > MAX_FUSED_TOPK:
             raise ValueError(f"fused top-k supports k <= {MAX_FUSED_TOPK}")
-        dev = _lib.require_cuda()
+        _lib.require_cuda()
         table = item_emb if isinstance(item_emb, ShardedItemTable) else ShardedItemTable(
             item_emb, normalize=normalize, bf16=(mode == MR_SCORE_BF16))
         if table.bf16 != (mode == MR_SCORE_BF16):
             raise ValueError("the item table was prepared for a different scoring mode (bf16 table <-> MR_SCORE_BF16)")
         if k > table.n_total:
             raise RuntimeError(f"selected index k out of range (k={k}, N={table.n_total})")
-        users = user_emb.to(device=dev, dtype=torch.float32)
-        if normalize:
-            users = torch.nn.functional.normalize(users, p=2, dim=-1)
-        u_hi, u_lo = (to_bf16(users), None) if table.bf16 else split_tf32(users)
-        vals, ids = score_topk(u_hi, u_lo, table, k, mode)
-        if table.group is not None:
-            vals, ids = exchange_topk(vals, ids, k, table.group)
-        return vals, ids
+        queries = user_emb if isinstance(user_emb, PreparedQueries) else PreparedQueries(user_emb, normalize, table.bf16)
+        if queries.bf16 != table.bf16:
+            raise ValueError("the queries were prepared for a different scoring mode than the item table")
+        if table.group is None or table.world == 1:
+            return score_topk(queries.hi, queries.lo, table, k, mode)
+        # sharded: the kernel writes this rank's list into the buffer that the single all-gather sends
+        local, loc_v, loc_i = new_packed_list(queries.shape[0], k, queries.hi.device)
+        score_topk(queries.hi, queries.lo, table, k, mode, out=(loc_v, loc_i))
+        return exchange_packed(local, k, table.group, gathered=table.gather_buffer(queries.shape[0], k))
 
-    def evaluate_embeddings(self, user_emb: torch.Tensor, item_emb: Union[torch.Tensor, ShardedItemTable],
+    @staticmethod
+    def prepare_queries(user_emb: torch.Tensor, normalize: bool = False, mode: int = MR_SCORE_TF32X3) -> PreparedQueries:
+        """Split / convert the query embeddings once; pass the result as `user_emb` to `topk_embeddings` /
+        `evaluate_embeddings` as often as needed (several catalogs, several ks, repeated evaluation)."""
+        return PreparedQueries(user_emb, normalize, mode == MR_SCORE_BF16)
+
+    def evaluate_embeddings(self, user_emb: Union[torch.Tensor, PreparedQueries], item_emb: Union[torch.Tensor, ShardedItemTable],
                             labels: torch.Tensor, metric_prefix: str = "", normalize: bool = False,
                             mode: int = MR_SCORE_TF32X3) -> Dict[str, float]:
         _, ids = self.topk_embeddings(user_emb, item_emb, self._max_k, normalize, mode)

@@ -42,15 +42,26 @@ def label_rank(ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
 
 
 def recall_from_ranks(ranks: np.ndarray, k: int) -> float:
-    vals: List[float] = np.where((ranks >= 0) & (ranks < k), 1.0, 0.0).tolist()
-    return sum(vals) / len(vals) if vals else 0.0
+    """`sum([1.0 | 0.0 per row]) / len` (metrics.py:49-61).  The sum of n ones is the exact float n, whatever the
+    summation order, so the hit count gives the same bits as the reference's row loop."""
+    n = int(ranks.shape[0])
+    if n == 0:
+        return 0.0
+    hits = int(np.count_nonzero((ranks >= 0) & (ranks < k)))
+    return float(hits) / n if hits else 0 / n
 
 
 def ndcg_from_ranks(ranks: np.ndarray, k: int) -> float:
+    """`sum([gain | 0.0 per row]) / len` in row order (metrics.py:77-88).  The builtin `sum` is kept (CPython >= 3.12
+    uses compensated summation for floats, which the reference inherits); rows that miss contribute 0.0, which
+    changes neither the running sum nor its compensation term, so only the hit rows are summed -- same bits."""
+    n = int(ranks.shape[0])
+    if n == 0:
+        return 0.0
     hit = (ranks >= 0) & (ranks < k)
     table = _gain_table(max(int(k), 1))
-    vals: List[float] = np.where(hit, table[np.where(hit, ranks, 0)], 0.0).tolist()
-    return sum(vals) / len(vals) if vals else 0.0
+    vals: List[float] = table[ranks[hit]].tolist()
+    return sum(vals) / n
 
 
 class BaseMetric:

@@ -72,6 +72,10 @@ class ShardedItemTable:
     id_base    global id of local row 0.
     n_total    catalog size over all ranks (defaults to n_local: a single-GPU table).
     group      torch.distributed process group holding the other shards (None = no exchange).
+
+    The handle also keeps the scratch the scoring kernel needs (`workspace`: candidate buffers and per-split lists,
+    sized by `mr_score_topk_workspace_bytes`) and the all-gather landing buffer, so repeated evaluations against the
+    same table allocate nothing.
     """
 
     def __init__(self, items: torch.Tensor, id_base: int = 0, n_total: Optional[int] = None, group=None,
@@ -91,6 +95,20 @@ class ShardedItemTable:
         self.id_base = int(id_base)
         self.n_total = int(n_total if n_total is not None else self.n_local)
         self.group = group
+        self._ws: Optional[torch.Tensor] = None
+        self._gathered: Optional[torch.Tensor] = None
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        """Scratch of at least `nbytes` on the table's device, kept between calls (grown when needed)."""
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.hi.device)
+        return self._ws
+
+    def gather_buffer(self, Q: int, k: int) -> torch.Tensor:
+        shape = (self.world, 2, Q, k)
+        if self._gathered is None or tuple(self._gathered.shape) != shape:
+            self._gathered = torch.empty(shape, dtype=torch.int32, device=self.hi.device)
+        return self._gathered
 
     @classmethod
     def from_full(cls, items: torch.Tensor, group=None, normalize: bool = False, bf16: bool = False) -> "ShardedItemTable":
@@ -110,18 +128,50 @@ class ShardedItemTable:
         return dist.get_world_size(self.group)
 
 
-def exchange_topk(local_vals: torch.Tensor, local_ids: torch.Tensor, k: int, group,
-                  merge: Callable = topk_merge) -> Tuple[torch.Tensor, torch.Tensor]:
-    """The exchange step: allgather every rank's (Q, k) list and merge.  `merge` is injectable so the host logic
-    can be exercised with the gloo backend on CPU tensors (tests); the product path uses `mr_topk_merge`."""
+def topk_merge_packed(packed: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge the exchange buffer (L, 2, Q, K_in) int32 -- plane 0 the fp32 score bits, plane 1 the global ids of
+    rank l's list -- into (Q, k_out) (`mr_topk_merge_packed`)."""
+    dev = _lib.require_cuda()
+    lib = _lib.load()
+    if packed.dtype != torch.int32 or packed.dim() != 4 or packed.shape[1] != 2 or not packed.is_contiguous():
+        raise ValueError("expected a contiguous (L, 2, Q, K) int32 exchange buffer")
+    L, _, Q, K_in = packed.shape
+    out_v = torch.empty((Q, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((Q, k_out), dtype=torch.int32, device=dev)
+    _lib.check(lib.mr_topk_merge_packed(_lib.dptr(packed), L, Q, K_in, k_out, _lib.dptr(out_v), _lib.dptr(out_i),
+                                        _lib.stream_handle()), "mr_topk_merge_packed")
+    return out_v, out_i
+
+
+def new_packed_list(Q: int, k: int, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """One (2, Q, k) int32 buffer and its two planes viewed as the (values fp32, ids int32) outputs of the scoring
+    kernel: the kernel writes its result straight into the buffer the all-gather sends."""
+    buf = torch.empty((2, Q, k), dtype=torch.int32, device=device)
+    return buf, buf[0].view(torch.float32), buf[1]
+
+
+def exchange_packed(local: torch.Tensor, k: int, group, merge: Optional[Callable] = None,
+                    gathered: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The exchange step: ONE all-gather (NCCL over NVLink) of every rank's (2, Q, k) list buffer, then the merge.
+    `merge(vals (L, Q, k), ids (L, Q, k), k)` is injectable so the host logic can run with the gloo backend on CPU
+    tensors (tests); the product path (merge=None) uses `mr_topk_merge_packed` on the gathered buffer as it is."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    if world == 1:
+    _, Q, kk = local.shape
+    if gathered is None or gathered.shape != (world, 2, Q, kk) or gathered.device != local.device:
+        gathered = torch.empty((world, 2, Q, kk), dtype=torch.int32, device=local.device)
+    # concatenated form (world * 2 * Q, k): accepted by both the nccl and the gloo backends
+    dist.all_gather_into_tensor(gathered.view(world * 2 * Q, kk), local.view(2 * Q, kk), group=group)
+    if merge is None:
+        return topk_merge_packed(gathered, k)
+    return merge(gathered[:, 0].contiguous().view(torch.float32), gathered[:, 1].contiguous(), k)
+
+
+def exchange_topk(local_vals: torch.Tensor, local_ids: torch.Tensor, k: int, group,
+                  merge: Optional[Callable] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`exchange_packed` for lists held as two separate (Q, k) tensors (packs them with one copy)."""
+    import torch.distributed as dist
+    if dist.get_world_size(group) == 1:
         return local_vals, local_ids
-    Q = local_vals.shape[0]
-    all_v = torch.empty((world, Q, k), dtype=local_vals.dtype, device=local_vals.device)
-    all_i = torch.empty((world, Q, k), dtype=local_ids.dtype, device=local_ids.device)
-    # concatenated form (world * Q, k): accepted by both the nccl and the gloo backends
-    dist.all_gather_into_tensor(all_v.view(world * Q, k), local_vals.contiguous(), group=group)
-    dist.all_gather_into_tensor(all_i.view(world * Q, k), local_ids.contiguous(), group=group)
-    return merge(all_v, all_i, k)
+    local = torch.stack([local_vals.contiguous().view(torch.int32), local_ids.contiguous().to(torch.int32)])
+    return exchange_packed(local, k, group, merge)

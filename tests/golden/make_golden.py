@@ -170,6 +170,34 @@ def gen_evaluator():
     save("evaluator", **out)
 
 
+def gen_evaluator_cfg4():
+    """BASELINE config 4's evaluator shape: the reference Evaluator on its own CPU scores; canonical ids from a stable
+    descending sort of those scores, metric floats from the reference's Recall / NDCG objects fed the canonical ids."""
+    out = {}
+    for case in gc.EVAL_CFG4_CASES:
+        users, items, labels = synth.make_catalog(case["Q"], case["N"], case["E"], kind=case["kind"], seed=case["seed"])
+        scores = T(users) @ T(items).T
+        tl = T(labels)
+        kmax = max(case["ks"])
+        res = Evaluator(case["metrics"], case["ks"])(scores, tl, metric_prefix=case["prefix"])
+        out[f"{case['name']}/raw_keys"] = np.array(list(res.keys()))
+        out[f"{case['name']}/raw_values"] = np.asarray(list(res.values()), np.float64)
+        order = torch.sort(scores, dim=1, descending=True, stable=True)
+        canon = order.indices[:, :kmax]
+        out[f"{case['name']}/canon_topk"] = canon.numpy().astype(np.int32)
+        out[f"{case['name']}/canon_vals"] = order.values[:, :kmax].numpy()
+        raw = torch.topk(scores, kmax, dim=1)
+        assert torch.equal(raw.values, order.values[:, :kmax])       # same score multiset per row
+        vals = {}
+        for m in case["metrics"]:
+            for k in case["ks"]:
+                obj = {"RECALL": Recall, "NDCG": NDCG}[m](k)
+                vals[case["prefix"] + obj.name] = obj(y_true=tl, y_pred=canon)
+        out[f"{case['name']}/canon_keys"] = np.array(list(vals.keys()))
+        out[f"{case['name']}/canon_values"] = np.asarray(list(vals.values()), np.float64)
+    save("evaluator_cfg4", **out)
+
+
 def gen_evaluator_bf16():
     """The reference's default bf16-mixed pipeline on grid catalogs: scores = (U.bf16 @ I.bf16.T) as torch computes them
     (bf16 result), canonical ids = stable descending sort, metrics from the reference's own Recall / NDCG objects."""
@@ -382,7 +410,7 @@ if __name__ == "__main__":
     print("torch", torch.__version__, "cpu capability", torch.backends.cpu.get_cpu_capability())
     only = set(sys.argv[1:])   # e.g. `make_golden.py lns` regenerates one file
     for name, fn in [("merge_flat", gen_merge_flat), ("model_merger", gen_model_merger), ("lambda_merge", gen_lambda),
-                     ("ties", gen_ties), ("lns", gen_lns), ("evaluator", gen_evaluator), ("evaluator_bf16", gen_evaluator_bf16),
+                     ("ties", gen_ties), ("lns", gen_lns), ("evaluator", gen_evaluator), ("evaluator_bf16", gen_evaluator_bf16), ("evaluator_cfg4", gen_evaluator_cfg4),
                      ("module_e2e", gen_module_e2e), ("distill", gen_distill), ("pcb", gen_pcb), ("dare", gen_dare), ("collab_distill", gen_collab_distill)]:
         if not only or name in only:
             fn()

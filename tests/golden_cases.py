@@ -50,6 +50,11 @@ EVAL_CASES = [
     dict(name="grid_top100", kind="grid", Q=96, N=3000, E=64, seed=53, metrics=["RECALL", "NDCG"], ks=[1, 10, 100], prefix="val_"),
 ]
 
+# BASELINE config 4's evaluator shape (200,000-item union catalog, E = 1024, top-50) on a slice of the queries.
+EVAL_CFG4_CASES = [
+    dict(name="grid_cfg4_q64", kind="grid", Q=64, N=200_000, E=1024, seed=54, metrics=["NDCG", "RECALL"], ks=[10, 50], prefix=""),
+]
+
 MODULE_CASES = [
     dict(name="tv_taskwise", merge_type="TASK_VECTOR", learn_type="TASK_WISE", K=3, seed=61, disable_softmax=True),
     dict(name="tv_layerwise", merge_type="TASK_VECTOR", learn_type="LAYER_WISE", K=3, seed=62, disable_softmax=True),

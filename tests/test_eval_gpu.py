@@ -17,7 +17,7 @@ from mergerec_b200 import _lib, synth
 from mergerec_b200.evaluator import Evaluator, NDCG, Recall, ShardedItemTable, shard_bounds
 from mergerec_b200.evaluator.evaluator import score_topk, topk_rows
 from mergerec_b200.evaluator.metrics import label_rank
-from mergerec_b200.evaluator.sharded import MR_SCORE_TF32X1, MR_SCORE_TF32X3, split_tf32, topk_merge
+from mergerec_b200.evaluator.sharded import MR_SCORE_BF16, MR_SCORE_TF32X1, MR_SCORE_TF32X3, split_tf32, topk_merge
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -353,3 +353,70 @@ def test_fused_bf16_compat_gauss_and_shards():
     assert np.array_equal(host(mi), i) and np.array_equal(host(mv).view(np.uint32), v.view(np.uint32))
     with pytest.raises(ValueError):
         ev.topk_embeddings(dev(users), ShardedItemTable(dev(items)), mode=MR_SCORE_BF16)   # fp32-split table, bf16 mode
+
+
+# ------------------------------------------------------------------------------------------ round 2 additions
+def test_topk_merge_packed_equals_separate_lists():
+    """The exchange buffer form (L, 2, Q, K) merges to the same lists as separate (L, Q, K) vals / ids."""
+    from mergerec_b200.evaluator.sharded import topk_merge_packed
+    rng = np.random.Generator(np.random.PCG64(11))
+    for L, Q, K, k_out in ((2, 37, 10, 10), (8, 129, 100, 100), (3, 5, 7, 4)):
+        vals = rng.standard_normal((L, Q, K)).astype(np.float32)
+        vals[0, 0, :3] = vals[1, 0, :3]                           # equal scores across lists: lower id first
+        ids = rng.permutation(L * Q * K).reshape(L, Q, K).astype(np.int32)
+        ids[L - 1, Q - 1, K - 1] = -1                             # an empty slot
+        packed = np.stack([vals.view(np.int32), ids], axis=1)     # (L, 2, Q, K)
+        pv, pi = topk_merge_packed(dev(packed), k_out)
+        mv, mi = topk_merge(dev(vals), dev(ids), k_out)
+        assert np.array_equal(host(pi), host(mi))
+        assert_bit_equal(host(pv), host(mv), "packed merge values")
+
+
+@pytest.mark.parametrize("case", gc.EVAL_CFG4_CASES, ids=lambda c: c["name"])
+def test_fused_cfg4_shape_vs_golden(case):
+    """BASELINE config 4's evaluator shape -- N = 200,000 items, E = 1024, top-50 -- through the fused tensor-core path:
+    ids, scores and metric floats bit-identical to the golden run of the unmodified reference (grid inputs)."""
+    g = golden("evaluator_cfg4")
+    users, items, labels = synth.make_catalog(case["Q"], case["N"], case["E"], kind=case["kind"], seed=case["seed"])
+    ev = Evaluator(case["metrics"], case["ks"])
+    vals, ids = ev.topk_embeddings(dev(users), dev(items))
+    assert np.array_equal(host(ids), g[f"{case['name']}/canon_topk"])
+    assert_bit_equal(host(vals), g[f"{case['name']}/canon_vals"], "fused scores at E=1024")
+    res = ev.evaluate_embeddings(dev(users), dev(items), dev(labels), metric_prefix=case["prefix"])
+    assert list(res.keys()) == list(g[f"{case['name']}/canon_keys"])
+    assert np.array_equal(np.asarray(list(res.values()), np.float64), g[f"{case['name']}/canon_values"])
+
+
+def test_fused_cfg4_shape_vs_fp32_kernel_more_queries():
+    """E = 1024, K = 50, N = 200,000 with enough queries for several query blocks (Q = 1,100: 5 CTA pairs, a ragged
+    last block): the fused path equals `mr_scores_fp32` + `mr_topk_rows` bit for bit on grid inputs."""
+    from mergerec_b200 import _lib
+    users, items, _ = synth.make_catalog(1100, 200_000, 1024, kind="grid", seed=55)
+    tu, ti = dev(users), dev(items)
+    ev = Evaluator(["RECALL"], [50])
+    vals, ids = ev.topk_embeddings(tu, ti)
+    sc = torch.empty((1100, 200_000), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().mr_scores_fp32(_lib.dptr(tu), 1100, _lib.dptr(ti), 200_000, 1024, _lib.dptr(sc), 200_000,
+                                          _lib.stream_handle()), "mr_scores_fp32")
+    rv, ri = topk_rows(sc, 50)
+    assert torch.equal(ids, ri)
+    assert_bit_equal(host(vals), host(rv), "fused vs fp32 kernel scores")
+
+
+def test_prepared_queries_and_table_scratch_reuse():
+    """`prepare_queries` + a reused ShardedItemTable give the same lists as raw tensors, call after call."""
+    from mergerec_b200.evaluator import ShardedItemTable
+    users, items, labels = synth.make_catalog(300, 5000, 64, kind="grid", seed=19)
+    ev = Evaluator(["NDCG", "RECALL"], [10, 50])
+    tu, ti, tl = dev(users), dev(items), dev(labels)
+    v0, i0 = ev.topk_embeddings(tu, ti)
+    table = ShardedItemTable(ti)
+    q = ev.prepare_queries(tu)
+    for _ in range(3):
+        v, i = ev.topk_embeddings(q, table)
+        assert torch.equal(i, i0) and torch.equal(v, v0)
+    ws = table._ws
+    assert ws is not None and table.workspace(16) is ws
+    assert ev.evaluate_embeddings(q, table, tl) == ev.evaluate_embeddings(tu, ti, tl)
+    with pytest.raises(ValueError):
+        ev.topk_embeddings(ev.prepare_queries(tu, mode=MR_SCORE_BF16), table)

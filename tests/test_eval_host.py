@@ -63,6 +63,27 @@ def test_metric_edge_cases():
         Evaluator(["MRR"], [10])
 
 
+def test_fast_metric_finalisation_equals_the_row_loop():
+    """`recall_from_ranks` / `ndcg_from_ranks` skip the rows that miss; the result must be the very float the reference's
+    row loop `sum([...per row...]) / len` gives (metrics.py:49-61, 77-88), for any hit pattern."""
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        n = int(rng.integers(0, 5000))
+        k = int(rng.choice([1, 5, 10, 50, 100]))
+        ranks = np.where(rng.random(n) < rng.random(), rng.integers(0, 120, size=n), -1).astype(np.int32)
+        table = _gain_table(max(k, 1))
+        rec, ndcg = [], []
+        for r in ranks.tolist():                     # the reference's loop, one python float per row
+            hit = 0 <= r < k
+            rec.append(1.0 if hit else 0.0)
+            ndcg.append(float(table[r]) if hit else 0.0)
+        want_r = sum(rec) / len(rec) if rec else 0.0
+        want_n = sum(ndcg) / len(ndcg) if ndcg else 0.0
+        got_r, got_n = recall_from_ranks(ranks, k), ndcg_from_ranks(ranks, k)
+        assert isinstance(got_r, float) and isinstance(got_n, float)
+        assert got_r.hex() == float(want_r).hex() and got_n.hex() == float(want_n).hex()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

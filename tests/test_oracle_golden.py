@@ -139,6 +139,22 @@ def test_evaluator(case):
         assert np.array_equal(np.asarray(list(res.values()), np.float64), g[f"{case['name']}/raw_values"])
 
 
+@pytest.mark.parametrize("case", gc.EVAL_CFG4_CASES, ids=lambda c: c["name"])
+def test_evaluator_cfg4_shape(case):
+    """BASELINE config 4's evaluator shape (N = 200,000, E = 1024, top-50): oracle ids / values / metric floats equal the
+    golden run of the unmodified reference."""
+    g = golden("evaluator_cfg4")
+    users, items, labels = synth.make_catalog(case["Q"], case["N"], case["E"], kind=case["kind"], seed=case["seed"])
+    kmax = max(case["ks"])
+    scores = orc.scores_f32(users, items)
+    vals, ids = orc.topk_rows(scores, kmax)
+    assert np.array_equal(ids, g[f"{case['name']}/canon_topk"])
+    assert np.array_equal(vals, g[f"{case['name']}/canon_vals"])
+    res = orc.evaluate_ids(ids, labels, case["metrics"], case["ks"], case["prefix"])
+    assert list(res.keys()) == list(g[f"{case['name']}/canon_keys"])
+    assert np.array_equal(np.asarray(list(res.values()), np.float64), g[f"{case['name']}/canon_values"])
+
+
 def test_ndcg_gain_table():
     g = golden("evaluator")
     table = np.asarray([1 / orc._log2_f32(r + 2) for r in range(1024)], np.float64)
