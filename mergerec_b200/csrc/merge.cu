@@ -13,6 +13,7 @@ namespace mr {
 
 constexpr int kMergeThreads = 256;
 constexpr int kMaxSmemSegs = 2048;
+constexpr int kMaxMergeSmem = 224 * 1024;   // dynamic shared memory a CTA may opt in to on sm_100a (227 KB) minus slack
 
 struct SegView {
     const int64_t* seg_end;    // dev, P entries (ascending, exclusive)
@@ -154,9 +155,13 @@ static int launch_merge(const float* base, const float* const* src, int64_t d, c
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    // tables above 48 KB of shared memory (more than ~4,000 blocks) need the opt-in; mr_merge_axpy caps P at what 227 KB hold
 #define MR_LAUNCH(SEG, VEC)                                                                            \
-    merge_kernel<K, ORDER, SRC_IS_MODEL, SEG, VEC><<<(unsigned)blocks, kMergeThreads, smem, st>>>(     \
-        base, pack, d, w, G, sv, out)
+    do {                                                                                               \
+        auto kern = merge_kernel<K, ORDER, SRC_IS_MODEL, SEG, VEC>;                                    \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kern<<<(unsigned)blocks, kMergeThreads, smem, st>>>(base, pack, d, w, G, sv, out);             \
+    } while (0)
     if (segmented) { if (vec) MR_LAUNCH(true, true); else MR_LAUNCH(true, false); }
     else           { if (vec) MR_LAUNCH(false, true); else MR_LAUNCH(false, false); }
 #undef MR_LAUNCH
@@ -229,7 +234,8 @@ extern "C" int mr_merge_axpy(const float* base, const float* const* src, int K, 
     MR_REQUIRE(src && w && out, "mr_merge_axpy: null pointer");
     MR_REQUIRE(order == MR_ORDER_LINEAR || base, "mr_merge_axpy: base required unless order == LINEAR");
     MR_REQUIRE(P == 1 || (seg_end && seg_group), "mr_merge_axpy: P > 1 needs seg_end and seg_group");
-    MR_REQUIRE(P <= kMaxSmemSegs * 8, "mr_merge_axpy: too many blocks (P=%d)", P);
+    MR_REQUIRE((size_t)G * K * 4 + (size_t)P * 12 + 64 <= (size_t)kMaxMergeSmem,
+               "mr_merge_axpy: the block table (P=%d blocks, G=%d groups) does not fit %d bytes of shared memory", P, G, kMaxMergeSmem);
     MR_REQUIRE(order >= 0 && order <= 2, "mr_merge_axpy: bad order %d", order);
     MR_REQUIRE(!(order == MR_ORDER_LINEAR && src_is_model), "mr_merge_axpy: LINEAR takes sources as they are");
     cudaStream_t st = (cudaStream_t)stream;

@@ -285,7 +285,7 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 static __global__ void __launch_bounds__(256)
 ties_cand_hist_kernel(const TiesState* __restrict__ st, const uint32_t* __restrict__ cand_cnt,
                       const u64* __restrict__ cand_keys, int cand_cap, int n_lists, uint32_t* __restrict__ hist,
-                      u64* __restrict__ above) {
+                      u64* __restrict__ above /* NULL: refinement level, histogram only */) {
     __shared__ uint32_t s_hist[kTiesBins];
     __shared__ uint32_t s_not_above;
     const int k = blockIdx.y;
@@ -314,7 +314,7 @@ ties_cand_hist_kernel(const TiesState* __restrict__ st, const uint32_t* __restri
         const uint32_t v = s_hist[i];
         if (v) atomicAdd(&hist[k * kTiesBins + i], v);
     }
-    if (threadIdx.x == 0 && s_not_above) atomicAdd(&above[k], (u64)0 - (u64)s_not_above);   // two's-complement subtract
+    if (above && threadIdx.x == 0 && s_not_above) atomicAdd(&above[k], (u64)0 - (u64)s_not_above);   // two's-complement subtract
 }
 
 // ---- pick: turn a histogram into a narrower bracket ---------------------------------------------------
@@ -356,7 +356,7 @@ ties_pick_kernel(TiesState* st, const uint32_t* __restrict__ hist, const u64* __
     s_suffix[bin] = v;  // keys in bins >= bin
     if (t == 0) s_suffix[kTiesBins] = 0;
     __syncthreads();
-    const u64 above = above_ctr[k];
+    const u64 above = above_ctr ? above_ctr[k] : s.above;   // refinement level: keys above the bracket are known
     const u64 total_in = s_suffix[0];
     // bin holding rank r: the largest b with above + suffix[b] >= r
     const u64 ge = above + s_suffix[bin], gt = above + s_suffix[bin + 1];
@@ -738,8 +738,12 @@ int ties_build_launch_lns(const BuildLaunch& L);
 #if MR_TIES_PART >= 1
 template <int MODE>
 static int ties_build_launch_mode(const BuildLaunch& L) {
-#define MR_BUILD(VEC, MASKS) \
-    ties_build_kernel<KK, MODE, VEC, MASKS><<<(unsigned)L.blocks, kTiesThreads, L.smem, L.st>>>(L.base, pack, L.d, L.cut, L.a)
+#define MR_BUILD(VEC, MASKS)                                                                                       \
+    do {                                                                                                           \
+        auto kern = ties_build_kernel<KK, MODE, VEC, MASKS>;                                                       \
+        if (L.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem); \
+        kern<<<(unsigned)L.blocks, kTiesThreads, L.smem, L.st>>>(L.base, pack, L.d, L.cut, L.a);                   \
+    } while (0)
     MR_DISPATCH_K(L.K, {
         PtrPack<KK> pack;
         for (int k = 0; k < KK; ++k) pack.p[k] = L.models[k];
@@ -864,11 +868,16 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
 }
 
 static int ties_finish(const TiesWs& L, int K, int64_t k_cnt, u64* cut, int32_t* status, cudaStream_t st) {
-    {
-        dim3 hgrid(128, (unsigned)K);
-        ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.hist, L.above);
-    }
+    dim3 hgrid(128, (unsigned)K);
+    ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.hist, L.above);
     ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, k_cnt, k_cnt, 1, status);
+    // second refinement level over the collected keys only (a few MB): the bin picked above holds in_bracket / 1024 keys
+    // on average -- more than the final sort takes once d exceeds ~3e8 (Recformer-large: 3.2 M keys in the bracket) --
+    // and composite keys are distinct, so another 1024-way split always brings it down to a handful
+    cudaError_t e = cudaMemsetAsync(L.hist, 0, (size_t)K * kTiesBins * 4, st);
+    if (e != cudaSuccess) { set_error("mr_ties_select: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.hist, nullptr);
+    ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, nullptr, k_cnt, k_cnt, 1, status);
     dim3 grid(256, (unsigned)K);
     ties_compact_kernel<<<grid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.fin_cnt,
                                               L.fin_keys, status);
@@ -989,6 +998,8 @@ extern "C" int mr_ties_build(const float* base, const float* const* models, int 
     MR_REQUIRE(!rows_out || ldo >= d, "mr_ties_build: need ldo >= d");
     MR_REQUIRE(mode != TIES_MODE_FUSED_MERGE || (G >= 1 && P >= 1 && (P == 1 || (seg_end && seg_group))),
                "mr_ties_build: FUSED_MERGE needs G >= 1 and a block table when P > 1");
+    MR_REQUIRE(mode != TIES_MODE_FUSED_MERGE || (size_t)G * K * 4 + (size_t)P * 12 + 64 <= (size_t)224 * 1024,
+               "mr_ties_build: the block table (P=%d blocks, G=%d groups) does not fit shared memory", P, G);
     cudaStream_t st = (cudaStream_t)stream;
     bool vec = host_aligned16(base) && host_aligned16(out) && (!rows_out || (ldo % 4 == 0));
     for (int k = 0; k < K; ++k) vec = vec && host_aligned16(models[k]);

@@ -10,6 +10,7 @@ reference: scripts/2_ft_postprocess/extract.py:7-20   Lightning ckpt -> state_di
 from __future__ import annotations
 
 import ast
+import re
 from pathlib import Path
 from typing import Any, Dict, Iterable, List, Union
 
@@ -60,12 +61,33 @@ def read_weight_log(path: PathStr) -> List[Dict[str, Any]]:
     return [_literal(line) for line in text.splitlines()] if text else []
 
 
+_NAN_TOKEN = "__mergerec_nan__"
+# a bare inf / nan NAME (what repr() writes for non-finite floats), i.e. not part of a quoted key or another word
+_BARE_NONFINITE = re.compile(r"(?<![\w'\"])(-?)(inf|nan)(?![\w'\"])")
+
+
+def _restore_nan(obj):
+    if isinstance(obj, str) and obj == _NAN_TOKEN:
+        return float("nan")
+    if isinstance(obj, dict):
+        return {k: _restore_nan(v) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [_restore_nan(v) for v in obj]
+    if isinstance(obj, tuple):
+        return tuple(_restore_nan(v) for v in obj)
+    return obj
+
+
 def _literal(line: str):
     try:
         return ast.literal_eval(line)
     except ValueError:
-        # repr() writes non-finite floats as bare names, which literal_eval refuses
-        return ast.literal_eval(line.replace("inf", "1e999").replace("nan", "None"))
+        # repr() writes non-finite floats as the bare names inf / nan, which literal_eval refuses (the reference's eval
+        # would fail on them too unless the names are defined).  Only stand-alone tokens are rewritten, so group keys
+        # that contain "inf" / "nan" stay intact; nan comes back as float("nan"), inf as float("inf").
+        def sub(m):
+            return f"{m.group(1)}1e999" if m.group(2) == "inf" else f"'{_NAN_TOKEN}'"
+        return _restore_nan(ast.literal_eval(_BARE_NONFINITE.sub(sub, line)))
 
 
 def resolve_weights(weight_file: PathStr, weight_file_line: Union[int, float], num_models: int) -> WeightsDict:

@@ -39,7 +39,12 @@ def get_pcb_vectors(base_model: FlattenedModel, models: List[FlattenedModel], de
     dev = base_model.device
     i_lo, i_hi = int(d * 0.01), int(d * (1 - 0.01) - 1)          # pcb.py:20-21 with min_ratio = max_ratio = 0.01
     i_hi = i_hi if i_hi >= 0 else d + i_hi                       # sorted_x[-1] for tiny d, like the reference's indexing
-    lo = _magnitude_of(select_kth_largest(base_model, rows, d - i_lo)).contiguous()
+    if i_lo == 0:
+        # d < 100: sorted_x[0] is the row minimum of |tau| (pcb.py:20); the order-statistic select answers "keep
+        # everything" for k = d with cut 0 rather than the d-th largest magnitude, so take the minimum directly
+        lo = torch.stack([(r - base_model).abs().min() for r in rows]).to(torch.float32).contiguous()
+    else:
+        lo = _magnitude_of(select_kth_largest(base_model, rows, d - i_lo)).contiguous()
     hi = _magnitude_of(select_kth_largest(base_model, rows, d - i_hi)).contiguous()
     q_index = int(d * (1 - density))                             # pcb.py:53: min_ratio = 1 - density, max_ratio = 0
     out = alloc_rows(K, d, dev)

@@ -12,7 +12,7 @@ from typing import Iterable, List, Sequence
 import torch
 from torch import nn
 
-__all__ = ["ItemEncoderMixin", "ItemEncodingCallback", "MultiDatasetItemEncodingCallback"]
+__all__ = ["ItemEncoderMixin", "ItemEncodingCallback", "MultiDatasetItemEncodingCallback", "WeightCheckpointCallback"]
 
 
 def _to_device(batch, device):
@@ -78,3 +78,33 @@ class MultiDatasetItemEncodingCallback(ItemEncoderMixin):
     def on_test_epoch_start(self, trainer, pl_module):
         if pl_module.item_embeddings is None:
             self.inject_item_embeddings(self.item_dataloaders, pl_module)
+
+
+class WeightCheckpointCallback:
+    """Keep the best lambda set seen during validation and restore it afterwards (callbacks.py:177-205).
+
+    `monitor` is a regex matched with `re.fullmatch` against the names in `trainer.callback_metrics`; the score of an
+    epoch is the mean of the matching metrics, lower is better.  Built on `serialize_weights` /
+    `load_weights_from_dict` of the merging module (weight_learning/module/_base.py:67-89)."""
+
+    def __init__(self, monitor: str = "val/loss"):
+        self.monitor = monitor
+        self.best_score = float("inf")
+        self.best_weights = None
+
+    def on_validation_epoch_end(self, trainer, pl_module):
+        import re
+        scores = []
+        for name, value in trainer.callback_metrics.items():
+            if re.fullmatch(self.monitor, name):
+                scores.append(value.item() if hasattr(value, "item") else float(value))
+        if len(scores) == 0:
+            raise RuntimeError(f"No metrics found matching the monitor pattern: {self.monitor}")
+        current_score = sum(scores) / len(scores)
+        if current_score < self.best_score:
+            self.best_score = current_score
+            self.best_weights = pl_module.merged_model.serialize_weights()
+
+    def load_weights(self, pl_module):
+        if self.best_weights is not None:
+            pl_module.merged_model.load_weights_from_dict(self.best_weights)

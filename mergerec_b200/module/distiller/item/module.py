@@ -44,7 +44,7 @@ class DistillModule(DistillSequenceModule):
         spec = self.loss_fn.spec
         keep, ptrs = (None, None)
         if spec.needs_teacher:
-            keep, ptrs = self.score_embeddings.rows(batch.dataset_indexes, batch.item_ids)
+            keep, ptrs = self.score_embeddings.rows(batch.dataset_indexes, batch.item_ids, self.item_embeddings)
         losses = fused_distill_losses(rep, list(self.item_embeddings), batch.dataset_indexes, ptrs, spec)
         del keep
         return losses.mean()

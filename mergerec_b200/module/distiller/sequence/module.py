@@ -121,22 +121,61 @@ class TeacherScores:
         else:
             self.scores = [make_score_embeddings(i, s) for i, s in zip(item_embeddings, sequence_embeddings)]
 
+    # teacher matrices above this many bytes (all domains together) stay in pinned host memory, like the reference keeps
+    # them on the CPU (merge_train.py:126), and only the B rows of a step are copied to the device
+    MAX_DEVICE_BYTES = 32 << 30
+
     @classmethod
-    def from_scores(cls, score_embeddings: Sequence[torch.Tensor]) -> "TeacherScores":
+    def from_scores(cls, score_embeddings: Sequence[torch.Tensor], max_device_bytes: Optional[int] = None) -> "TeacherScores":
+        """Wrap precomputed (num_sequences_d, num_items_d) teacher matrices.  Up to `max_device_bytes` in total they are
+        moved to HBM (rows are then handed to the loss kernel as pointers, no copies); larger sets stay on the host in
+        pinned memory and `rows` stages the B needed rows per step."""
         self = cls.__new__(cls)
         self.on_the_fly = False
         dev = _lib.require_cuda()
-        self.scores = [s.to(device=dev, dtype=torch.float32).contiguous() for s in score_embeddings]
+        limit = cls.MAX_DEVICE_BYTES if max_device_bytes is None else int(max_device_bytes)
+        total = sum(int(s.numel()) * 4 for s in score_embeddings)
+        if total <= limit:
+            self.scores = [s.to(device=dev, dtype=torch.float32).contiguous() for s in score_embeddings]
+        else:
+            self.scores = []
+            for s in score_embeddings:
+                h = s.detach().to(device="cpu", dtype=torch.float32).contiguous()
+                self.scores.append(h if h.is_pinned() else h.pin_memory())
         return self
 
-    def rows(self, dataset_indexes: Sequence[int], sequence_ids: Sequence[int]):
-        """(keep-alive tensor(s), device addresses of the B teacher rows)."""
+    def width(self, d: int) -> int:
+        """Number of item columns of domain d's teacher rows."""
+        return int(self.items[d].shape[0]) if self.on_the_fly else int(self.scores[d].shape[1])
+
+    def rows(self, dataset_indexes: Sequence[int], sequence_ids: Sequence[int],
+             item_embeddings: Optional[Sequence[torch.Tensor]] = None):
+        """(keep-alive tensor(s), device addresses of the B teacher rows).  With `item_embeddings` given, every teacher
+        row is checked to be exactly as wide as the item table the loss kernel will read it against (a narrower teacher
+        matrix would be read out of bounds): ValueError otherwise."""
+        if item_embeddings is not None:
+            for d in set(int(x) for x in dataset_indexes):
+                if not 0 <= d < len(item_embeddings):
+                    raise ValueError(f"dataset index {d} outside [0, {len(item_embeddings)})")
+                if self.width(d) != int(item_embeddings[d].shape[0]):
+                    raise ValueError(f"teacher scores of dataset {d} have {self.width(d)} columns but its item table has "
+                                     f"{int(item_embeddings[d].shape[0])} rows")
         if not self.on_the_fly:
+            for d, s in zip(dataset_indexes, sequence_ids):
+                if not 0 <= s < self.scores[d].shape[0]:
+                    raise IndexError(f"sequence id {s} outside the teacher matrix of dataset {d}")
+            if self.scores and not self.scores[0].is_cuda:
+                # host-resident matrices: stage the B rows (one pinned -> device copy per row, stream-ordered)
+                dev = _lib.require_cuda()
+                ld = (max(self.scores[d].shape[1] for d in dataset_indexes) + 3) // 4 * 4
+                t = torch.empty((len(dataset_indexes), ld), dtype=torch.float32, device=dev)
+                for b, (d, s) in enumerate(zip(dataset_indexes, sequence_ids)):
+                    row = self.scores[d][s]
+                    t[b, :row.numel()].copy_(row, non_blocking=True)
+                return t, [t.data_ptr() + b * t.stride(0) * 4 for b in range(t.shape[0])]
             ptrs = []
             for d, s in zip(dataset_indexes, sequence_ids):
                 m = self.scores[d]
-                if not 0 <= s < m.shape[0]:
-                    raise IndexError(f"sequence id {s} outside the teacher matrix of dataset {d}")
                 ptrs.append(m.data_ptr() + int(s) * m.stride(0) * 4)
             return None, ptrs
         rep = torch.stack([self.sequences[d][s] for d, s in zip(dataset_indexes, sequence_ids)])
@@ -227,7 +266,7 @@ class DistillSequenceModule(nn.Module):
         spec = self.loss_fn.spec
         keep, ptrs = (None, None)
         if spec.needs_teacher:
-            keep, ptrs = self.score_embeddings.rows(batch.dataset_indexes, batch.sequence_ids)
+            keep, ptrs = self.score_embeddings.rows(batch.dataset_indexes, batch.sequence_ids, self.item_embeddings)
         losses = fused_distill_losses(rep, self.item_embeddings, batch.dataset_indexes, ptrs, spec)
         del keep
         return losses.mean()

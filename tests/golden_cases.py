@@ -83,6 +83,7 @@ PCB_CASES = [
     dict(name="k8_d4165", K=8, d=4165, seed=92, density=0.2, weights=[0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]),
     dict(name="k5_d10007", K=5, d=10007, seed=93, density=0.1, weights=[1.0, 0.5, 0.25, 2.0, 1.5]),
     dict(name="k2_d40000", K=2, d=40000, seed=94, density=0.5, weights=[0.6, 0.4]),
+    dict(name="k3_d77", K=3, d=77, seed=95, density=0.2, weights=[0.3, 0.5, 0.7]),   # d < 100: int(0.01 d) = 0 -> clamp_min = row minimum
 ]
 
 # DARE: the reference draws its dropout masks from torch's CPU generator; the golden file stores those masks (replayed

@@ -223,3 +223,28 @@ def test_item_distill_module_shares_the_step():
     assert enc_only.shape == (case["B"], case["E"]) and torch.allclose(enc_only.norm(dim=-1), torch.ones(case["B"], device="cuda"), atol=1e-5)
     with pytest.raises(ValueError):
         item_mod(object())
+
+
+def test_teacher_rows_are_validated_and_host_resident_matrices_match():
+    """A teacher matrix narrower than the item table must raise (it would be read out of bounds by the loss kernel);
+    teacher matrices kept in pinned host memory (large catalogs) give the same losses as device-resident ones."""
+    from mergerec_b200.module.distiller.sequence.module import DistillSequenceModule
+    c = synth.make_distill_case(6, 64, [37, 130, 257], 5, seed=81, planted=8.0)
+    tables = [dev(t) for t in c["tables"]]
+    scores = [torch.from_numpy(orc.teacher_scores(i, s).astype(np.float32)) for i, s in zip(c["teacher_items"], c["teacher_seqs"])]
+    on_dev = TeacherScores.from_scores(scores)
+    on_host = TeacherScores.from_scores(scores, max_device_bytes=0)
+    assert on_dev.scores[0].is_cuda and not on_host.scores[0].is_cuda and on_host.scores[0].is_pinned()
+    spec = loss_object("KD", dict(temperature=2.0)).spec
+    out = []
+    for teacher in (on_dev, on_host):
+        keep, ptrs = teacher.rows(c["dataset_indexes"], c["sequence_ids"], tables)
+        out.append(fused_distill_losses(dev(c["rep"]), tables, c["dataset_indexes"], ptrs, spec).cpu().numpy())
+        del keep
+    assert np.array_equal(out[0], out[1])
+    narrow = TeacherScores.from_scores([s[:, :-1] for s in scores])
+    with pytest.raises(ValueError, match="columns"):
+        narrow.rows(c["dataset_indexes"], c["sequence_ids"], tables)
+    with pytest.raises(IndexError):
+        on_dev.rows(c["dataset_indexes"], [10 ** 6] * len(c["sequence_ids"]), tables)
+    assert DistillSequenceModule is not None

@@ -155,6 +155,12 @@ def test_recformer_large_config4_properties():
     assert bool((trim.sum(dim=1) == k_cnt).all())
     assert torch.equal(That != 0, elect)
     del trim, elect
+    # the stream-ordered fast select must hold at this size too (3.2 M keys fall inside the sample bracket: two
+    # refinement levels over the collected keys), and agree with the public path's cut
+    from mergerec_b200.merger.algorithms.ties import select_kth_largest
+    fast_cut, status = select_kth_largest(base, models, k_cnt, None, defer_status=True)
+    assert status.cpu().tolist() == [1] * K, "fast select fell back at d = 433,610,754"
+    assert torch.equal(fast_cut, cut)
     lam = torch.rand((len(keys), K), device="cuda") * 0.4 + 0.1
     two_step = merge_axpy(base, list(That.unbind(0)), lam, _lib.MR_ORDER_SUM_FIRST, False, seg_end, seg_group)
     del That

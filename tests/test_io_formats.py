@@ -69,3 +69,51 @@ def test_weight_log_non_finite(tmp_path):
     p = tmp_path / "w.jsonl"
     p.write_text(repr({"epoch": 0, "step": 0, "weights": {"per_weights": {"all": [float("inf"), 1.0]}}}) + "\n")
     assert math.isinf(mio.read_weight_log(p)[0]["weights"]["per_weights"]["all"][0])
+
+
+def test_weight_log_nan_and_keys_containing_inf(tmp_path):
+    """A NaN lambda comes back as float('nan') (not None); group keys that merely contain "inf" / "nan" are untouched."""
+    p = tmp_path / "w.jsonl"
+    weights = {"per_weights": {"info_layer": [float("nan"), float("-inf"), 0.25], "nanny": [1.0]},
+               "global_weights": {"info_layer": [float("inf")]}}
+    p.write_text(repr({"epoch": 1, "step": 7, "weights": weights}) + "\n")
+    got = mio.read_weight_log(p)[0]
+    pw = got["weights"]["per_weights"]
+    assert set(pw.keys()) == {"info_layer", "nanny"} and pw["nanny"] == [1.0]
+    assert math.isnan(pw["info_layer"][0]) and pw["info_layer"][1] == float("-inf") and pw["info_layer"][2] == 0.25
+    assert got["weights"]["global_weights"]["info_layer"] == [float("inf")] and got["step"] == 7
+
+
+def test_weight_checkpoint_callback_keeps_the_best_lambda_set():
+    """callbacks.py:177-205: mean of the metrics matching the monitor regex, lower is better, restore at the end."""
+    import torch
+    from mergerec_b200.module.callbacks import WeightCheckpointCallback
+
+    class _Merged:
+        def __init__(self):
+            self.w = [0.0]
+
+        def serialize_weights(self):
+            return {"per_weights": {"all": list(self.w)}}
+
+        def load_weights_from_dict(self, d):
+            self.w = list(d["per_weights"]["all"])
+
+    class _PL:
+        merged_model = _Merged()
+
+    class _Trainer:
+        callback_metrics = {}
+
+    cb, pl, tr = WeightCheckpointCallback(monitor=r"val/loss.*"), _PL(), _Trainer()
+    for step, (a, b) in enumerate([(3.0, 1.0), (1.0, 0.5), (2.0, 2.0)]):
+        pl.merged_model.w = [float(step)]
+        tr.callback_metrics = {"val/loss/dataloader_idx_0": torch.tensor(a), "val/loss/dataloader_idx_1": torch.tensor(b), "train/loss": torch.tensor(9.0)}
+        cb.on_validation_epoch_end(tr, pl)
+    assert cb.best_score == 0.75 and cb.best_weights == {"per_weights": {"all": [1.0]}}
+    cb.load_weights(pl)
+    assert pl.merged_model.w == [1.0]
+    tr.callback_metrics = {"train/loss": torch.tensor(1.0)}
+    import pytest
+    with pytest.raises(RuntimeError):
+        cb.on_validation_epoch_end(tr, pl)

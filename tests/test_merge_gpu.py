@@ -160,3 +160,27 @@ def test_full_size_blair_base(K, order):
         sb, se, sg, _ = orc.segment_table(synth.roberta_shapes(), layer_wise=True)
         want = orc.lambda_merge(hb, orc.task_vectors(hb, hm), w, sb, se, sg)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_lambda_merge_many_blocks_needs_large_shared_memory():
+    """A layer-wise table of 6,000 tensors (72 KB of block table, above the 48 KB default) must launch -- the kernel opts
+    in to the larger dynamic shared memory -- and stay bit-exact; a table that cannot fit 224 KB is refused with a clear
+    argument error instead of a launch failure."""
+    P, K, G = 6000, 3, 7
+    rng = np.random.Generator(np.random.PCG64(21))
+    sizes = rng.integers(1, 40, size=P)
+    seg_end = np.cumsum(sizes).astype(np.int64)
+    seg_begin = seg_end - sizes
+    seg_group = rng.integers(0, G, size=P).astype(np.int32)
+    d = int(seg_end[-1])
+    base, models = synth.make_flat(d, K, seed=5)
+    T = orc.task_vectors(base, models)
+    w = rng.uniform(0.1, 0.5, size=(G, K)).astype(np.float32)
+    rows = alloc_rows(K, d, "cuda")
+    rows.copy_(dev(T))
+    out = merge_axpy(dev(base), list(rows.unbind(0)), dev(w), _lib.MR_ORDER_SUM_FIRST, False, dev(seg_end), dev(seg_group))
+    assert_bit_equal(host(out), orc.lambda_merge(base, T, w, seg_begin, seg_end, seg_group), "P = 6000 blocks")
+    P2 = 20000
+    with pytest.raises(ValueError, match="does not fit"):
+        merge_axpy(dev(base), list(rows.unbind(0)), dev(w), _lib.MR_ORDER_SUM_FIRST, False,
+                   dev(np.arange(1, P2 + 1, dtype=np.int64)), dev(np.zeros(P2, np.int32)))

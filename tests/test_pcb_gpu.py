@@ -45,7 +45,7 @@ def test_pcb_vectors_match_oracle_and_reference(case):
     assert (np.abs(task - o_task) <= 4e-7 * np.abs(o_task) + 1e-30).all()
     assert np.allclose(thr[:, 0], o_q, rtol=1e-6, atol=0) and np.allclose(thr[:, 1], o_max, rtol=1e-6, atol=0)
     near = (np.abs(o_task - o_q[:, None]) <= 1e-3 * np.abs(o_q[:, None])).any(axis=0)
-    assert near.mean() < 0.01
+    assert near.sum() <= max(0.01 * d, 2 * K)    # (each model's own threshold element is always "near": K columns when d is tiny)
     ref = g[f"{case['name']}/vectors"]
     assert row_rel(out, o_vec)[:, ~near].max() < TOL
     assert row_rel(out, ref)[:, ~near].max() < TOL
