@@ -132,6 +132,19 @@ enum mr_ties_mode {
     MR_TIES_LNS = 3,
 };
 
+/* Selection and build in ONE pass over the data (mode MR_TIES_VECTORS or MR_TIES_FUSED_MERGE, unweighted trim): the
+ * result of mr_ties_select(k_cnt) followed by mr_ties_build(mode), bit for bit, for (2K+1)*d*4 resp. (K+2)*d*4 bytes of
+ * traffic instead of (3K+2)*d*4 / (2K+3)*d*4.  Two passes over a strided sample bracket each model's cut; ONE full pass
+ * then builds `out` with a provisional cut (the middle of the bracket) while it counts the keys above the bracket and
+ * collects the ~0.75 % of keys inside it; the exact cut is finished from the collected keys and only the columns whose
+ * provisional decision was wrong (keys between the two cuts, ~0.05 %) are rebuilt.  Stream-ordered, no host sync.
+ * cut / status / ws as for mr_ties_select: when status[k] != MR_TIES_DONE for some k the contents of `out` are
+ * undefined and the caller must run mr_ties_select_exact + mr_ties_build instead.
+ * ref: merger/algorithms/ties.py:8-72 (+ weight_learning/module/layer_wise.py:76-82 for FUSED_MERGE). */
+int mr_ties_select_build(const float* base, const float* const* models, int K, int64_t d, int64_t k_cnt, int mode,
+                         const float* w, int G, const int64_t* seg_end, const int32_t* seg_group, int P, float* out,
+                         int64_t ldo, uint64_t* cut, int32_t* status, void* ws, int64_t ws_bytes, mr_stream_t stream);
+
 /* trim_mask / elect_mask: optional dev (K, d) bytes: survived the magnitude trim / survived trim and sign
  * election (That != 0).  NULL to skip. */
 int mr_ties_build(const float* base, const float* const* models, int K, int64_t d, const uint64_t* cut, int mode,

@@ -34,6 +34,7 @@ SIGNATURES = {
     "mr_ties_workspace_bytes": ([_i64, _i32], _i64),
     "mr_ties_select": ([_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "mr_ties_select_exact": ([_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp], C.c_int),
+    "mr_ties_select_build": ([_vp, _vp, _i32, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "mr_topk_rows": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp], C.c_int),
     "mr_topk_merge": ([_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp], C.c_int),
     "mr_topk_merge_packed": ([_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp], C.c_int),

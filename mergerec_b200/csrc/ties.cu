@@ -23,6 +23,7 @@
 // The full pass reads base + K models once ((K+1)*d*4 bytes, HBM-bound: a subtract, an AND and two compares
 // per element; no atomics outside the bracket).  The build kernels read them once more and write the result.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -488,6 +489,46 @@ __device__ __forceinline__ float div_by_count_fast(float x, float fc, float inv)
     return __fmaf_rn(r, inv, q0);
 }
 
+// Sign election and disjoint mean of one column from its TRIMMED updates s[k] (0 where model k was trimmed): ties.py:31-72.
+template <int K, bool TAIL>
+__device__ __forceinline__ void ties_elect(const float (&s)[K], bool lo_ok, float (&res)[K], uint32_t& elect_bits) {
+    float pp[K], nn[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        pp[k] = fmaxf(s[k], 0.0f);           // ties.py:35 torch.where(s > 0, s, 0): -0.0 and NaN become +0.0 either way
+        nn[k] = s[k] < 0.0f ? s[k] : 0.0f;   // ties.py:36 (fminf would keep a -0.0)
+    }
+    const float pos = torch_sum_dim0<K>(pp, TAIL);
+    const float neg = torch_sum_dim0<K>(nn, TAIL);
+    const float t = __fadd_rn(pos, neg);
+    // both sums non-zero: the larger magnitude wins, ties go to + (ties.py:41-45); otherwise sign(pos + neg) with
+    // 0 -> +1 (ties.py:47-50).  A NaN sum compares false and elects minus, as in the previous formulation.
+    const bool both = (pos != 0.0f) && (neg != 0.0f);
+    const bool plus = both ? (fabsf(pos) >= fabsf(neg)) : (t >= 0.0f);
+    int cnt = 0;
+    elect_bits = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        res[k] = plus ? pp[k] : nn[k];        // ties.py:61-65
+        const bool nz = res[k] != 0.0f;
+        cnt += nz ? 1 : 0;
+        elect_bits |= (nz ? 1u : 0u) << k;
+    }
+    // ties.py:68-70: x / cnt (cnt == 0: all zeros stay zero; cnt == 1: exact)
+    const float fc = (float)(cnt > 1 ? cnt : 1);
+    const float bound = fabsf(plus ? pos : neg);
+    if (lo_ok && bound < 0x1p100f) {
+        const float inv = c_inv_count[cnt];
+#pragma unroll
+        for (int k = 0; k < K; ++k) res[k] = div_by_count_fast(res[k], fc, inv);
+    } else {
+#pragma unroll
+        // (+ 0.0f: the compiler may turn the `s < 0 ? s : 0` select above into a min, which keeps the sign of a
+        //  -0.0 update; the reference's torch.where yields +0.0 there.  The fast path maps -0.0 to +0.0 by itself.)
+        for (int k = 0; k < K; ++k) res[k] = __fadd_rn(__fdiv_rn(res[k], fc), 0.0f);
+    }
+}
+
 // One flat column: trim, sign election, disjoint mean (or the trimmed sum for merge_ties).
 // TAIL = false: the column lies in the sequential part of torch.sum(dim=0) (every column when K <= 4).
 // The hot path is branch-free apart from the (never taken in practice) IEEE-divide escape.
@@ -521,40 +562,7 @@ __device__ __forceinline__ void ties_column(const float (&x)[K], float b, int64_
     } else if constexpr (MODE == TIES_MODE_TRIMSUM) {
         res[0] = __fadd_rn(b, torch_sum_dim0<K>(s, TAIL));   // ties.py:81-83
     } else {
-        float pp[K], nn[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            pp[k] = fmaxf(s[k], 0.0f);           // ties.py:35 torch.where(s > 0, s, 0): -0.0 and NaN become +0.0 either way
-            nn[k] = s[k] < 0.0f ? s[k] : 0.0f;   // ties.py:36 (fminf would keep a -0.0)
-        }
-        const float pos = torch_sum_dim0<K>(pp, TAIL);
-        const float neg = torch_sum_dim0<K>(nn, TAIL);
-        const float t = __fadd_rn(pos, neg);
-        // both sums non-zero: the larger magnitude wins, ties go to + (ties.py:41-45); otherwise sign(pos + neg) with
-        // 0 -> +1 (ties.py:47-50).  A NaN sum compares false and elects minus, as in the previous formulation.
-        const bool both = (pos != 0.0f) && (neg != 0.0f);
-        const bool plus = both ? (fabsf(pos) >= fabsf(neg)) : (t >= 0.0f);
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            res[k] = plus ? pp[k] : nn[k];        // ties.py:61-65
-            const bool nz = res[k] != 0.0f;
-            cnt += nz ? 1 : 0;
-            elect_bits |= (nz ? 1u : 0u) << k;
-        }
-        // ties.py:68-70: x / cnt (cnt == 0: all zeros stay zero; cnt == 1: exact)
-        const float fc = (float)(cnt > 1 ? cnt : 1);
-        const float bound = fabsf(plus ? pos : neg);
-        if (lo_ok && bound < 0x1p100f) {
-            const float inv = c_inv_count[cnt];
-#pragma unroll
-            for (int k = 0; k < K; ++k) res[k] = div_by_count_fast(res[k], fc, inv);
-        } else {
-#pragma unroll
-            // (+ 0.0f: the compiler may turn the `s < 0 ? s : 0` select above into a min, which keeps the sign of a
-            //  -0.0 update; the reference's torch.where yields +0.0 there.  The fast path maps -0.0 to +0.0 by itself.)
-            for (int k = 0; k < K; ++k) res[k] = __fadd_rn(__fdiv_rn(res[k], fc), 0.0f);
-        }
+        ties_elect<K, TAIL>(s, lo_ok, res, elect_bits);
     }
 }
 
@@ -711,6 +719,396 @@ ties_build_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, 
     for (int64_t q = nq_hot + gtid; q < nq; q += gsz) ties_quad<K, MODE, VEC, MASKS, true>(base, models, d, q, cut, lo_ok, wk, a, fs, hint);
 }
 
+// ---- speculative select + build in ONE pass over the data (VECTORS and FUSED_MERGE) --------------------------------------
+// After the two sample passes the cut of every model is known to lie in a narrow bracket [lo, hi] (about 0.75 % of the
+// keys).  Instead of one full pass that only counts / collects (the select) followed by a second full pass that
+// builds, this kernel does both at once: it builds the output with a PROVISIONAL cut (the middle of the bracket) while
+// counting the keys above the bracket and collecting the keys inside it exactly as the select's full pass does.  The
+// exact cut then comes from the collected keys (cand_hist -> pick -> pick -> compact -> final, a few microseconds), and
+// ties_patch_kernel recomputes only the columns whose provisional decision was wrong: the collected keys between the
+// provisional and the exact cut, typically 0.05 % of the columns.  The result is bit-identical to select + build.
+//
+// FUSED_MERGE keeps the lambda row and the bounds of the block a thread last met in registers: a quad that lies wholly
+// inside the sequential part of that block takes the hot path, any other quad looks its blocks up column by column.
+constexpr int kSpecStages = 2;
+__device__ __forceinline__ uint32_t spec_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void spec_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void spec_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void spec_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void spec_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct SpecState {     // per model, staged in shared memory
+    u64 lo, hi, mid;
+};
+
+template <int K, int MODE, bool VEC>
+__global__ void __launch_bounds__(kTiesThreads, K <= 8 ? 2 : 1)
+ties_spec_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const TiesState* __restrict__ st,
+                 const u64* __restrict__ mid_dev, PassCounters pc, BuildArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [FUSED_MERGE tables] | SpecState[K] | ge[K] u32 | lom[K] i32 | span[K] u32 | cnt[K][blockDim] u32
+    // (the bracket words and the per-thread candidate counters live in shared memory, not in registers: the hot loop
+    //  needs them once per model and quad, and 64 registers per thread keep four CTAs resident per SM)
+    size_t off = 0;
+    FusedSegs fs{nullptr, nullptr, nullptr, 1};
+    if (MODE == TIES_MODE_FUSED_MERGE) {
+        const int G = (int)a.ldo;   // number of lambda groups travels in ldo for this mode
+        float* s_w = reinterpret_cast<float*>(smem_raw);
+        off = ((size_t)G * K * 4 + 15) & ~(size_t)15;
+        const bool table = a.seg_end && a.seg_group;
+        int64_t* s_end = reinterpret_cast<int64_t*>(smem_raw + off);
+        int32_t* s_grp = reinterpret_cast<int32_t*>(s_end + (table ? a.P : 0));
+        if (table) off += (((size_t)a.P * 12) + 15) & ~(size_t)15;
+        for (int i = threadIdx.x; i < G * K; i += blockDim.x) s_w[i] = a.w[i];
+        if (table)
+            for (int i = threadIdx.x; i < a.P; i += blockDim.x) { s_end[i] = a.seg_end[i]; s_grp[i] = a.seg_group[i]; }
+        fs = FusedSegs{s_w, table ? s_end : nullptr, table ? s_grp : nullptr, a.P};
+    }
+    SpecState* s_st = reinterpret_cast<SpecState*>(smem_raw + off);
+    uint32_t* s_ge = reinterpret_cast<uint32_t*>(s_st + K);
+    uint32_t* s_lom = s_ge + K;
+    uint32_t* s_span = s_lom + K;
+    uint32_t* s_cnt = s_span + K;       // [K][blockDim.x]
+    // VEC: the TMA ring (kSpecStages x (K + 1) x 4 KB, 128-byte aligned) and its mbarriers follow the counters
+    const size_t ring_off = (off + (size_t)K * (sizeof(SpecState) + 12 + (size_t)kTiesThreads * 4) + 127) & ~(size_t)127;
+    if (threadIdx.x < K) {
+        const TiesState t = st[threadIdx.x];
+        s_st[threadIdx.x].lo = t.lo;
+        s_st[threadIdx.x].hi = t.hi;
+        s_st[threadIdx.x].mid = mid_dev[threadIdx.x];
+        s_ge[threadIdx.x] = 0;
+        s_lom[threadIdx.x] = (uint32_t)(t.lo >> 32);
+        s_span[threadIdx.x] = (uint32_t)(t.hi >> 32) - (uint32_t)(t.lo >> 32);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) s_cnt[k * kTiesThreads + threadIdx.x] = 0;
+    __syncthreads();
+
+    // magnitudes below the bracket, two 16-bit counters per register (a thread sees fewer than 2^16 elements per model:
+    // the grid is one resident wave and the host falls back to the two-pass path otherwise)
+    constexpr int KP = (K + 1) / 2;
+    uint32_t below2[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) below2[i] = 0;
+    bool lo_ok = true;   // every survivor is at least the bracket's lower magnitude: >= 2^-100 keeps the fast divide exact
+#pragma unroll
+    for (int k = 0; k < K; ++k) lo_ok = lo_ok && (s_lom[k] >= (27u << 23));
+    uint32_t visited = 0;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nq = (d + 3) >> 2;
+    const int64_t nq_hot = (K >= 5 ? (d & ~(int64_t)31) : (d & ~(int64_t)3)) >> 2;
+
+    // FUSED_MERGE: the block the thread is in -- [cur_lo, cur_hi) is its part where all four columns of a quad share
+    // one lambda row and the sequential summation order
+    int64_t cur_lo = 0, cur_hi = -1;
+    int hint = 0;
+    float wrow[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) wrow[k] = 0.0f;
+
+    // bracket magnitudes in registers (like the build kernel keeps its cut keys)
+    uint32_t lom[K], span[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { lom[k] = s_lom[k]; span[k] = s_span[k]; }
+
+    // Grid-stride over tiles of 256 quads (one quad per thread and tile).  With 16-byte aligned inputs (VEC) the tile's
+    // 2K + 1... K + 1 input slices (4 KB each) are brought in by 1-D TMA bulk copies into a ring of kSpecStages shared-
+    // memory stages: thread 0 keeps the next tile(s) in flight while the CTA computes, so the bytes in flight per SM
+    // (2 CTAs x 2 stages x (K + 1) x 4 KB = 147 KB at K = 8) do not depend on how many registers the column logic
+    // needs.  (Direct 128-bit loads left the kernel latency-bound: 52 % of the warp samples sat on the first use of
+    // the loaded values at 16 warps per SM.)
+    float* ring = reinterpret_cast<float*>(smem_raw + ring_off);
+    const uint32_t bar0 = spec_smem_u32(smem_raw + ring_off + (size_t)kSpecStages * (K + 1) * 4096);
+    const int64_t n_tiles = (nq_hot + kTiesThreads - 1) / kTiesThreads;
+    auto issue_tile = [&](int64_t tile, int stage) {   // thread 0 only
+        const int64_t q0 = tile * kTiesThreads;
+        const uint32_t nqt = (uint32_t)((nq_hot - q0) < kTiesThreads ? (nq_hot - q0) : kTiesThreads);
+        const uint32_t bytes = nqt * 16u;
+        const uint32_t bar = bar0 + 8u * stage;
+        spec_mbar_expect_tx(bar, bytes * (K + 1));
+        float* dst = ring + (size_t)stage * (K + 1) * 1024;
+        spec_bulk_load(spec_smem_u32(dst), base + (q0 << 2), bytes, bar);
+#pragma unroll
+        for (int k = 0; k < K; ++k) spec_bulk_load(spec_smem_u32(dst + (size_t)(k + 1) * 1024), models.p[k] + (q0 << 2), bytes, bar);
+    };
+    if (VEC) {
+        if (threadIdx.x == 0) {
+            for (int st_ = 0; st_ < kSpecStages; ++st_) spec_mbar_init(bar0 + 8u * st_, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int st_ = 0; st_ < kSpecStages; ++st_) {
+                const int64_t tile = (int64_t)st_ * gridDim.x + blockIdx.x;
+                if (tile < n_tiles) issue_tile(tile, st_);
+            }
+    }
+    for (int64_t it = 0;; ++it) {
+        const int64_t tile = it * gridDim.x + blockIdx.x;
+        if (tile >= n_tiles) break;
+        const int64_t q = tile * kTiesThreads + threadIdx.x;
+        const int64_t j0 = q << 2;
+        float bx[4];
+        float xs[K][4];
+        if (VEC) {
+            const int stage = (int)(it % kSpecStages);
+            spec_mbar_wait(bar0 + 8u * stage, (uint32_t)((it / kSpecStages) & 1));
+            const float4* sm4 = reinterpret_cast<const float4*>(ring + (size_t)stage * (K + 1) * 1024) + threadIdx.x;
+            if (q < nq_hot) {
+                const float4 b4 = sm4[0];
+                bx[0] = b4.x; bx[1] = b4.y; bx[2] = b4.z; bx[3] = b4.w;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float4 v = sm4[(k + 1) * 256];
+                    xs[k][0] = v.x; xs[k][1] = v.y; xs[k][2] = v.z; xs[k][3] = v.w;
+                }
+            }
+            __syncthreads();   // every thread holds its quad in registers: the stage can be refilled
+            if (threadIdx.x == 0) {
+                const int64_t next = (it + kSpecStages) * gridDim.x + blockIdx.x;
+                if (next < n_tiles) issue_tile(next, stage);
+            }
+            if (q >= nq_hot) continue;
+        } else {
+            if (q >= nq_hot) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                bx[c] = base[j0 + c];
+#pragma unroll
+                for (int k = 0; k < K; ++k) xs[k][c] = models.p[k][j0 + c];
+            }
+        }
+        // per column: provisional trim by the magnitude window (rare: exact key test against the provisional cut and
+        // collection of the key), then election + disjoint mean; xs[k][c] dies as res[c][k] is born
+        float res[4][K];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float sc[K];
+            bool hit = false;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float u = __fsub_rn(xs[k][c], bx[c]);
+                const uint32_t t = (__float_as_uint(u) & 0x7FFFFFFFu) - lom[k];
+                below2[k >> 1] += (t >> 31) << (16 * (k & 1));      // magnitude below the bracket: trimmed
+                hit |= t <= span[k];                                  // inside the bracket's magnitude window
+                sc[k] = ((int)t >= 0) ? u : 0.0f;
+            }
+            if (hit) {   // rare (~6 % of the columns at K = 8): collect the in-window keys, the provisional cut decides
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float u = __fsub_rn(xs[k][c], bx[c]);
+                    const uint32_t mag = __float_as_uint(u) & 0x7FFFFFFFu;
+                    if (mag - lom[k] <= span[k]) {
+                        const u64 key = ties_key(mag, j0 + c);
+                        const uint32_t n = s_cnt[k * kTiesThreads + threadIdx.x];
+                        if (n < (uint32_t)pc.cand_cap) pc.cand_keys[((size_t)k * gsz + gtid) * pc.cand_cap + n] = key;
+                        s_cnt[k * kTiesThreads + threadIdx.x] = n + 1;
+                        sc[k] = (key >= s_st[k].mid) ? u : 0.0f;
+                    }
+                }
+            }
+            uint32_t eb;
+            ties_elect<K, false>(sc, lo_ok, res[c], eb);
+        }
+        visited += 4;
+
+        if (MODE == TIES_MODE_VECTORS) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float* o = a.out + (int64_t)k * a.ldo + j0;
+                if (VEC) stg_stream4(o, make_float4(res[0][k], res[1][k], res[2][k], res[3][k]));
+                else
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) o[c] = res[c][k];
+            }
+        } else {   // FUSED_MERGE
+            float r[4];
+            if (!fs.end) {   // task-wise: one block, one lambda row (the tail columns are not in the hot range)
+                if (cur_hi < 0) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) wrow[k] = fs.w[k];
+                    cur_hi = 0;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float prod[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wrow[k], res[c][k]);
+                    r[c] = __fadd_rn(bx[c], sum_seq<K>(prod));
+                }
+            } else if (j0 >= cur_lo && j0 + 4 <= cur_hi) {   // hot: the whole quad in the sequential part of one block
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float prod[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wrow[k], res[c][k]);
+                    r[c] = __fadd_rn(bx[c], sum_seq<K>(prod));
+                }
+            } else {
+                // a block boundary (or a block's interleaved tail) inside or before this quad: per-column lookup,
+                // then remember the block the quad ended in
+                if (!(j0 < fs.end[hint] && (hint == 0 || j0 >= fs.end[hint - 1]))) {
+                    int lo_ = 0, hi_ = fs.P - 1;
+                    while (lo_ < hi_) { const int mid_ = (lo_ + hi_) >> 1; if (fs.end[mid_] > j0) hi_ = mid_; else lo_ = mid_ + 1; }
+                    hint = lo_;
+                }
+                int pseg = hint;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    while (j0 + c >= fs.end[pseg]) ++pseg;
+                    const int64_t beg = pseg ? fs.end[pseg - 1] : 0;
+                    const int64_t n = fs.end[pseg] - beg;
+                    const bool tail = (K >= 5) && ((j0 + c - beg) >= (n & ~(int64_t)31));
+                    const float* wr = fs.w + fs.grp[pseg] * K;
+                    float prod[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wr[k], res[c][k]);
+                    r[c] = __fadd_rn(bx[c], torch_sum_dim0<K>(prod, tail));
+                }
+                hint = pseg;
+                const int64_t beg = pseg ? fs.end[pseg - 1] : 0;
+                const int64_t n = fs.end[pseg] - beg;
+                cur_lo = beg;
+                cur_hi = (K >= 5) ? beg + (n & ~(int64_t)31) : fs.end[pseg];
+#pragma unroll
+                for (int k = 0; k < K; ++k) wrow[k] = fs.w[fs.grp[pseg] * K + k];
+            }
+            float* o = a.out + j0;
+            if (VEC) stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
+            else
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[c] = r[c];
+        }
+    }
+    // the few cold columns (partial last quad; the <= 31 trailing columns that use the interleaved order when K >= 5):
+    // counted and collected here, built by ties_patch_kernel with the exact cut
+    for (int64_t q = nq_hot + gtid; q < nq; q += gsz) {
+        const int64_t j0 = q << 2;
+        const int nvalid = (int)((d - j0) < 4 ? (d - j0) : 4);
+        for (int c = 0; c < nvalid; ++c) {
+            const float b = base[j0 + c];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float u = __fsub_rn(models.p[k][j0 + c], b);
+                const uint32_t mag = __float_as_uint(u) & 0x7FFFFFFFu;
+                const uint32_t t = mag - lom[k];
+                below2[k >> 1] += (t >> 31) << (16 * (k & 1));
+                if (t <= span[k]) {
+                    const uint32_t n = s_cnt[k * kTiesThreads + threadIdx.x];
+                    if (n < (uint32_t)pc.cand_cap)
+                        pc.cand_keys[((size_t)k * gsz + gtid) * pc.cand_cap + n] = ties_key(mag, j0 + c);
+                    s_cnt[k * kTiesThreads + threadIdx.x] = n + 1;
+                }
+            }
+        }
+        visited += (uint32_t)nvalid;
+    }
+
+    // above = #magnitudes >= lo_mag; ties_cand_hist_kernel subtracts the collected keys that are not above the bracket
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        uint32_t v = visited - ((below2[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_ge[k], v);
+        pc.cand_cnt[(size_t)k * gsz + gtid] = s_cnt[k * kTiesThreads + threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x < K && s_ge[threadIdx.x]) atomicAdd(&pc.above[threadIdx.x], (u64)s_ge[threadIdx.x]);
+}
+
+// provisional cut = middle of the sample bracket (only read when the model is still searching)
+static __global__ void ties_mid_kernel(const TiesState* __restrict__ st, int K, u64* __restrict__ mid) {
+    const int k = threadIdx.x;
+    if (k < K) mid[k] = st[k].lo + ((st[k].hi - st[k].lo) >> 1);
+}
+
+// One column rebuilt with the exact cuts (scalar accesses).
+template <int K, int MODE>
+__device__ __forceinline__ void ties_patch_column(const float* __restrict__ base, const PtrPack<K>& models, int64_t d, int64_t j,
+                                                  const u64 (&cut)[K], bool lo_ok, const BuildArgs& a) {
+    float x[K], res[K];
+    uint32_t tb, eb;
+    const float b = base[j];
+#pragma unroll
+    for (int k = 0; k < K; ++k) x[k] = models.p[k][j];
+    const bool flat_tail = (K >= 5) && (j >= (d & ~(int64_t)31));
+    if (MODE == TIES_MODE_VECTORS) {
+        if (flat_tail) ties_column<K, TIES_MODE_VECTORS, true>(x, b, j, cut, lo_ok, nullptr, res, tb, eb);
+        else ties_column<K, TIES_MODE_VECTORS, false>(x, b, j, cut, lo_ok, nullptr, res, tb, eb);
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.out[(int64_t)k * a.ldo + j] = res[k];
+    } else {
+        // the election's sums run over the K models of ONE column: their order depends on the position in the flat
+        // vector (VECTORS semantics of get_ties_vectors: tail = last d mod 32 columns of the whole vector)
+        if (flat_tail) ties_column<K, TIES_MODE_VECTORS, true>(x, b, j, cut, lo_ok, nullptr, res, tb, eb);
+        else ties_column<K, TIES_MODE_VECTORS, false>(x, b, j, cut, lo_ok, nullptr, res, tb, eb);
+        const float* wr = a.w;
+        bool tail = flat_tail;
+        if (a.seg_end && a.seg_group) {
+            int lo_ = 0, hi_ = a.P - 1;
+            while (lo_ < hi_) { const int mid_ = (lo_ + hi_) >> 1; if (a.seg_end[mid_] > j) hi_ = mid_; else lo_ = mid_ + 1; }
+            const int64_t beg = lo_ ? a.seg_end[lo_ - 1] : 0;
+            const int64_t n = a.seg_end[lo_] - beg;
+            tail = (K >= 5) && ((j - beg) >= (n & ~(int64_t)31));
+            wr = a.w + a.seg_group[lo_] * K;
+        }
+        float prod[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wr[k], res[k]);
+        a.out[j] = __fadd_rn(b, torch_sum_dim0<K>(prod, tail));
+    }
+}
+
+// Fix-up after the exact cut is known: every collected key between the provisional and the exact cut names a column
+// whose provisional decision was wrong; block (0, 0) also builds the cold columns.  One candidate list per thread.
+template <int K, int MODE>
+__global__ void __launch_bounds__(256)
+ties_patch_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const u64* __restrict__ cut_dev,
+                  const u64* __restrict__ mid_dev, const int32_t* __restrict__ status, const uint32_t* __restrict__ cand_cnt,
+                  const u64* __restrict__ cand_keys, int cand_cap, int n_lists, BuildArgs a) {
+    u64 cut[K];
+    bool lo_ok = true, ok = true;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        cut[k] = cut_dev[k];
+        lo_ok = lo_ok && ((uint32_t)(cut[k] >> 32) >= (27u << 23));
+        ok = ok && status[k] == TIES_ST_DONE;
+    }
+    if (!ok) return;   // a failed select: the caller sees the status and takes the exact path
+    const int k = blockIdx.y;
+    const u64 a_ = cut_dev[k], b_ = mid_dev[k];
+    const u64 lo = a_ < b_ ? a_ : b_, hi = a_ < b_ ? b_ : a_;   // mis-decided keys: lo <= key < hi
+    const int64_t hot_end = (K >= 5 ? (d & ~(int64_t)31) : (d & ~(int64_t)3));
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_lists; c += gridDim.x * blockDim.x) {
+        uint32_t n = cand_cnt[(size_t)k * n_lists + c];
+        if (n > (uint32_t)cand_cap) n = (uint32_t)cand_cap;
+        const u64* keys = cand_keys + ((size_t)k * n_lists + c) * cand_cap;
+        for (uint32_t e = 0; e < n; ++e) {
+            const u64 key = keys[e];
+            if (key >= lo && key < hi) {
+                const int64_t j = (int64_t)(0xFFFFFFFFu - (uint32_t)key);
+                if (j < hot_end) ties_patch_column<K, MODE>(base, models, d, j, cut, lo_ok, a);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+        for (int64_t j = hot_end + threadIdx.x; j < d; j += blockDim.x) ties_patch_column<K, MODE>(base, models, d, j, cut, lo_ok, a);
+}
+
 // ---- per-mode launchers of the build kernel ---------------------------------------------------------------------------
 // This file is compiled five times (Makefile): MR_TIES_PART = 0 holds the selection kernels and every C entry point,
 // MR_TIES_PART = 1..4 hold the 64 instantiations (K x alignment x masks) of the build kernel for ONE mode each, so that
@@ -735,7 +1133,29 @@ int ties_build_launch_trimsum(const BuildLaunch& L);
 int ties_build_launch_fused(const BuildLaunch& L);
 int ties_build_launch_lns(const BuildLaunch& L);
 
+struct SpecLaunch {
+    const float* base;
+    const float* const* models;
+    int K;
+    int64_t d;
+    const TiesState* st;
+    const u64* mid;
+    const u64* cut;
+    const int32_t* status;
+    PassCounters pc;
+    BuildArgs a;
+    size_t smem;
+    int n_lists;     // candidate lists available in the workspace (>= threads of the spec grid)
+    bool vec;
+    cudaStream_t stream;
+};
+// phase 0: query the grid (one resident wave) -> *blocks; phase 1: launch the speculative pass with `blocks` CTAs;
+// phase 2: launch the patch kernel
+int ties_spec_launch_vectors(const SpecLaunch& L, int phase, int* blocks);
+int ties_spec_launch_fused(const SpecLaunch& L, int phase, int* blocks);
+
 #if MR_TIES_PART >= 1
+#if MR_TIES_PART <= 4
 template <int MODE>
 static int ties_build_launch_mode(const BuildLaunch& L) {
 #define MR_BUILD(VEC, MASKS)                                                                                       \
@@ -762,6 +1182,40 @@ int ties_build_launch_fused(const BuildLaunch& L) { return ties_build_launch_mod
 #elif MR_TIES_PART == 4
 int ties_build_launch_lns(const BuildLaunch& L) { return ties_build_launch_mode<TIES_MODE_LNS>(L); }
 #endif
+#endif  // MR_TIES_PART <= 4
+#if MR_TIES_PART >= 5
+template <int MODE>
+static int ties_spec_launch_mode(const SpecLaunch& L, int phase, int* blocks) {
+    MR_DISPATCH_K(L.K, {
+        PtrPack<KK> pack;
+        for (int k = 0; k < KK; ++k) pack.p[k] = L.models[k];
+        if (phase == 0 || phase == 1) {
+            auto kern = L.vec ? ties_spec_kernel<KK, MODE, true> : ties_spec_kernel<KK, MODE, false>;
+            if (L.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+            if (phase == 0) {
+                int per_sm = 0;
+                cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTiesThreads, L.smem);
+                if (e != cudaSuccess || per_sm < 1) { set_error("mr_ties_select_build: occupancy query failed"); return e != cudaSuccess ? (int)e : MR_ERR_UNSUPPORTED; }
+                int b = per_sm * sm_count();
+                if (b * kTiesThreads > L.n_lists) b = L.n_lists / kTiesThreads;
+                *blocks = b;
+                return MR_OK;
+            }
+            kern<<<*blocks, kTiesThreads, L.smem, L.stream>>>(L.base, pack, L.d, L.st, L.mid, L.pc, L.a);
+        } else {
+            dim3 grid(64, (unsigned)KK);
+            ties_patch_kernel<KK, MODE><<<grid, 256, 0, L.stream>>>(L.base, pack, L.d, L.cut, L.mid, L.status, L.pc.cand_cnt,
+                                                                    L.pc.cand_keys, L.pc.cand_cap, *blocks * kTiesThreads, L.a);
+        }
+    });
+    return MR_OK;
+}
+#if MR_TIES_PART == 5
+int ties_spec_launch_vectors(const SpecLaunch& L, int phase, int* blocks) { return ties_spec_launch_mode<TIES_MODE_VECTORS>(L, phase, blocks); }
+#elif MR_TIES_PART == 6
+int ties_spec_launch_fused(const SpecLaunch& L, int phase, int* blocks) { return ties_spec_launch_mode<TIES_MODE_FUSED_MERGE>(L, phase, blocks); }
+#endif
+#endif  // MR_TIES_PART >= 5
 #endif  // MR_TIES_PART >= 1
 
 #if MR_TIES_PART == 0
@@ -771,6 +1225,7 @@ struct TiesWs {
     uint32_t* hist;      // K * bins       } zeroed together before every pass
     u64* above;          // K              }
     uint32_t* fin_cnt;   // K              }
+    u64* mid;            // K: provisional cuts of the speculative select + build
     uint32_t* cand_cnt;  // K * n_lists
     u64* fin_keys;       // K * final cap
     u64* cand_keys;      // K * n_lists * cand_cap
@@ -810,7 +1265,9 @@ static void ties_sample_ranks(int64_t d, int64_t k_cnt, int64_t n_s, int64_t* r_
 
 static TiesWs ties_layout(void* ws, int64_t d, int K) {
     TiesWs L;
-    const int n_lists = ties_pass_blocks(K) * kTiesThreads;   // one private candidate list per thread of the pass grid
+    // one private candidate list per thread of the collecting grid: the select's pass kernel runs 3 (K <= 8) or 2 CTAs per
+    // SM, the speculative select + build kernel up to 4
+    const int n_lists = sm_count() * (K <= 8 ? 4 : 2) * kTiesThreads;
     // expected fraction of keys inside the sample bracket: the +-6 sigma rank window plus bin slack
     const int64_t stride = ties_sample_stride(d);
     const int64_t n_s = ties_sample_count(d, stride);
@@ -831,6 +1288,7 @@ static TiesWs ties_layout(void* ws, int64_t d, int K) {
     L.above = reinterpret_cast<u64*>(p + off); off += align256((size_t)K * 8);
     L.fin_cnt = reinterpret_cast<uint32_t*>(p + off); off += align256((size_t)K * 4);
     L.zero_bytes = off - z0;
+    L.mid = reinterpret_cast<u64*>(p + off); off += align256((size_t)K * 8);
     L.cand_cnt = reinterpret_cast<uint32_t*>(p + off); off += align256((size_t)K * n_lists * 4);
     L.fin_keys = reinterpret_cast<u64*>(p + off); off += align256((size_t)K * kTiesFinalCap * 8);
     L.cand_keys = reinterpret_cast<u64*>(p + off); off += align256((size_t)K * n_lists * (size_t)cap * 8);
@@ -846,7 +1304,7 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
     for (int k = 0; k < K; ++k) { pack.p[k] = models[k]; vec = vec && host_aligned16(models[k]); }
     PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap};
     const size_t smem = PassSmem<K>::bytes();
-    const int blocks = ties_pass_blocks(K);
+    const int blocks = ties_pass_blocks(K);   // (sample passes too: a smaller grid makes them latency-bound, 70 -> 236 us)
     cudaError_t e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
     if (e != cudaSuccess) { set_error("mr_ties_select: memset: %s", cudaGetErrorString(e)); return (int)e; }
 #define MR_PASS(VEC, W, COLLECT)                                                                               \
@@ -867,19 +1325,20 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
     return MR_OK;
 }
 
-static int ties_finish(const TiesWs& L, int K, int64_t k_cnt, u64* cut, int32_t* status, cudaStream_t st) {
+// n_lists: the candidate lists the collecting pass wrote = its thread count (the workspace may hold more)
+static int ties_finish(const TiesWs& L, int K, int64_t k_cnt, u64* cut, int32_t* status, cudaStream_t st, int n_lists) {
     dim3 hgrid(128, (unsigned)K);
-    ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.hist, L.above);
+    ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, n_lists, L.hist, L.above);
     ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, k_cnt, k_cnt, 1, status);
     // second refinement level over the collected keys only (a few MB): the bin picked above holds in_bracket / 1024 keys
     // on average -- more than the final sort takes once d exceeds ~3e8 (Recformer-large: 3.2 M keys in the bracket) --
     // and composite keys are distinct, so another 1024-way split always brings it down to a handful
     cudaError_t e = cudaMemsetAsync(L.hist, 0, (size_t)K * kTiesBins * 4, st);
     if (e != cudaSuccess) { set_error("mr_ties_select: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.hist, nullptr);
+    ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, n_lists, L.hist, nullptr);
     ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, nullptr, k_cnt, k_cnt, 1, status);
     dim3 grid(256, (unsigned)K);
-    ties_compact_kernel<<<grid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, L.n_lists, L.fin_cnt,
+    ties_compact_kernel<<<grid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, n_lists, L.fin_cnt,
                                               L.fin_keys, status);
     ties_final_kernel<<<K, 1024, 0, st>>>(L.st, L.fin_cnt, L.fin_keys, k_cnt, cut, status);
     MR_CUDA_LAUNCH_CHECK("mr_ties_select(finish)");
@@ -939,7 +1398,7 @@ extern "C" int mr_ties_select(const float* base, const float* const* models, int
         rc = ties_launch_pass<KK>(base, models, d, w, 1, 1, L, st);
         if (rc != MR_OK) return rc;
     });
-    return ties_finish(L, K, k_cnt, reinterpret_cast<u64*>(cut), status, st);
+    return ties_finish(L, K, k_cnt, reinterpret_cast<u64*>(cut), status, st, ties_pass_blocks(K) * kTiesThreads);
 }
 
 // Exact path for any input (e.g. millions of equal magnitudes).  SYNCHRONOUS: reads the bracket state back after
@@ -977,10 +1436,84 @@ extern "C" int mr_ties_select_exact(const float* base, const float* const* model
         rc = ties_launch_pass<KK>(base, models, d, w, 1, 2, L, st);
         if (rc != MR_OK) return rc;
     });
-    rc = ties_finish(L, K, k_cnt, reinterpret_cast<u64*>(cut), status, st);
+    rc = ties_finish(L, K, k_cnt, reinterpret_cast<u64*>(cut), status, st, ties_pass_blocks(K) * kTiesThreads);
     if (rc != MR_OK) return rc;
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("mr_ties_select_exact: %s", cudaGetErrorString(e)); return (int)e; }
+    return MR_OK;
+}
+
+// get_ties_vectors / the fused TIES + lambda merge in ONE pass over the data: sample passes, then the speculative
+// select + build pass, the exact cut from the collected keys, and the fix-up of the mis-decided columns.
+extern "C" int mr_ties_select_build(const float* base, const float* const* models, int K, int64_t d, int64_t k_cnt, int mode,
+                                    const float* w, int G, const int64_t* seg_end, const int32_t* seg_group, int P,
+                                    float* out, int64_t ldo, uint64_t* cut, int32_t* status, void* ws, int64_t ws_bytes,
+                                    mr_stream_t stream) {
+    using namespace mr;
+    int rc = ties_check_args(base, models, K, d, cut, status, ws, ws_bytes, "mr_ties_select_build");
+    if (rc != MR_OK) return rc;
+    MR_REQUIRE(mode == TIES_MODE_VECTORS || mode == TIES_MODE_FUSED_MERGE, "mr_ties_select_build: mode must be VECTORS or FUSED_MERGE");
+    if (d == 0 || k_cnt <= 0 || k_cnt >= d) {
+        // trivial cuts (keep nothing / everything): nothing to speculate about
+        rc = mr_ties_select(base, models, K, d, nullptr, k_cnt, cut, status, ws, ws_bytes, stream);
+        if (rc != MR_OK || d == 0) return rc;
+        return mr_ties_build(base, models, K, d, cut, mode, w, G, seg_end, seg_group, P, out, ldo, nullptr, nullptr, stream);
+    }
+    MR_REQUIRE(out, "mr_ties_select_build: null output");
+    const bool rows_out = mode == TIES_MODE_VECTORS;
+    MR_REQUIRE(rows_out || w, "mr_ties_select_build: FUSED_MERGE needs the lambdas");
+    MR_REQUIRE(!rows_out || ldo >= d, "mr_ties_select_build: need ldo >= d");
+    MR_REQUIRE(rows_out || (G >= 1 && P >= 1 && (P == 1 || (seg_end && seg_group))),
+               "mr_ties_select_build: FUSED_MERGE needs G >= 1 and a block table when P > 1");
+    MR_REQUIRE(rows_out || (size_t)G * K * 4 + (size_t)P * 12 + 1024 <= (size_t)200 * 1024,
+               "mr_ties_select_build: the block table (P=%d blocks, G=%d groups) does not fit shared memory", P, G);
+    cudaStream_t st = (cudaStream_t)stream;
+    const TiesWs L = ties_layout(ws, d, K);
+    ties_init_kernel<<<1, 32, 0, st>>>(L.st, K, reinterpret_cast<u64*>(cut), status, k_cnt, d);
+    MR_CUDA_LAUNCH_CHECK("mr_ties_select_build(init)");
+    const int64_t stride = ties_sample_stride(d);
+    const int64_t n_s = ties_sample_count(d, stride);
+    int64_t r_hi, r_lo;
+    ties_sample_ranks(d, k_cnt, n_s, &r_hi, &r_lo);
+    MR_DISPATCH_K(K, {
+        for (int it = 0; it < 2; ++it) {
+            rc = ties_launch_pass<KK>(base, models, d, nullptr, stride, 0, L, st);
+            if (rc != MR_OK) return rc;
+            ties_pick_kernel<<<KK, kTiesBins, 0, st>>>(L.st, L.hist, L.above, r_hi, r_lo, 0, status);
+        }
+    });
+    ties_mid_kernel<<<1, 32, 0, st>>>(L.st, K, L.mid);
+    cudaError_t e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
+    if (e != cudaSuccess) { set_error("mr_ties_select_build: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    bool vec = host_aligned16(base) && host_aligned16(out) && (!rows_out || (ldo % 4 == 0));
+    for (int k = 0; k < K; ++k) vec = vec && host_aligned16(models[k]);
+    BuildArgs a{out, rows_out ? ldo : (int64_t)G, nullptr, nullptr, w, seg_end, seg_group, rows_out ? 1 : P};
+    size_t smem = (size_t)K * (sizeof(SpecState) + 12 + (size_t)kTiesThreads * 4) + 32;
+    if (!rows_out) smem += (((size_t)G * K * 4 + 15) & ~(size_t)15) + ((seg_end && seg_group) ? ((((size_t)P * 12) + 15) & ~(size_t)15) : 0);
+    if (vec) smem = ((smem + 127) & ~(size_t)127) + (size_t)kSpecStages * (K + 1) * 4096 + 64;   // TMA ring + mbarriers
+    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap};
+    SpecLaunch S{base, models, K, d, L.st, L.mid, reinterpret_cast<const u64*>(cut), status, pc, a, smem, L.n_lists, vec, st};
+    int blocks = 0;
+    auto launch = rows_out ? ties_spec_launch_vectors : ties_spec_launch_fused;
+    rc = launch(S, 0, &blocks);
+    if (rc != MR_OK) return rc;
+    {   // the kernel counts per thread in 16 bits: a grid too small for that (a tiny GPU, a huge vector) takes two passes
+        const int64_t nq_hot = (K >= 5 ? (d & ~(int64_t)31) : (d & ~(int64_t)3)) >> 2;
+        const int64_t per_thread = blocks > 0 ? (nq_hot + (int64_t)blocks * kTiesThreads - 1) / ((int64_t)blocks * kTiesThreads) : nq_hot;
+        if (blocks < 1 || (per_thread + 2) * 4 >= 65535) {
+            rc = mr_ties_select(base, models, K, d, nullptr, k_cnt, cut, status, ws, ws_bytes, stream);
+            if (rc != MR_OK) return rc;
+            return mr_ties_build(base, models, K, d, cut, mode, w, G, seg_end, seg_group, P, out, ldo, nullptr, nullptr, stream);
+        }
+    }
+    rc = launch(S, 1, &blocks);
+    if (rc != MR_OK) return rc;
+    MR_CUDA_LAUNCH_CHECK("mr_ties_select_build(pass)");
+    rc = ties_finish(L, K, k_cnt, reinterpret_cast<u64*>(cut), status, st, blocks * kTiesThreads);
+    if (rc != MR_OK) return rc;
+    rc = launch(S, 2, &blocks);
+    if (rc != MR_OK) return rc;
+    MR_CUDA_LAUNCH_CHECK("mr_ties_select_build(patch)");
     return MR_OK;
 }
 

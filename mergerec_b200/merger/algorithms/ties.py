@@ -77,6 +77,41 @@ def _build(base_model, rows, cut, mode, w=None, G=1, seg_end=None, seg_group=Non
     _lib.check(rc, "mr_ties_build")
 
 
+def select_build(base_model: FlattenedModel, rows: Sequence[torch.Tensor], k_cnt: int, mode: int, out: torch.Tensor,
+                 ldo: int = 0, w: Optional[torch.Tensor] = None, G: int = 1, seg_end: Optional[torch.Tensor] = None,
+                 seg_group: Optional[torch.Tensor] = None, defer_status: bool = False):
+    """Selection and build in ONE pass over the data (`mr_ties_select_build`: build with a provisional cut while the
+    keys around it are collected, finish the exact cut, rebuild the few mis-decided columns) -- bit-identical to
+    `select_kth_largest` + `_build` for `MR_TIES_VECTORS` / `MR_TIES_FUSED_MERGE`.  Returns the cut keys; if a model's
+    sampled bracket missed (adversarial inputs) the exact select and the plain build run instead.
+    `defer_status=True`: no host synchronisation (CUDA-graph capturable); returns `(cut, status)` and the caller must
+    pass `status` to :func:`verify_select_status` before trusting `out`."""
+    lib = _lib.load()
+    K, d = len(rows), base_model.numel()
+    dev = base_model.device
+    P = 1 if seg_end is None else seg_end.numel()
+    ws_bytes = int(lib.mr_ties_workspace_bytes(d, K))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cut = torch.empty(K, dtype=torch.int64, device=dev)
+    status = torch.zeros(K, dtype=torch.int32, device=dev)
+    parr = _lib.ptr_array(rows)
+    _lib.check(lib.mr_ties_select_build(_lib.dptr(base_model, torch.float32), parr, K, d, int(k_cnt), mode, _lib.dptr(w), G,
+                                        _lib.dptr(seg_end), _lib.dptr(seg_group), P, _lib.dptr(out), ldo, _lib.dptr(cut),
+                                        _lib.dptr(status), _lib.dptr(ws), ws_bytes, _lib.stream_handle()),
+               "mr_ties_select_build")
+    if defer_status:
+        return cut, status
+    if bool((status.cpu() != 1).any()):
+        args = (_lib.dptr(base_model, torch.float32), parr, K, d, None, int(k_cnt), _lib.dptr(cut), _lib.dptr(status),
+                _lib.dptr(ws), ws_bytes, _lib.stream_handle())
+        _lib.check(lib.mr_ties_select_exact(*args), "mr_ties_select_exact")
+        st = status.cpu()
+        if bool((st != 1).any()):
+            raise _lib.MergeRecLibraryError(f"TIES select failed with status {st.tolist()}")
+        _build(base_model, rows, cut, mode, w=w, G=G, seg_end=seg_end, seg_group=seg_group, out=out, ldo=ldo)
+    return cut
+
+
 def get_ties_vectors(base_model: FlattenedModel, models: List[FlattenedModel], density: float,
                      return_masks: bool = False, **__):
     """(K, d) TIES vectors: per model the trimmed update where it agrees with the elected sign, divided by the
@@ -85,8 +120,12 @@ def get_ties_vectors(base_model: FlattenedModel, models: List[FlattenedModel], d
     the cut keys."""
     rows = as_rows(models)
     K, d = len(rows), base_model.numel()
-    cut = ties_select(base_model, rows, density)
     That = alloc_rows(K, d, base_model.device)
+    if not return_masks:
+        # one pass over the data: speculative build + exact cut + fix-up of the mis-decided columns
+        select_build(base_model, rows, ties_topk_count(density, d), _lib.MR_TIES_VECTORS, That, ldo=max(That.stride(0), d))
+        return That
+    cut = ties_select(base_model, rows, density)
     trim = elect = None
     if return_masks:
         trim = torch.empty((K, d), dtype=torch.uint8, device=base_model.device)
@@ -122,11 +161,14 @@ def merge_ties_lambda(base_model: FlattenedModel, models: List[FlattenedModel], 
     weight_learning/module/layer_wise.py:76-82.  ``w`` is (G, K) fp32 on the device."""
     rows = as_rows(models)
     K = len(rows)
-    if cut is None:
-        cut = ties_select(base_model, rows, density)
     if out is None:
         out = torch.empty_like(base_model)
     assert w.dtype == torch.float32 and w.is_contiguous() and w.shape[-1] == K
+    if cut is None:
+        # one pass over the data (select folded into the fused build)
+        select_build(base_model, rows, ties_topk_count(density, base_model.numel()), _lib.MR_TIES_FUSED_MERGE, out, w=w,
+                     G=w.numel() // K, seg_end=seg_end, seg_group=seg_group)
+        return out
     _build(base_model, rows, cut, _lib.MR_TIES_FUSED_MERGE, w=w, G=w.numel() // K, seg_end=seg_end,
            seg_group=seg_group, out=out)
     return out

@@ -187,3 +187,96 @@ def test_localize_and_stitch_module(monkeypatch):
     sd = mod.get_state_dict()
     got = np.concatenate([sd[k].detach().cpu().numpy().reshape(-1) for k in keys])
     assert_bit_equal(got, want, "merged state_dict through the L&S module")
+
+
+# ------------------------------------------------------------------------------------------ one-pass select + build
+def _spec_case(K, d, seed, quantize=0.0, density=0.2, shift=0):
+    from mergerec_b200 import _lib
+    from mergerec_b200.merger.algorithms.ties import _build, select_build, select_kth_largest
+    from mergerec_b200.merger.layout import alloc_rows
+    base, models = synth.make_flat(d, K, seed=seed, quantize=quantize)
+    if shift:      # pointers off the 16-byte grid: the scalar-load instantiation
+        buf = torch.empty((K + 1) * (d + 8) + 8, dtype=torch.float32, device="cuda")
+        views = [buf[i * (d + 8) + shift: i * (d + 8) + shift + d] for i in range(K + 1)]
+        views[0].copy_(dev(base))
+        for v, m in zip(views[1:], models):
+            v.copy_(dev(m))
+        tb, tm = views[0], views[1:]
+    else:
+        tb, tm = dev(base), [dev(m) for m in models]
+    k_cnt = ties_topk_count(density, d)
+    cut = select_kth_largest(tb, tm, k_cnt)
+    want = alloc_rows(K, d, "cuda")
+    _build(tb, tm, cut, _lib.MR_TIES_VECTORS, out=want, ldo=max(want.stride(0), d))
+    got = alloc_rows(K, d, "cuda")
+    got.fill_(float("nan"))
+    cut2, status = select_build(tb, tm, k_cnt, _lib.MR_TIES_VECTORS, got, ldo=max(got.stride(0), d), defer_status=True)
+    return tb, tm, k_cnt, cut, want, got, cut2, status
+
+
+@pytest.mark.parametrize("K,d,quantize", [(1, 4096, 0.0), (2, 100_003, 0.0), (3, 262_144 + 17, 0.0), (5, 300_031, 0.0),
+                                          (8, 1_000_003, 0.0), (8, 524_288, 2.5e-4), (16, 200_001, 0.0), (4, 37, 0.0),
+                                          (7, 2_000_029, 1e-5)])
+def test_select_build_equals_select_then_build(K, d, quantize):
+    """`mr_ties_select_build` (speculative build + exact cut + fix-up) == `mr_ties_select` + `mr_ties_build`, bit for bit:
+    cut keys and every element of the (K, d) TIES vectors, including the interleaved-order tail columns (K >= 5), a partial
+    last quad, and inputs with many equal magnitudes around the cut."""
+    _, _, _, cut, want, got, cut2, status = _spec_case(K, d, seed=300 + K, quantize=quantize)
+    if status.cpu().tolist() != [1] * K:
+        pytest.skip(f"sampled bracket missed on this input (status {status.cpu().tolist()}): the public path falls back")
+    assert torch.equal(cut2, cut)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+
+
+@pytest.mark.parametrize("shift", [1, 2, 3])
+def test_select_build_unaligned_pointers(shift):
+    _, _, _, cut, want, got, cut2, status = _spec_case(8, 150_001, seed=77, shift=shift)
+    assert status.cpu().tolist() == [1] * 8
+    assert torch.equal(cut2, cut) and torch.equal(got.view(torch.int32), want.view(torch.int32))
+
+
+@pytest.mark.parametrize("density", [0.0, 1e-7, 0.01, 0.5, 0.999, 1.0])
+def test_select_build_edge_densities(density):
+    _, _, _, cut, want, got, cut2, status = _spec_case(5, 70_001, seed=5, density=density)
+    if status.cpu().tolist() == [1] * 5:
+        assert torch.equal(cut2, cut) and torch.equal(got.view(torch.int32), want.view(torch.int32))
+
+
+def test_select_build_falls_back_on_massive_ties():
+    """All updates equal in magnitude: the sampled bracket cannot isolate the cut; the public entry points must notice and
+    still return the exact answer (exact select + plain build)."""
+    d, K = 300_000, 3
+    base = np.zeros(d, np.float32)
+    models = [np.full(d, 0.5, np.float32) * (1 if k % 2 == 0 else -1) for k in range(K)]
+    got = get_ties_vectors(dev(base), [dev(m) for m in models], 0.2)
+    want = orc.ties_vectors(base, models, 0.2)
+    assert_bit_equal(host(got)[:, :d], want, "massive ties")
+
+
+@pytest.mark.parametrize("recformer,K", [(False, 3), (True, 8), (False, 5)])
+def test_fused_select_build_merge_layerwise(recformer, K):
+    """FUSED_MERGE through the one-pass kernel: layer-wise lambdas over a state_dict-shaped block table (blocks that
+    straddle quads, blocks shorter than a quad, per-block interleaved tails) == materialised T-hat + lambda merge."""
+    from mergerec_b200 import _lib
+    from mergerec_b200.merger.algorithms._common import merge_axpy
+    shapes = synth.tiny_shapes(layers=3, hidden=40, ffn=72, vocab=301, max_pos=18, recformer=recformer)
+    layout = FlatLayout.from_shape_dict(shapes)
+    d = layout.d
+    base, models = synth.make_flat(d, K, seed=900 + K)
+    tb, tm = dev(base), [dev(m) for m in models]
+    seg_end, seg_group, keys = layout.device_blocks(True, tb.device)
+    rng = np.random.Generator(np.random.PCG64(3))
+    w = dev(rng.uniform(0.1, 0.5, size=(len(keys), K)).astype(np.float32))
+    That = get_ties_vectors(tb, tm, 0.2)
+    two_step = merge_axpy(tb, list(That.unbind(0)), w, _lib.MR_ORDER_SUM_FIRST, False, seg_end, seg_group)
+    fused = merge_ties_lambda(tb, tm, 0.2, w, seg_end, seg_group)
+    assert torch.equal(fused.view(torch.int32), two_step.view(torch.int32))
+    cut = ties_select(tb, tm, 0.2)
+    fused_given_cut = merge_ties_lambda(tb, tm, 0.2, w, seg_end, seg_group, cut=cut)
+    assert torch.equal(fused_given_cut.view(torch.int32), two_step.view(torch.int32))
+    # task-wise lambdas (one block)
+    w1 = dev(rng.uniform(0.1, 0.5, size=(1, K)).astype(np.float32))
+    two_step1 = merge_axpy(tb, list(That.unbind(0)), w1, _lib.MR_ORDER_SUM_FIRST, False)
+    assert torch.equal(merge_ties_lambda(tb, tm, 0.2, w1).view(torch.int32), two_step1.view(torch.int32))
+    oT = orc.ties_vectors(base, models, 0.2)
+    assert_bit_equal(host(That)[:, :d], oT, "one-pass TIES vectors vs oracle")

@@ -1,0 +1,8 @@
+set -x
+python -m pytest tests/test_ties_gpu.py -m gpu -q --maxfail=5 > gpurun_out/r2_pytest6.log 2>&1; echo "pytest rc=$?"
+for m in 2 3 4; do
+MR_TIES_SPEC_MINB=$m python bench.py --workload ties_cfg2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_ties_m$m.json 2> gpurun_out/r2_bench_ties_m$m.err; echo "rc=$?"
+done
+tail -3 gpurun_out/r2_pytest6.log
+export MR_BENCH_NO_GRAPH=1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/r2_launches_ties2.csv python bench.py --workload ties_cfg2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_l2.log 2>&1
