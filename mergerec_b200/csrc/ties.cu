@@ -756,7 +756,7 @@ struct SpecState {     // per model, staged in shared memory
 template <int K, int MODE, bool VEC>
 __global__ void __launch_bounds__(kTiesThreads, K <= 8 ? 2 : 1)
 ties_spec_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const TiesState* __restrict__ st,
-                 const u64* __restrict__ mid_dev, PassCounters pc, BuildArgs a) {
+                 const u64* __restrict__ mid_dev, PassCounters pc, BuildArgs a, int blocked_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [FUSED_MERGE tables] | SpecState[K] | ge[K] u32 | lom[K] i32 | span[K] u32 | cnt[K][blockDim] u32
     // (the bracket words and the per-thread candidate counters live in shared memory, not in registers: the hot loop
@@ -850,14 +850,23 @@ ties_spec_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (threadIdx.x == 0)
-            for (int st_ = 0; st_ < kSpecStages; ++st_) {
-                const int64_t tile = (int64_t)st_ * gridDim.x + blockIdx.x;
-                if (tile < n_tiles) issue_tile(tile, st_);
-            }
     }
+    // VECTORS: tile `it` of CTA c is it * grid + c (grid-stride).  FUSED_MERGE: CTA c owns the contiguous tiles
+    // [c * per, (c + 1) * per), so a thread's successive quads are 1024 columns apart and mostly stay inside one
+    // tensor -- the cached lambda row / block bounds keep hitting (with a grid stride every quad lands in another
+    // tensor and pays the block lookup: measured 1.9 vs 1.5 ms)
+    const int64_t tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    auto tile_of = [&](int64_t it) -> int64_t {
+        if (blocked_tiles) return it < tiles_per_cta ? (int64_t)blockIdx.x * tiles_per_cta + it : n_tiles;
+        return it * gridDim.x + blockIdx.x;
+    };
+    if (VEC && threadIdx.x == 0)
+        for (int st_ = 0; st_ < kSpecStages; ++st_) {
+            const int64_t tile = tile_of(st_);
+            if (tile < n_tiles) issue_tile(tile, st_);
+        }
     for (int64_t it = 0;; ++it) {
-        const int64_t tile = it * gridDim.x + blockIdx.x;
+        const int64_t tile = tile_of(it);
         if (tile >= n_tiles) break;
         const int64_t q = tile * kTiesThreads + threadIdx.x;
         const int64_t j0 = q << 2;
@@ -878,7 +887,7 @@ ties_spec_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
             }
             __syncthreads();   // every thread holds its quad in registers: the stage can be refilled
             if (threadIdx.x == 0) {
-                const int64_t next = (it + kSpecStages) * gridDim.x + blockIdx.x;
+                const int64_t next = tile_of(it + kSpecStages);
                 if (next < n_tiles) issue_tile(next, stage);
             }
             if (q >= nq_hot) continue;
@@ -949,42 +958,46 @@ ties_spec_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
                     for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wrow[k], res[c][k]);
                     r[c] = __fadd_rn(bx[c], sum_seq<K>(prod));
                 }
-            } else if (j0 >= cur_lo && j0 + 4 <= cur_hi) {   // hot: the whole quad in the sequential part of one block
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float prod[K];
-#pragma unroll
-                    for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wrow[k], res[c][k]);
-                    r[c] = __fadd_rn(bx[c], sum_seq<K>(prod));
-                }
             } else {
-                // a block boundary (or a block's interleaved tail) inside or before this quad: per-column lookup,
-                // then remember the block the quad ended in
-                if (!(j0 < fs.end[hint] && (hint == 0 || j0 >= fs.end[hint - 1]))) {
-                    int lo_ = 0, hi_ = fs.P - 1;
-                    while (lo_ < hi_) { const int mid_ = (lo_ + hi_) >> 1; if (fs.end[mid_] > j0) hi_ = mid_; else lo_ = mid_ + 1; }
-                    hint = lo_;
+                if (!(j0 >= cur_lo && j0 + 4 <= cur_hi)) {
+                    // left the cached block: find the block of j0 (binary search in shared memory, last hit first) and
+                    // cache its sequential range and lambda row
+                    if (!(j0 < fs.end[hint] && (hint == 0 || j0 >= fs.end[hint - 1]))) {
+                        int lo_ = 0, hi_ = fs.P - 1;
+                        while (lo_ < hi_) { const int mid_ = (lo_ + hi_) >> 1; if (fs.end[mid_] > j0) hi_ = mid_; else lo_ = mid_ + 1; }
+                        hint = lo_;
+                    }
+                    const int64_t beg = hint ? fs.end[hint - 1] : 0;
+                    const int64_t n = fs.end[hint] - beg;
+                    cur_lo = beg;
+                    cur_hi = (K >= 5) ? beg + (n & ~(int64_t)31) : fs.end[hint];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) wrow[k] = fs.w[fs.grp[hint] * K + k];
                 }
-                int pseg = hint;
+                if (j0 >= cur_lo && j0 + 4 <= cur_hi) {   // hot: the whole quad in the sequential part of one block
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    while (j0 + c >= fs.end[pseg]) ++pseg;
-                    const int64_t beg = pseg ? fs.end[pseg - 1] : 0;
-                    const int64_t n = fs.end[pseg] - beg;
-                    const bool tail = (K >= 5) && ((j0 + c - beg) >= (n & ~(int64_t)31));
-                    const float* wr = fs.w + fs.grp[pseg] * K;
-                    float prod[K];
+                    for (int c = 0; c < 4; ++c) {
+                        float prod[K];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wr[k], res[c][k]);
-                    r[c] = __fadd_rn(bx[c], torch_sum_dim0<K>(prod, tail));
+                        for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wrow[k], res[c][k]);
+                        r[c] = __fadd_rn(bx[c], sum_seq<K>(prod));
+                    }
+                } else {
+                    // a block boundary or a block's interleaved tail inside this quad: per-column lookup
+                    int pseg = hint;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        while (j0 + c >= fs.end[pseg]) ++pseg;
+                        const int64_t beg = pseg ? fs.end[pseg - 1] : 0;
+                        const int64_t n = fs.end[pseg] - beg;
+                        const bool tail = (K >= 5) && ((j0 + c - beg) >= (n & ~(int64_t)31));
+                        const float* wr = fs.w + fs.grp[pseg] * K;
+                        float prod[K];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) prod[k] = __fmul_rn(wr[k], res[c][k]);
+                        r[c] = __fadd_rn(bx[c], torch_sum_dim0<K>(prod, tail));
+                    }
                 }
-                hint = pseg;
-                const int64_t beg = pseg ? fs.end[pseg - 1] : 0;
-                const int64_t n = fs.end[pseg] - beg;
-                cur_lo = beg;
-                cur_hi = (K >= 5) ? beg + (n & ~(int64_t)31) : fs.end[pseg];
-#pragma unroll
-                for (int k = 0; k < K; ++k) wrow[k] = fs.w[fs.grp[pseg] * K + k];
             }
             float* o = a.out + j0;
             if (VEC) stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
@@ -1037,9 +1050,11 @@ static __global__ void ties_mid_kernel(const TiesState* __restrict__ st, int K, 
 }
 
 // One column rebuilt with the exact cuts (scalar accesses).
+// VECTORS: a model that is trimmed under the provisional AND under the exact cut holds 0 in this column before and after
+// the fix-up, so only the rows with key >= either[k] = min(provisional, exact cut) are written (about K/5 + 1 of K).
 template <int K, int MODE>
 __device__ __forceinline__ void ties_patch_column(const float* __restrict__ base, const PtrPack<K>& models, int64_t d, int64_t j,
-                                                  const u64 (&cut)[K], bool lo_ok, const BuildArgs& a) {
+                                                  const u64 (&cut)[K], const u64 (&either)[K], bool lo_ok, const BuildArgs& a) {
     float x[K], res[K];
     uint32_t tb, eb;
     const float b = base[j];
@@ -1050,7 +1065,10 @@ __device__ __forceinline__ void ties_patch_column(const float* __restrict__ base
         if (flat_tail) ties_column<K, TIES_MODE_VECTORS, true>(x, b, j, cut, lo_ok, nullptr, res, tb, eb);
         else ties_column<K, TIES_MODE_VECTORS, false>(x, b, j, cut, lo_ok, nullptr, res, tb, eb);
 #pragma unroll
-        for (int k = 0; k < K; ++k) a.out[(int64_t)k * a.ldo + j] = res[k];
+        for (int k = 0; k < K; ++k) {
+            const uint32_t mag = __float_as_uint(__fsub_rn(x[k], b)) & 0x7FFFFFFFu;
+            if (ties_key(mag, j) >= either[k]) a.out[(int64_t)k * a.ldo + j] = res[k];
+        }
     } else {
         // the election's sums run over the K models of ONE column: their order depends on the position in the flat
         // vector (VECTORS semantics of get_ties_vectors: tail = last d mod 32 columns of the whole vector)
@@ -1080,11 +1098,14 @@ __global__ void __launch_bounds__(256)
 ties_patch_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const u64* __restrict__ cut_dev,
                   const u64* __restrict__ mid_dev, const int32_t* __restrict__ status, const uint32_t* __restrict__ cand_cnt,
                   const u64* __restrict__ cand_keys, int cand_cap, int n_lists, BuildArgs a) {
-    u64 cut[K];
+    u64 cut[K], either[K], zero[K];
     bool lo_ok = true, ok = true;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         cut[k] = cut_dev[k];
+        const u64 m = mid_dev[k];
+        either[k] = cut[k] < m ? cut[k] : m;
+        zero[k] = 0;
         lo_ok = lo_ok && ((uint32_t)(cut[k] >> 32) >= (27u << 23));
         ok = ok && status[k] == TIES_ST_DONE;
     }
@@ -1101,12 +1122,12 @@ ties_patch_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, 
             const u64 key = keys[e];
             if (key >= lo && key < hi) {
                 const int64_t j = (int64_t)(0xFFFFFFFFu - (uint32_t)key);
-                if (j < hot_end) ties_patch_column<K, MODE>(base, models, d, j, cut, lo_ok, a);
+                if (j < hot_end) ties_patch_column<K, MODE>(base, models, d, j, cut, either, lo_ok, a);
             }
         }
     }
     if (blockIdx.x == 0 && blockIdx.y == 0)
-        for (int64_t j = hot_end + threadIdx.x; j < d; j += blockDim.x) ties_patch_column<K, MODE>(base, models, d, j, cut, lo_ok, a);
+        for (int64_t j = hot_end + threadIdx.x; j < d; j += blockDim.x) ties_patch_column<K, MODE>(base, models, d, j, cut, zero, lo_ok, a);   // cold columns: never built before, write every row
 }
 
 // ---- per-mode launchers of the build kernel ---------------------------------------------------------------------------
@@ -1201,7 +1222,9 @@ static int ties_spec_launch_mode(const SpecLaunch& L, int phase, int* blocks) {
                 *blocks = b;
                 return MR_OK;
             }
-            kern<<<*blocks, kTiesThreads, L.smem, L.stream>>>(L.base, pack, L.d, L.st, L.mid, L.pc, L.a);
+            static const int blocked_env = []() { const char* e = getenv("MR_TIES_FUSED_BLOCKED"); return e ? atoi(e) : -1; }();
+            const int blocked = blocked_env >= 0 ? blocked_env : (MODE == TIES_MODE_FUSED_MERGE ? 1 : 0);
+            kern<<<*blocks, kTiesThreads, L.smem, L.stream>>>(L.base, pack, L.d, L.st, L.mid, L.pc, L.a, blocked);
         } else {
             dim3 grid(64, (unsigned)KK);
             ties_patch_kernel<KK, MODE><<<grid, 256, 0, L.stream>>>(L.base, pack, L.d, L.cut, L.mid, L.status, L.pc.cand_cnt,
@@ -1240,9 +1263,9 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // alone at a third of the occupancy after the others have finished
 static int ties_pass_blocks(int K) { return sm_count() * (K <= 8 ? 3 : 2); }
 
-static int64_t ties_sample_stride(int64_t d) {
+static int64_t ties_sample_stride(int64_t d, int64_t sample_quads = kTiesSampleQuads) {
     const int64_t nq = (d + 3) >> 2;
-    const int64_t s = nq / kTiesSampleQuads;
+    const int64_t s = nq / sample_quads;
     return s < 1 ? 1 : s;
 }
 
@@ -1471,12 +1494,20 @@ extern "C" int mr_ties_select_build(const float* base, const float* const* model
     const TiesWs L = ties_layout(ws, d, K);
     ties_init_kernel<<<1, 32, 0, st>>>(L.st, K, reinterpret_cast<u64*>(cut), status, k_cnt, d);
     MR_CUDA_LAUNCH_CHECK("mr_ties_select_build(init)");
-    const int64_t stride = ties_sample_stride(d);
-    const int64_t n_s = ties_sample_count(d, stride);
-    int64_t r_hi, r_lo;
-    ties_sample_ranks(d, k_cnt, n_s, &r_hi, &r_lo);
+    // Three sample passes.  The first two walk the select's sparse sample (~131 K quads) and bracket the cut to about
+    // 0.75 % of the keys; the third walks a 4x denser sample but only histograms the keys inside that bracket (a rare
+    // path, sparse per-CTA histograms) and halves it.  (Strided 16-byte picks cost a 32-byte DRAM sector each and run at
+    // ~20 G sectors/s: 8x / 16x / 32x samples were measured slower overall, 3.02 / 3.14 / 3.67 / 4.59 ms per cfg-2 step.)  The number of columns the fix-up has to rebuild (scattered
+    // 32-byte accesses, 17 per column) and the number of keys the full pass collects are both proportional to the
+    // error of the sample quantile, i.e. to 1 / sqrt(sample size).
+    static const int64_t dense_quads = []() { const char* e = getenv("MR_TIES_SPEC_SAMPLE_QUADS"); return e ? atoll(e) : 4 * kTiesSampleQuads; }();
     MR_DISPATCH_K(K, {
-        for (int it = 0; it < 2; ++it) {
+        for (int it = 0; it < 3; ++it) {
+            const int64_t stride = ties_sample_stride(d, it < 2 ? kTiesSampleQuads : dense_quads);
+            if (it == 2 && stride >= ties_sample_stride(d)) break;     // small vectors: the sparse sample is already everything
+            const int64_t n_s = ties_sample_count(d, stride);
+            int64_t r_hi, r_lo;
+            ties_sample_ranks(d, k_cnt, n_s, &r_hi, &r_lo);
             rc = ties_launch_pass<KK>(base, models, d, nullptr, stride, 0, L, st);
             if (rc != MR_OK) return rc;
             ties_pick_kernel<<<KK, kTiesBins, 0, st>>>(L.st, L.hist, L.above, r_hi, r_lo, 0, status);

@@ -154,7 +154,8 @@ def merge_ties(base_model: FlattenedModel, models: List[FlattenedModel], weights
 
 def merge_ties_lambda(base_model: FlattenedModel, models: List[FlattenedModel], density: float, w: torch.Tensor,
                       seg_end: Optional[torch.Tensor] = None, seg_group: Optional[torch.Tensor] = None,
-                      cut: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> FlattenedModel:
+                      cut: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                      one_pass: bool = False) -> FlattenedModel:
     """Extension: ``get_ties_vectors`` followed by the (task- or layer-wise) lambda merge in ONE pass that never
     materialises the (K, d) TIES vectors.  Bit-identical to
     ``base + (w[g][:, None] * get_ties_vectors(...)).sum(0)`` evaluated block by block like
@@ -164,11 +165,15 @@ def merge_ties_lambda(base_model: FlattenedModel, models: List[FlattenedModel], 
     if out is None:
         out = torch.empty_like(base_model)
     assert w.dtype == torch.float32 and w.is_contiguous() and w.shape[-1] == K
-    if cut is None:
-        # one pass over the data (select folded into the fused build)
+    if cut is None and one_pass:
+        # one pass over the data (select folded into the fused build).  Measured on K = 8 BLaIR-base: 2.6 ms against
+        # 2.1-2.4 ms for select + fused build -- this mode's pass is instruction-bound (1.13 G warp-instructions, 26 % of
+        # the warp samples waiting on instruction fetch), so the two-pass form stays the default here
         select_build(base_model, rows, ties_topk_count(density, base_model.numel()), _lib.MR_TIES_FUSED_MERGE, out, w=w,
                      G=w.numel() // K, seg_end=seg_end, seg_group=seg_group)
         return out
+    if cut is None:
+        cut = ties_select(base_model, rows, density)
     _build(base_model, rows, cut, _lib.MR_TIES_FUSED_MERGE, w=w, G=w.numel() // K, seg_end=seg_end,
            seg_group=seg_group, out=out)
     return out

@@ -269,14 +269,16 @@ def test_fused_select_build_merge_layerwise(recformer, K):
     w = dev(rng.uniform(0.1, 0.5, size=(len(keys), K)).astype(np.float32))
     That = get_ties_vectors(tb, tm, 0.2)
     two_step = merge_axpy(tb, list(That.unbind(0)), w, _lib.MR_ORDER_SUM_FIRST, False, seg_end, seg_group)
-    fused = merge_ties_lambda(tb, tm, 0.2, w, seg_end, seg_group)
+    fused = merge_ties_lambda(tb, tm, 0.2, w, seg_end, seg_group, one_pass=True)
     assert torch.equal(fused.view(torch.int32), two_step.view(torch.int32))
+    assert torch.equal(merge_ties_lambda(tb, tm, 0.2, w, seg_end, seg_group).view(torch.int32), two_step.view(torch.int32))
     cut = ties_select(tb, tm, 0.2)
     fused_given_cut = merge_ties_lambda(tb, tm, 0.2, w, seg_end, seg_group, cut=cut)
     assert torch.equal(fused_given_cut.view(torch.int32), two_step.view(torch.int32))
     # task-wise lambdas (one block)
     w1 = dev(rng.uniform(0.1, 0.5, size=(1, K)).astype(np.float32))
     two_step1 = merge_axpy(tb, list(That.unbind(0)), w1, _lib.MR_ORDER_SUM_FIRST, False)
+    assert torch.equal(merge_ties_lambda(tb, tm, 0.2, w1, one_pass=True).view(torch.int32), two_step1.view(torch.int32))
     assert torch.equal(merge_ties_lambda(tb, tm, 0.2, w1).view(torch.int32), two_step1.view(torch.int32))
     oT = orc.ties_vectors(base, models, 0.2)
     assert_bit_equal(host(That)[:, :d], oT, "one-pass TIES vectors vs oracle")
