@@ -929,21 +929,21 @@ class CollabStepCfg3(Workload):
 class TiesSharded(TiesCfg2):
     """SURVEY.md section 8(e), merger row: the TIES merge of BASELINE config 2 with the flat vector SHARDED over the
     ranks (d/G columns per GPU, 32-column aligned).  One step = global trim threshold (per-slice order statistic, then two
-    windowed radix levels of `mr_ties_mag_hist` with one NCCL all-reduce of K x 2049 int64 each + two all-gathers of K values), TIES build of
+    sampled-bracket select `mr_ties_select_dist`: 4 all-reduces of 33 KB + 1 all-gather of 262 KB per rank, no host sync), TIES build of
     the local slice, task-wise lambda merge of the local slice.  Strong scaling: the whole job's algorithmic bytes
     ((2K+1) + (K+2)) * d * 4 divided by the slowest rank's time.  Results are bit-identical to the single-GPU merge
     (tests/test_sharded_merger_gpu.py)."""
 
     name = "ties_sharded"
     scaling = "strong"
-    launches_per_step = 14  # per-slice select (10), 2 x mag_hist, build, merge (plus torch's tiny histogram-walk ops and the collectives)
+    launches_per_step = 14  # init, 2 x sample pass, 5 x pick, full pass, 2 x cand_hist, compact, final, build, merge (+ NCCL's)
 
     def config(self):
         return {"workload": "TIES (density 0.2) of K=8 BLaIR-base models, flat vector sharded d/G per GPU; global trim via "
                             "all-reduced radix histograms; local build + task-wise lambda merge",
                 "K": self.K, "d": self.d, "density": 0.2, "l2": "per-rank inputs (4.5 GB / G) exceed L2 for G <= 8",
-                "parallelism": "flat dimension sharded d/G per GPU (strong scaling); per select level one all-reduce of "
-                               "K x 2049 int64 + small all-gathers; the same code path without collectives on 1 GPU"}
+                "parallelism": "flat dimension sharded d/G per GPU (strong scaling); per select 4 all-reduces of the K x 1024 "
+                               "counters + 1 all-gather of the survivors; the same code path without collectives on 1 GPU"}
 
     def setup(self):
         import torch.distributed as dist
@@ -966,8 +966,10 @@ class TiesSharded(TiesCfg2):
         self.out = torch.empty(hi - lo, dtype=torch.float32, device=self.device)
 
     def _select(self):
+        """Stream-ordered device-side select (status checked after the timed loop, like the single-GPU step)."""
         from mergerec_b200.merger.sharded import sharded_select
-        return sharded_select(self.base, self.models, int(0.2 * self.d), self.d, None, self.group)
+        cut, self._status = sharded_select(self.base, self.models, int(0.2 * self.d), self.d, None, self.group, defer_status=True)
+        return cut
 
     def _build(self, cut):
         from mergerec_b200 import _lib
@@ -1008,30 +1010,20 @@ class TiesSharded(TiesCfg2):
 
     def roofline(self, peaks):
         from bench import event_time_ms
-        from mergerec_b200.merger.sharded import CudaKernels
         n, K = self.hi - self.lo, self.K
         cut = self._cut                      # rank 0 only from here on: kernels, no collectives
-        hist = torch.zeros((K, 2048), dtype=torch.int64, device=self.device)
-        above = torch.zeros(K, dtype=torch.int64, device=self.device)
-        lo = ((cut >> 32) - 64).clamp(min=0).to(torch.int32)                  # the first window of this (iid) workload
-        sh = torch.zeros(K, dtype=torch.int32, device=self.device)
-        ms_hist = event_time_ms(lambda: CudaKernels.mag_hist(self.base, self.models, None, lo, sh, hist, above), 10)
-        lo_w = ((cut >> 32) - (1 << 17)).clamp(min=0).to(torch.int32)         # a wide window (shards with different statistics)
-        sh_w = torch.full((K,), 7, dtype=torch.int32, device=self.device)
-        ms_hist_wide = event_time_ms(lambda: CudaKernels.mag_hist(self.base, self.models, None, lo_w, sh_w, hist, above), 10)
         ms_select = event_time_ms(self._select, 5) if self.world == 1 else None
         ms_build = event_time_ms(lambda: self._build(cut), 10)
         ms_merge = event_time_ms(self._merge_only, 10)
-        b_build, b_hist, b_merge = (2 * K + 1) * n * 4, (K + 1) * n * 4, (K + 2) * n * 4
+        b_build, b_merge = (2 * K + 1) * n * 4, (K + 2) * n * 4
         ach = b_build / GB / (ms_build * 1e-3)
         return {"bound": "hbm", "kernel": "mr::ties_build_kernel<8, VECTORS, vec4> on this rank's slice",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": ms_build,
                 "algorithmic_bytes_per_launch": b_build,
                 "other_kernels": {
-                    "mag_hist_kernel (one windowed radix level)": {"ms": ms_hist, "GB/s": b_hist / GB / (ms_hist * 1e-3), "bytes": b_hist},
-                    "mag_hist_kernel, window 2^18 bit patterns wide (1.3 % of the elements inside)": {"ms": ms_hist_wide, "GB/s": b_hist / GB / (ms_hist_wide * 1e-3)},
-                    "sharded select (per-slice order statistic + windowed level(s) + all-reduce + tie scan)": {"ms": ms_select},
+                    "device-side sharded select (mr_ties_select_dist: 2 sample passes + 1 full pass + finish; timed without "
+                    "collectives, 1 GPU only)": {"ms": ms_select},
                     "lambda merge of the slice (merge_kernel)": {"ms": ms_merge, "GB/s": b_merge / GB / (ms_merge * 1e-3), "bytes": b_merge}}}
 
     def extra(self):

@@ -302,6 +302,22 @@ int mr_ties_mag_hist(const float* base, const float* const* models, int K, int64
                      const int32_t* shift, int64_t* hist, int64_t* above, uint32_t* cand, uint32_t* cand_count,
                      int cand_cap, mr_stream_t stream);
 
+/* Sharded select, stream-ordered (no host synchronisation): the sampled-bracket algorithm of mr_ties_select with every
+ * counter summed over the ranks.  Keys carry GLOBAL indices (j_off + local index), so the cut is the single-GPU cut bit
+ * for bit.  The caller runs phases 0..5 in order on every rank and applies, after each phase, the collective named
+ * here to the workspace regions mr_ties_dist_layout reports (the library never communicates itself):
+ *   phases 0-3: all-reduce(sum, as int32 words) of the counters region;  phase 4: all-gather of the survivors region;
+ *   phase 5 takes the gathered survivors (`world` regions, rank-major; world == 1: the rank's own region) and writes
+ *   cut_local (for mr_ties_build on this rank's slice), optionally cut_global, and status (mr_ties_status).
+ * Requires 0 < k_cnt < d_global < 2^32; ws: mr_ties_workspace_bytes(max(d_local, 1), K) + 256 bytes.
+ * ref: merger/algorithms/ties.py:14-23 (top-k over the WHOLE vector); SURVEY.md section 8(e) merger row. */
+int mr_ties_dist_layout(int64_t d_local, int K, int64_t* counters_off, int64_t* counters_bytes, int64_t* survivors_off,
+                        int64_t* survivors_bytes);
+int mr_ties_select_dist(const float* base, const float* const* models, int K, int64_t d_local, int64_t j_off,
+                        int64_t d_global, const float* w, int64_t k_cnt, int phase, const void* gathered, int world,
+                        uint64_t* cut_local, uint64_t* cut_global, int32_t* status, void* ws, int64_t ws_bytes,
+                        mr_stream_t stream);
+
 /* DARE merge with explicit keep masks.                       ref: merger/algorithms/dare.py:9-31 (+ torch dropout)
  * out[j] = base[j] (+) sum in order k of fl( fl(w[k] * (models[k][j] - base[j])) * (keep[k, j] ? scale : 0) ),
  * scale = 1 / (1 - p) in fp32.  keep: dev uint8, K rows of leading dimension ld_keep (1 = kept).  w: dev K floats. */

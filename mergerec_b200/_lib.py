@@ -53,6 +53,8 @@ SIGNATURES = {
     "mr_pcb_workspace_bytes": ([_i32], _i64),
     "mr_pcb_vectors": ([_vp, _vp, _i32, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "mr_ties_mag_hist": ([_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp], C.c_int),
+    "mr_ties_dist_layout": ([_i64, _i32, _vp, _vp, _vp, _vp], C.c_int),
+    "mr_ties_select_dist": ([_vp, _vp, _i32, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "mr_merge_dare": ([_vp, _vp, _i32, _i64, _vp, _vp, _i64, C.c_float, _vp, _vp], C.c_int),
     "mr_ties_build": ([_vp, _vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp], C.c_int),
 }

@@ -88,6 +88,7 @@ struct PassCounters {
     uint32_t* cand_cnt;  // K * n_threads (COLLECT): one private candidate list per thread and model
     u64* cand_keys;      // K * n_threads * cand_cap
     int cand_cap;
+    int64_t j_off;       // global index of local element 0 (sharded select: keys carry GLOBAL indices); 0 otherwise
 };
 
 // Shared-memory layout of the pass kernel (dynamic): hist[K][bins] u32 | lo[K] hi[K] u64 | shift[K] i32 |
@@ -194,11 +195,11 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
                 /* the few keys outside [lo, hi] (an end magnitude, index on the wrong side) into above / ignore. */ \
                 /* Millions of equal magnitudes overflow the lists: reported, and the exact path takes over.       */ \
                 if (mycnt[K_] < (uint32_t)pc.cand_cap)                          \
-                    pc.cand_keys[((size_t)(K_) * gsz + gtid) * pc.cand_cap + mycnt[K_]] = ties_key((MAG_), (J_)); \
+                    pc.cand_keys[((size_t)(K_) * gsz + gtid) * pc.cand_cap + mycnt[K_]] = ties_key((MAG_), (J_) + pc.j_off); \
                 ++mycnt[K_];                                                    \
             } else if (COLLECT == 2) {                                          \
                 /* exact path (bracket already narrowed to <= cand_cap keys): classify against the 64-bit ends */ \
-                const u64 key_ = ties_key((MAG_), (J_));                        \
+                const u64 key_ = ties_key((MAG_), (J_) + pc.j_off);             \
                 if (key_ < sm.lo[K_]) {                                         \
                     ++nab[K_]; /* below the bracket: not "above", and not collected (the hist kernel cannot see it) */ \
                 } else if (key_ <= sm.hi[K_]) {                                 \
@@ -207,7 +208,7 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
                     ++mycnt[K_];                                                \
                 }                                                               \
             } else {                                                            \
-                ties_pass_edge<K, false>(smem_raw, (MAG_), (J_), (K_), pc.cand_keys, pc.cand_cap); \
+                ties_pass_edge<K, false>(smem_raw, (MAG_), (J_) + pc.j_off, (K_), pc.cand_keys, pc.cand_cap); \
             }                                                                   \
         }                                                                       \
     } while (0)
@@ -455,6 +456,77 @@ ties_final_kernel(TiesState* st, const uint32_t* __restrict__ fin_cnt, const u64
     }
     if (threadIdx.x == 0) {
         cut[k] = s_keys[r - 1];
+        st[k].status = TIES_ST_DONE;
+        status[k] = TIES_ST_DONE;
+    }
+}
+
+// ---- sharded select (flat vector split over ranks): final sort over the survivors of ALL ranks ---------------------------
+// gathered: `world` copies of the [fin_keys (K x cap) | fin_cnt (K, padded)] region, rank-major (what one all-gather of
+// every rank's region leaves).  Keys carry global indices, so the r-th largest of the union is the global cut; each rank
+// then rewrites it for its own slice: an element at the cut magnitude survives iff its GLOBAL index <= the cut's.
+static __global__ void __launch_bounds__(1024)
+ties_final_dist_kernel(TiesState* st, const unsigned char* __restrict__ gathered, int world, size_t region_bytes,
+                       size_t cnt_off, int64_t k_cnt, int64_t j_off, u64* cut_local, u64* cut_global, int32_t* status) {
+    __shared__ u64 s_keys[kTiesFinalCap];
+    __shared__ uint32_t s_base[65];
+    const int k = blockIdx.x;
+    TiesState s = st[k];
+    if (s.status != TIES_ST_SEARCH) {
+        if (threadIdx.x == 0 && s.status == TIES_ST_DONE && cut_global) cut_global[k] = cut_local[k];   // trivial cuts
+        return;
+    }
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int r = 0; r < world && r < 64; ++r) {
+            s_base[r] = tot;
+            tot += reinterpret_cast<const uint32_t*>(gathered + (size_t)r * region_bytes + cnt_off)[k];
+        }
+        s_base[world < 64 ? world : 64] = tot;
+    }
+    __syncthreads();
+    const uint32_t n = s_base[world < 64 ? world : 64];
+    const long long r = (long long)k_cnt - (long long)s.above;
+    int err = 0;
+    if (n > (uint32_t)kTiesFinalCap) err = TIES_ERR_TOO_MANY;
+    else if ((u64)n != s.in_bracket || r < 1 || r > (long long)n) err = TIES_ERR_INCONSISTENT;
+    if (err) {
+        if (threadIdx.x == 0) { st[k].status = err; status[k] = err; }
+        return;
+    }
+    int cap2 = 2;
+    while (cap2 < (int)n) cap2 <<= 1;
+    for (int i = threadIdx.x; i < cap2; i += blockDim.x) s_keys[i] = 0;
+    __syncthreads();
+    for (int rk = 0; rk < world && rk < 64; ++rk) {
+        const u64* keys = reinterpret_cast<const u64*>(gathered + (size_t)rk * region_bytes) + (size_t)k * kTiesFinalCap;
+        const uint32_t c = s_base[rk + 1] - s_base[rk];
+        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) s_keys[s_base[rk] + i] = keys[i];
+    }
+    __syncthreads();
+    for (int size = 2; size <= cap2; size <<= 1) {
+        for (int strd = size >> 1; strd > 0; strd >>= 1) {
+            for (int i = threadIdx.x; i < cap2 / 2; i += blockDim.x) {
+                const int a = 2 * i - (i & (strd - 1));
+                const int b = a + strd;
+                const bool desc = ((a & size) == 0);
+                const u64 x = s_keys[a], y = s_keys[b];
+                if ((x < y) == desc) { s_keys[a] = y; s_keys[b] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        const u64 g = s_keys[r - 1];
+        if (cut_global) cut_global[k] = g;
+        // local form: same magnitude, index limit shifted into this rank's coordinates
+        const u64 mag = g >> 32;
+        const long long jg = (long long)(0xFFFFFFFFu - (uint32_t)g);      // global index of the last survivor at `mag`
+        const long long jl = jg - (long long)j_off;
+        u64 c;
+        if (jl < 0) c = (mag + 1) << 32;                                   // none of my elements at `mag` survives
+        else c = (mag << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(jl > 0xFFFFFFFFll ? 0xFFFFFFFFll : jl));
+        cut_local[k] = c;
         st[k].status = TIES_ST_DONE;
         status[k] = TIES_ST_DONE;
     }
@@ -1321,15 +1393,18 @@ static TiesWs ties_layout(void* ws, int64_t d, int K) {
 
 template <int K>
 static int ties_launch_pass(const float* base, const float* const* models, int64_t d, const float* w, int64_t stride,
-                            int collect /* 0 none, 1 magnitude window (fast path), 2 exact */, const TiesWs& L, cudaStream_t st) {
+                            int collect /* 0 none, 1 magnitude window (fast path), 2 exact */, const TiesWs& L, cudaStream_t st,
+                            int64_t j_off = 0, bool zero_counters = true) {
     PtrPack<K> pack;
     bool vec = host_aligned16(base);
     for (int k = 0; k < K; ++k) { pack.p[k] = models[k]; vec = vec && host_aligned16(models[k]); }
-    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap};
+    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap, j_off};
     const size_t smem = PassSmem<K>::bytes();
     const int blocks = ties_pass_blocks(K);   // (sample passes too: a smaller grid makes them latency-bound, 70 -> 236 us)
-    cudaError_t e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
-    if (e != cudaSuccess) { set_error("mr_ties_select: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    if (zero_counters) {
+        cudaError_t e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
+        if (e != cudaSuccess) { set_error("mr_ties_select: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
 #define MR_PASS(VEC, W, COLLECT)                                                                               \
     do {                                                                                                       \
         auto kern = ties_pass_kernel<K, VEC, W, COLLECT>;                                                      \
@@ -1466,6 +1541,122 @@ extern "C" int mr_ties_select_exact(const float* base, const float* const* model
     return MR_OK;
 }
 
+// ---- sharded select: the single-GPU sampled-bracket algorithm with the counters summed over the ranks ------------------------
+// The caller (one process per GPU) runs phases 0..5 in order on every rank and, after each phase, applies the collective
+// named below to the workspace regions reported by mr_ties_dist_layout (NCCL through torch.distributed; the library
+// itself never communicates):
+//   phase 0  init, sparse sample pass                      -> all-reduce(sum) of the counters region
+//   phase 1  pick the bracket, second sparse sample pass   -> all-reduce(sum) of the counters region
+//   phase 2  pick, full pass (count + collect), histogram  -> all-reduce(sum) of the counters region
+//   phase 3  pick, second-level histogram of the collected -> all-reduce(sum) of the counters region
+//   phase 4  pick, compact the survivors                   -> all-gather of the survivors region
+//   phase 5  (gathered given) final sort, global and local cut
+// Every decision is taken from all-reduced integers, so all ranks walk the same brackets; keys carry GLOBAL indices
+// (j_off + local index), which makes the result the single-GPU cut bit for bit.
+extern "C" int mr_ties_dist_layout(int64_t d_local, int K, int64_t* counters_off, int64_t* counters_bytes,
+                                   int64_t* survivors_off, int64_t* survivors_bytes) {
+    using namespace mr;
+    MR_REQUIRE(K >= 1 && K <= MR_MAX_K, "mr_ties_dist_layout: K=%d outside [1,%d]", K, MR_MAX_K);
+    MR_REQUIRE(d_local >= 0 && counters_off && counters_bytes && survivors_off && survivors_bytes, "mr_ties_dist_layout: bad argument");
+    char* const fake = reinterpret_cast<char*>((uintptr_t)1 << 20);     // offsets only: nothing is dereferenced
+    const TiesWs L = ties_layout(fake, d_local > 0 ? d_local : 1, K);
+    *counters_off = (int64_t)(reinterpret_cast<char*>(L.hist) - fake);
+    *counters_bytes = (int64_t)L.zero_bytes;
+    *survivors_off = (int64_t)(reinterpret_cast<char*>(L.fin_keys) - fake);
+    *survivors_bytes = (int64_t)(align256((size_t)K * kTiesFinalCap * 8) + align256((size_t)K * 4));
+    return MR_OK;
+}
+
+extern "C" int mr_ties_select_dist(const float* base, const float* const* models, int K, int64_t d_local, int64_t j_off,
+                                   int64_t d_global, const float* w, int64_t k_cnt, int phase, const void* gathered,
+                                   int world, uint64_t* cut_local, uint64_t* cut_global, int32_t* status, void* ws,
+                                   int64_t ws_bytes, mr_stream_t stream) {
+    using namespace mr;
+    MR_REQUIRE(K >= 1 && K <= MR_MAX_K, "mr_ties_select_dist: K=%d outside [1,%d]", K, MR_MAX_K);
+    MR_REQUIRE(d_local >= 0 && j_off >= 0 && d_global >= d_local + j_off && d_global < ((int64_t)1 << 32),
+               "mr_ties_select_dist: need 0 <= j_off, j_off + d_local <= d_global < 2^32");
+    MR_REQUIRE(k_cnt > 0 && k_cnt < d_global, "mr_ties_select_dist: trivial k_cnt is the caller's business");
+    MR_REQUIRE(phase >= 0 && phase <= 5, "mr_ties_select_dist: phase %d outside [0,5]", phase);
+    MR_REQUIRE(cut_local && status && ws, "mr_ties_select_dist: null pointer");
+    MR_REQUIRE(d_local == 0 || (base && models), "mr_ties_select_dist: null input");
+    MR_REQUIRE(world >= 1 && world <= 64, "mr_ties_select_dist: world=%d outside [1,64]", world);
+    const int64_t d_ws = d_local > 0 ? d_local : 1;
+    if (ws_bytes < mr_ties_workspace_bytes(d_ws, K) + (int64_t)align256((size_t)K * 4)) {
+        set_error("mr_ties_select_dist: workspace too small");
+        return MR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const TiesWs L = ties_layout(ws, d_ws, K);
+    // the survivors region is [fin_keys | fin_cnt copy]: fin_cnt lives among the counters (zeroed with them), so phase 4
+    // copies it behind fin_keys where the all-gather picks both up
+    uint32_t* fin_cnt_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(L.fin_keys) + align256((size_t)K * kTiesFinalCap * 8));
+    // every rank samples with the SAME stride (derived from the global length) so that the global sample size is the sum
+    const int64_t stride = ties_sample_stride(d_global);
+    const int64_t n_s = ties_sample_count(d_global, stride);
+    int64_t r_hi, r_lo;
+    ties_sample_ranks(d_global, k_cnt, n_s, &r_hi, &r_lo);
+    r_hi -= 4 * world;    // per-rank rounding of the sample size (partial strides at the slice ends)
+    r_lo += 4 * world;
+    const int n_lists = ties_pass_blocks(K) * kTiesThreads;
+    int rc = MR_OK;
+    cudaError_t e;
+    switch (phase) {
+        case 0:
+            ties_init_kernel<<<1, 32, 0, st>>>(L.st, K, reinterpret_cast<u64*>(cut_local), status, k_cnt, d_global);
+            MR_CUDA_LAUNCH_CHECK("mr_ties_select_dist(init)");
+            [[fallthrough]];
+        case 1:
+            if (phase == 1) ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, r_hi, r_lo, 0, status);
+            e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
+            if (e != cudaSuccess) { set_error("mr_ties_select_dist: memset: %s", cudaGetErrorString(e)); return (int)e; }
+            if (d_local > 0) MR_DISPATCH_K(K, { rc = ties_launch_pass<KK>(base, models, d_local, w, stride, 0, L, st, j_off, false); });
+            return rc;
+        case 2:
+            ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, r_hi, r_lo, 0, status);
+            e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(L.cand_cnt, 0, (size_t)K * n_lists * 4, st);
+            if (e != cudaSuccess) { set_error("mr_ties_select_dist: memset: %s", cudaGetErrorString(e)); return (int)e; }
+            if (d_local > 0) MR_DISPATCH_K(K, { rc = ties_launch_pass<KK>(base, models, d_local, w, 1, 1, L, st, j_off, false); });
+            if (rc != MR_OK) return rc;
+            {
+                dim3 hgrid(128, (unsigned)K);
+                ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, n_lists, L.hist, L.above);
+            }
+            MR_CUDA_LAUNCH_CHECK("mr_ties_select_dist(collect)");
+            return MR_OK;
+        case 3:
+            ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, k_cnt, k_cnt, 1, status);
+            e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
+            if (e != cudaSuccess) { set_error("mr_ties_select_dist: memset: %s", cudaGetErrorString(e)); return (int)e; }
+            {
+                dim3 hgrid(128, (unsigned)K);
+                ties_cand_hist_kernel<<<hgrid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, n_lists, L.hist, nullptr);
+            }
+            MR_CUDA_LAUNCH_CHECK("mr_ties_select_dist(refine)");
+            return MR_OK;
+        case 4: {
+            ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, nullptr, k_cnt, k_cnt, 1, status);
+            e = cudaMemsetAsync(L.fin_cnt, 0, (size_t)K * 4, st);
+            if (e != cudaSuccess) { set_error("mr_ties_select_dist: memset: %s", cudaGetErrorString(e)); return (int)e; }
+            dim3 grid(256, (unsigned)K);
+            ties_compact_kernel<<<grid, 256, 0, st>>>(L.st, L.cand_cnt, L.cand_keys, L.cand_cap, n_lists, L.fin_cnt, L.fin_keys, status);
+            e = cudaMemcpyAsync(fin_cnt_out, L.fin_cnt, (size_t)K * 4, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) { set_error("mr_ties_select_dist: copy: %s", cudaGetErrorString(e)); return (int)e; }
+            MR_CUDA_LAUNCH_CHECK("mr_ties_select_dist(compact)");
+            return MR_OK;
+        }
+        default: {
+            MR_REQUIRE(gathered, "mr_ties_select_dist: phase 5 needs the gathered survivors");
+            const size_t region = align256((size_t)K * kTiesFinalCap * 8) + align256((size_t)K * 4);
+            ties_final_dist_kernel<<<K, 1024, 0, st>>>(L.st, reinterpret_cast<const unsigned char*>(gathered), world, region,
+                                                       align256((size_t)K * kTiesFinalCap * 8), k_cnt, j_off,
+                                                       reinterpret_cast<u64*>(cut_local), reinterpret_cast<u64*>(cut_global), status);
+            MR_CUDA_LAUNCH_CHECK("mr_ties_select_dist(final)");
+            return MR_OK;
+        }
+    }
+}
+
 // get_ties_vectors / the fused TIES + lambda merge in ONE pass over the data: sample passes, then the speculative
 // select + build pass, the exact cut from the collected keys, and the fix-up of the mis-decided columns.
 extern "C" int mr_ties_select_build(const float* base, const float* const* models, int K, int64_t d, int64_t k_cnt, int mode,
@@ -1522,7 +1713,7 @@ extern "C" int mr_ties_select_build(const float* base, const float* const* model
     size_t smem = (size_t)K * (sizeof(SpecState) + 12 + (size_t)kTiesThreads * 4) + 32;
     if (!rows_out) smem += (((size_t)G * K * 4 + 15) & ~(size_t)15) + ((seg_end && seg_group) ? ((((size_t)P * 12) + 15) & ~(size_t)15) : 0);
     if (vec) smem = ((smem + 127) & ~(size_t)127) + (size_t)kSpecStages * (K + 1) * 4096 + 64;   // TMA ring + mbarriers
-    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap};
+    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap, 0};
     SpecLaunch S{base, models, K, d, L.st, L.mid, reinterpret_cast<const u64*>(cut), status, pc, a, smem, L.n_lists, vec, st};
     int blocks = 0;
     auto launch = rows_out ? ties_spec_launch_vectors : ties_spec_launch_fused;

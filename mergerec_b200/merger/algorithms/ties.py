@@ -37,7 +37,7 @@ def select_kth_largest(base_model: FlattenedModel, rows: Sequence[torch.Tensor],
     dev = base_model.device
     ws_bytes = int(lib.mr_ties_workspace_bytes(d, K))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    cut = torch.empty(K, dtype=torch.int64, device=dev)
+    cut = torch.zeros(K, dtype=torch.int64, device=dev)      # defined even when a deferred select fails (status says so)
     status = torch.zeros(K, dtype=torch.int32, device=dev)
     args = (_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(w), int(k_cnt), _lib.dptr(cut),
             _lib.dptr(status), _lib.dptr(ws), ws_bytes, _lib.stream_handle())

@@ -131,3 +131,80 @@ def test_full_size_world1_select_agrees_with_the_bracket_select():
     a = get_ties_vectors_sharded(base, models, 0.2, d, None)
     b = get_ties_vectors(base, models, 0.2)
     assert torch.equal(a[:, :d], b[:, :d])
+
+
+# ------------------------------------------------------------------------------------------ device-side sharded select
+def _emulated_dist_select(base, models, k_cnt, world, w=None):
+    """Run `world` DistSelect instances (one per emulated rank) on this GPU, playing the collectives by hand: sum the
+    counters views after phases 0-3, concatenate the survivors regions after phase 4."""
+    from mergerec_b200.merger.sharded import DistSelect
+    d = base.numel()
+    sels = []
+    for r in range(world):
+        lo, hi = flat_shard_bounds(d, world, r)
+        sels.append(DistSelect(base[lo:hi].clone(), [m[lo:hi].clone() for m in models], k_cnt, d, lo, w))
+    gathered = None
+    for phase in range(DistSelect.PHASES):
+        for s in sels:
+            s.run(phase, gathered, world)
+        if phase < 4:
+            total = torch.stack([s.counters for s in sels]).sum(0, dtype=torch.int32)
+            for s in sels:
+                s.counters.copy_(total)
+        elif phase == 4:
+            gathered = torch.cat([s.survivors for s in sels])
+    return sels
+
+
+@pytest.mark.parametrize("K,d,world,quantize,weighted", [(3, 200_003, 2, 0.0, False), (8, 1_000_003, 4, 0.0, False),
+                                                         (5, 300_031, 3, 2.5e-4, True), (8, 524_288, 8, 1e-5, False),
+                                                         (2, 4099, 5, 0.0, False), (16, 100_001, 2, 0.0, True)])
+def test_dist_select_emulated_ranks_equal_single_gpu(K, d, world, quantize, weighted):
+    """The phased device-side select over `world` slices (collectives played by hand) gives the single-GPU cut keys, and
+    the per-rank local cuts rebuild exactly the single-GPU TIES vectors / merge_ties on every slice."""
+    from mergerec_b200 import _lib
+    from mergerec_b200.merger.algorithms.ties import _build, select_kth_largest
+    from mergerec_b200.merger.layout import alloc_rows
+    base, models = synth.make_flat(d, K, seed=40 + K, quantize=quantize)
+    fb, fm = dev(base), [dev(m) for m in models]
+    w = torch.linspace(0.2, 1.1, K).cuda() if weighted else None
+    k_cnt = int(0.2 * d)
+    want_cut = select_kth_largest(fb, fm, k_cnt, w)
+    sels = _emulated_dist_select(fb, fm, k_cnt, world, w)
+    statuses = [s.status.cpu().tolist() for s in sels]
+    assert all(st == statuses[0] for st in statuses), f"ranks disagree on the verdict: {statuses}"
+    if statuses[0] != [1] * K:
+        # thousands of equal magnitudes AT the cut (quantised inputs): two 1024-way refinements cannot separate them;
+        # every rank reports it and `sharded_select` takes the exact path (test_dist_select_world1_and_fallback)
+        assert quantize > 0, f"fast select failed on a tie-free input: {statuses[0]}"
+        pytest.skip(f"sampled bracket cannot resolve this input (status {statuses[0]}): exact path")
+    for r, s in enumerate(sels):
+        assert torch.equal(s.cut_global, want_cut), f"rank {r}: global cut"
+    mode = _lib.MR_TIES_TRIMSUM if weighted else _lib.MR_TIES_VECTORS
+    full = torch.empty(d, device="cuda") if weighted else alloc_rows(K, d, "cuda")
+    _build(fb, fm, want_cut, mode, w=w, out=full, ldo=0 if weighted else max(full.stride(0), d))
+    for r, s in enumerate(sels):
+        lo, hi = flat_shard_bounds(d, world, r)
+        if hi == lo:
+            continue
+        part = torch.empty(hi - lo, device="cuda") if weighted else alloc_rows(K, hi - lo, "cuda")
+        _build(s.base, s.rows, s.cut, mode, w=w, out=part, ldo=0 if weighted else max(part.stride(0), hi - lo))
+        if weighted:
+            assert torch.equal(part.view(torch.int32), full[lo:hi].view(torch.int32)), f"rank {r}: merge_ties slice"
+        else:
+            assert torch.equal(part[:, :hi - lo].view(torch.int32), full[:, lo:hi].view(torch.int32)), f"rank {r}: TIES vectors slice"
+
+
+def test_dist_select_world1_and_fallback():
+    """group=None goes through the same phased kernels (no collective); an input the sampled bracket cannot resolve
+    (every magnitude equal) falls back to the exact windowed search and still returns the exact cut."""
+    from mergerec_b200.merger.algorithms.ties import select_kth_largest
+    from mergerec_b200.merger.sharded import sharded_select
+    base, models = synth.make_flat(150_001, 4, seed=9)
+    fb, fm = dev(base), [dev(m) for m in models]
+    k = int(0.2 * 150_001)
+    cut, status = sharded_select(fb, fm, k, 150_001, defer_status=True)
+    assert status.cpu().tolist() == [1] * 4 and torch.equal(cut, select_kth_largest(fb, fm, k))
+    zb = torch.zeros(100_000, device="cuda")
+    zm = [torch.full((100_000,), 0.5, device="cuda"), torch.full((100_000,), -0.5, device="cuda")]
+    assert torch.equal(sharded_select(zb, zm, 20_000, 100_000), select_kth_largest(zb, zm, 20_000))
