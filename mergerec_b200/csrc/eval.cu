@@ -93,13 +93,19 @@ topk_rows_kernel(const float* __restrict__ scores, int64_t Q, int64_t N, int64_t
 // ---- merge L top-K lists per row (the multi-GPU / multi-split exchange step) -----------------------------------
 // vals / ids: L lists of (Q, K_in), list l starting `list_stride` elements after list l - 1; entries with id < 0 are
 // empty.  Output (Q, K_out) sorted by (score desc, id asc).
+// Lists that are already sorted (what the scoring kernel and this kernel emit) are merged by RANK COUNTING: the final
+// position of a key is the number of keys, over all lists, that are greater -- one binary search per (key, list), no
+// barriers, far cheaper than sorting L * K_in keys again (8 lists of 100 took 4.1 ms for 65,536 rows with the sort).  Each
+// thread also checks its keys against their list neighbours; if any list turns out not to be sorted (the C ABI allows
+// that) the block falls back to the bitonic sort.  Keys are distinct (ids are), so the ranks are a permutation.
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ ids, int64_t list_stride, int L, int64_t Q,
                   int K_in, int K_out, int NP, float* __restrict__ out_val, int32_t* __restrict__ out_id) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* s_keys = reinterpret_cast<u64*>(smem_raw);
+    const int total = L * K_in;
     for (int64_t q = blockIdx.x; q < Q; q += gridDim.x) {
-        const int total = L * K_in;
+        int unsorted = 0;
         for (int i = threadIdx.x; i < NP; i += blockDim.x) {
             u64 key = 0;
             if (i < total) {
@@ -111,11 +117,53 @@ topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ id
             s_keys[i] = key;
         }
         __syncthreads();
-        block_bitonic_sort_desc(s_keys, NP);
-        for (int i = threadIdx.x; i < K_out; i += blockDim.x) {
-            const u64 key = (i < NP) ? s_keys[i] : 0;
-            out_id[q * K_out + i] = key ? (int32_t)key_id(key) : -1;
-            out_val[q * K_out + i] = key ? key_score(key) : -INFINITY;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int e = i % K_in;
+            if (e + 1 < K_in && s_keys[i] < s_keys[i + 1]) unsorted = 1;   // (empty slots are 0 and sit at the end)
+        }
+        if (__syncthreads_or(unsorted)) {
+            block_bitonic_sort_desc(s_keys, NP);
+            for (int i = threadIdx.x; i < K_out; i += blockDim.x) {
+                const u64 key = (i < NP) ? s_keys[i] : 0;
+                out_id[q * K_out + i] = key ? (int32_t)key_id(key) : -1;
+                out_val[q * K_out + i] = key ? key_score(key) : -INFINITY;
+            }
+        } else {
+            for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                const u64 key = s_keys[i];
+                if (key == 0) continue;
+                const int mine = i / K_in;
+                int rank = 0;
+                for (int l = 0; l < L; ++l) {
+                    const u64* lst = s_keys + l * K_in;
+                    if (l == mine) { rank += i - mine * K_in; continue; }     // sorted list: everything before me is greater
+                    // keys of list l that go before mine: the greater ones, plus an equal one (the same id in two lists
+                    // -- never produced by disjoint shards, but legal input) when l comes first: ranks stay a permutation
+                    int lo = 0, hi = K_in;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const bool before = l < mine ? (lst[mid] >= key) : (lst[mid] > key);
+                        if (before) lo = mid + 1; else hi = mid;
+                    }
+                    rank += lo;
+                }
+                if (rank < K_out) {
+                    out_id[q * K_out + rank] = (int32_t)key_id(key);
+                    out_val[q * K_out + rank] = key_score(key);
+                }
+            }
+            // rows with fewer than K_out candidates: the tail is empty
+            int n_valid = 0;
+            for (int l = 0; l < L; ++l) {          // non-empty keys per sorted list = position of its first 0
+                const u64* lst = s_keys + l * K_in;
+                int lo = 0, hi = K_in;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] != 0) lo = mid + 1; else hi = mid; }
+                n_valid += lo;
+            }
+            for (int i = n_valid + threadIdx.x; i < K_out; i += blockDim.x) {
+                out_id[q * K_out + i] = -1;
+                out_val[q * K_out + i] = -INFINITY;
+            }
         }
         __syncthreads();
     }

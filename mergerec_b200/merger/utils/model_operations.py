@@ -40,6 +40,13 @@ def flatten_model(model: StateDict, device: Optional[torch.device] = None) -> Tu
     device = device or _lib.require_cuda()
     shape_dict = {k: v.shape for k, v in model.items()}
     layout = FlatLayout.from_shape_dict(shape_dict)
+    if any(not t.is_cuda for t in model.values()):
+        # host tensors: the streamed loader (pinned runs coalesced, pageable tensors packed through a pinned staging ring
+        # on a copy stream); the current stream waits for its event, the host does not
+        from .loader import default_loader
+        flat, ready = default_loader(device).load(model, layout)
+        torch.cuda.current_stream(device).wait_event(ready)
+        return flat, shape_dict
     flat = torch.empty(layout.d, dtype=torch.float32, device=device)
     for t, off, n in zip(model.values(), layout.offsets, layout.sizes):
         if n:

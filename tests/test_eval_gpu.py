@@ -420,3 +420,34 @@ def test_prepared_queries_and_table_scratch_reuse():
     assert ev.evaluate_embeddings(q, table, tl) == ev.evaluate_embeddings(tu, ti, tl)
     with pytest.raises(ValueError):
         ev.topk_embeddings(ev.prepare_queries(tu, mode=MR_SCORE_BF16), table)
+
+
+def test_topk_merge_sorted_fast_path_unsorted_fallback_and_duplicates():
+    """`mr_topk_merge` merges sorted lists by rank counting and falls back to a sort when a list is not sorted; both
+    must give the (score desc, id asc) order, with short rows padded by empty slots and duplicate keys kept."""
+    rng = np.random.Generator(np.random.PCG64(23))
+    L, Q, K = 5, 61, 37
+    vals = rng.standard_normal((L, Q, K)).astype(np.float32)
+    vals[:, :, ::5] = np.round(vals[:, :, ::5], 1)                          # plenty of equal scores across lists
+    ids = rng.permutation(L * Q * K).reshape(L, Q, K).astype(np.int32)
+    ids[1, 3, :] = -1                                                        # an entirely empty list for one row
+    ids[:, 7, 2:] = -1                                                       # a row with only 2 candidates per list: 10 < k_out
+    order = np.lexsort((ids, -vals), axis=-1)                                # sort every list: score desc, id asc, empties last
+    empty = np.take_along_axis(ids, order, -1) < 0
+    order = np.take_along_axis(order, np.argsort(empty, axis=-1, kind="stable"), -1)
+    svals, sids = np.take_along_axis(vals, order, -1), np.take_along_axis(ids, order, -1)
+    want_v, want_i = orc.topk_merge(svals, sids)
+    for k_out in (K, 12, 50):
+        mv, mi = topk_merge(dev(svals), dev(sids), k_out)                    # sorted lists: rank-counting path
+        uv, ui = topk_merge(dev(vals), dev(ids), k_out)                      # unsorted lists: sort fallback
+        kk = min(k_out, want_i.shape[1])
+        for got_v, got_i in ((mv, mi), (uv, ui)):
+            assert np.array_equal(host(got_i)[:, :kk], want_i[:, :kk])
+            valid = want_i[:, :kk] >= 0
+            assert np.array_equal(host(got_v)[:, :kk][valid].view(np.uint32), want_v[:, :kk][valid].view(np.uint32))
+            assert (host(got_i)[7, 10:] == -1).all()
+    # the same (score, id) in two lists: both copies survive, next to each other
+    dv = np.array([[[3.0, 2.0, 1.0]], [[3.0, 1.5, 0.5]]], np.float32)
+    di = np.array([[[5, 6, 7]], [[5, 8, 9]]], np.int32)
+    v, i = topk_merge(dev(dv), dev(di), 6)
+    assert host(i)[0].tolist() == [5, 5, 6, 8, 7, 9] and host(v)[0].tolist() == [3.0, 3.0, 2.0, 1.5, 1.0, 0.5]
