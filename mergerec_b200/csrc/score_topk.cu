@@ -64,6 +64,7 @@ struct Params {
     float* out_val;     // (S * kEpiGroups, Q, K)
     int32_t* out_id;    // (S * kEpiGroups, Q, K)
     long long* dbg;     // optional timestamps of block 0 (mr_score_topk_debug_buffer), else NULL
+    int l2_hint;        // 1: query loads evict_last, item loads evict_first (MR_SCORE_L2HINT, default on)
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------------
@@ -116,6 +117,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int wha
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// L2 eviction policies for the two operand streams: the query block of a unit is re-read for every item tile and must
+// stay in L2 (evict_last); item tiles are read by the handful of pairs that walk the same split and then never again
+// (evict_first), so that streaming the 6 GB item table does not push the query blocks out.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t pol) {
+    if (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(pol) : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(pol) : "memory");
+    }
+}
 template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     if (CG == 1) {
@@ -414,6 +440,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
         if (lane == 0) {
             uint32_t kiter = 0;
             Unit u;
+            const uint64_t pol_q = l2_policy_evict_last(), pol_i = l2_policy_evict_first();
+            const bool hint = p.l2_hint != 0;
             for (int ui = cluster_id; get_unit(p, ui, u); ui += num_clusters) {
                 const int qrow = (u.qb * CG + (int)rank) * kBlockM;
                 for (int t = u.t0; t < u.t1; ++t) {
@@ -430,11 +458,20 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                         const uint32_t bytes = (x3 ? 2u : 1u) * (uint32_t)(kABytes + C::kBBytes);
                         if (leader) mbar_arrive_expect_tx(full, bytes * CG);
                         const int kc = kb * C::kElemsPerBlock;
-                        tma_load_2d<CG>(sbase, &map_uhi, full, kc, qrow);
-                        tma_load_2d<CG>(sbase + (BF16 ? 1 : 2) * kABytes, &map_ihi, full, kc, nrow);
-                        if (x3) {
-                            tma_load_2d<CG>(sbase + kABytes, &map_ulo, full, kc, qrow);
-                            tma_load_2d<CG>(sbase + 2 * kABytes + C::kBBytes, &map_ilo, full, kc, nrow);
+                        if (hint) {
+                            tma_load_2d_hint<CG>(sbase, &map_uhi, full, kc, qrow, pol_q);
+                            tma_load_2d_hint<CG>(sbase + (BF16 ? 1 : 2) * kABytes, &map_ihi, full, kc, nrow, pol_i);
+                            if (x3) {
+                                tma_load_2d_hint<CG>(sbase + kABytes, &map_ulo, full, kc, qrow, pol_q);
+                                tma_load_2d_hint<CG>(sbase + 2 * kABytes + C::kBBytes, &map_ilo, full, kc, nrow, pol_i);
+                            }
+                        } else {
+                            tma_load_2d<CG>(sbase, &map_uhi, full, kc, qrow);
+                            tma_load_2d<CG>(sbase + (BF16 ? 1 : 2) * kABytes, &map_ihi, full, kc, nrow);
+                            if (x3) {
+                                tma_load_2d<CG>(sbase + kABytes, &map_ulo, full, kc, qrow);
+                                tma_load_2d<CG>(sbase + 2 * kABytes + C::kBBytes, &map_ilo, full, kc, nrow);
+                            }
                         }
                         if (!leader) mbar_arrive_remote(full, 0);
                     }
@@ -688,8 +725,7 @@ static Plan make_plan(int64_t Q, int64_t N, int K) {
     const int clusters = sms / pl.cg;
     pl.QB = (int)((Q + (int64_t)kBlockM * pl.cg - 1) / ((int64_t)kBlockM * pl.cg));
     pl.T = (int)((N + kBlockN - 1) / kBlockN);
-    pl.QG = env_int("MR_SCORE_QGROUP", 16);
-    if (pl.QG < 1) pl.QG = 1;
+    pl.QG = 0;   // set below, once the number of splits is known
     // item splits: each unit pays a top-K warm-up (its first tiles pass everything and trigger bursts of row sorts),
     // measured at roughly (8 + K / 5) tile-times; units are executed in waves of `clusters`.  Pick the S that
     // minimises waves * (tiles per unit + warm-up).
@@ -710,6 +746,11 @@ static Plan make_plan(int64_t Q, int64_t N, int K) {
     }
     if (s > smax) s = smax;
     pl.S = s;
+    // query blocks per L2 group: one wave of CTA pairs = QG query blocks x S item splits, so that the pairs running at
+    // the same time walk only S item streams and clusters / S query blocks (measured at BASELINE config 5 with the L2
+    // eviction hints: QG = 37, S = 2 -> 443 ms; 16 x 2 -> 447; 18 x 4 -> 466; 8 x 9 -> 481; 74 x 2 -> 548)
+    pl.QG = env_int("MR_SCORE_QGROUP", clusters / pl.S);
+    if (pl.QG < 1) pl.QG = 1;
     const int64_t units = (int64_t)pl.QB * pl.S;
     pl.grid = (int)((units < clusters ? units : clusters) * pl.cg);
     if (pl.grid < pl.cg) pl.grid = pl.cg;
@@ -802,6 +843,7 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     p.T = pl.T; p.QB = pl.QB; p.S = pl.S; p.QG = pl.QG;
     p.cand = reinterpret_cast<mr::u64*>(w);
     p.dbg = g_score_dbg;
+    p.l2_hint = st::env_int("MR_SCORE_L2HINT", 1);
     float* part_val = reinterpret_cast<float*>(w + pl.cand_bytes);
     int32_t* part_id = reinterpret_cast<int32_t*>(w + pl.cand_bytes + pl.part_bytes / 2);
     p.out_val = part_val;

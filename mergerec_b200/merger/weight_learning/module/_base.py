@@ -40,10 +40,25 @@ def _lambda_grad(grads: List[Optional[torch.Tensor]], layout: FlatLayout, T: tor
         keep.append(g)
         ptrs.append(g.data_ptr())
     P = len(ptrs)
-    ptr_t = torch.tensor(ptrs, dtype=torch.int64).to(dev, non_blocking=False)
+    # Pointer table and workspace are cached on the layout: a gradient set that repeats (steady-state allocator
+    # addresses; always under CUDA-graph replay) uploads nothing, a new one goes up with ONE asynchronous copy from a
+    # pinned host table that stays alive in the cache -- no blocking transfer, no allocation, so the whole backward
+    # (and the collaborative step around it) can be captured in a CUDA graph.
+    cache = layout._dev_cache.setdefault(("lambda_grad", str(dev)), {"tables": {}, "ws": None})
+    key = tuple(ptrs)
+    entry = cache["tables"].get(key)
+    if entry is None:
+        host = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
+        entry = (host, host.to(dev, non_blocking=True))
+        if len(cache["tables"]) >= 16:
+            cache["tables"].pop(next(iter(cache["tables"])))
+        cache["tables"][key] = entry
+    ptr_t = entry[1]
     seg_off, seg_len = layout.device_segments(dev)
     ws_bytes = int(lib.mr_lambda_grad_workspace_bytes(d, P, K))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if cache["ws"] is None or cache["ws"].numel() < ws_bytes:
+        cache["ws"] = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = cache["ws"]
     out = torch.empty((G, K), dtype=torch.float32, device=dev)
     rc = lib.mr_lambda_grad(_lib.dptr(ptr_t), _lib.dptr(seg_off), _lib.dptr(seg_len), _lib.dptr(seg_group), P, d,
                             _lib.dptr(T), T.stride(0), K, G, _lib.dptr(out), _lib.dptr(ws), ws_bytes,

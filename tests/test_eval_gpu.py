@@ -436,7 +436,16 @@ def test_topk_merge_sorted_fast_path_unsorted_fallback_and_duplicates():
     empty = np.take_along_axis(ids, order, -1) < 0
     order = np.take_along_axis(order, np.argsort(empty, axis=-1, kind="stable"), -1)
     svals, sids = np.take_along_axis(vals, order, -1), np.take_along_axis(ids, order, -1)
-    want_v, want_i = orc.topk_merge(svals, sids)
+    # expectation in numpy (the oracle's merge has no notion of empty slots): per row, all non-empty candidates ordered
+    # by (score desc, id asc), padded with (-inf, -1)
+    want_v = np.full((Q, L * K), -np.inf, np.float32)
+    want_i = np.full((Q, L * K), -1, np.int32)
+    for q in range(Q):
+        v, i = vals[:, q, :].reshape(-1), ids[:, q, :].reshape(-1)
+        keep = i >= 0
+        v, i = v[keep], i[keep]
+        o = np.lexsort((i, -v))
+        want_v[q, :o.size], want_i[q, :o.size] = v[o], i[o]
     for k_out in (K, 12, 50):
         mv, mi = topk_merge(dev(svals), dev(sids), k_out)                    # sorted lists: rank-counting path
         uv, ui = topk_merge(dev(vals), dev(ids), k_out)                      # unsorted lists: sort fallback
@@ -445,7 +454,7 @@ def test_topk_merge_sorted_fast_path_unsorted_fallback_and_duplicates():
             assert np.array_equal(host(got_i)[:, :kk], want_i[:, :kk])
             valid = want_i[:, :kk] >= 0
             assert np.array_equal(host(got_v)[:, :kk][valid].view(np.uint32), want_v[:, :kk][valid].view(np.uint32))
-            assert (host(got_i)[7, 10:] == -1).all()
+            assert (host(got_i)[7, 10:] == -1).all() and np.isneginf(host(got_v)[7, 10:]).all()
     # the same (score, id) in two lists: both copies survive, next to each other
     dv = np.array([[[3.0, 2.0, 1.0]], [[3.0, 1.5, 0.5]]], np.float32)
     di = np.array([[[5, 6, 7]], [[5, 8, 9]]], np.int32)

@@ -218,3 +218,46 @@ def test_merge_test_flow_from_files(tmp_path):
     mod.load_weights_from_dict(mio.resolve_weights(tmp_path / "weights" / "v1.jsonl", 0, K))
     w = np.asarray([[0.7, 0.2, 0.4]], np.float32)
     assert_bit_equal(merged_flat(), orc.lambda_merge(fb, T, w), "line 0 of the lambda log")
+
+
+def test_lambda_merge_and_gradient_capture_in_a_cuda_graph():
+    """The merge forward and its lambda-gradient backward are allocation-free and stream-ordered once warm (cached pointer
+    table and workspace): both capture into ONE CUDA graph, and a replay with new lambdas / new upstream gradients gives the
+    eager result bit for bit."""
+    shapes = synth.tiny_shapes(hidden=64, ffn=128, vocab=1000)
+    layout = FlatLayout.from_shape_dict(shapes)
+    K = 5
+    g = torch.Generator(device="cuda").manual_seed(1)
+    T = torch.randn(K, layout.d, generator=g, device="cuda")
+    base = torch.randn(layout.d, generator=g, device="cuda")
+    seg_end, seg_group, keys = layout.device_blocks(True, "cuda")
+    G = len(keys)
+    from mergerec_b200 import _lib
+    from mergerec_b200.merger.algorithms._common import merge_axpy
+    w = torch.rand((G, K), generator=g, device="cuda")
+    grad = torch.randn(layout.d, generator=g, device="cuda")
+    grads = [grad[o:o + n] for o, n in zip(layout.offsets, layout.sizes)]       # fixed addresses: views of one buffer
+    merged = torch.empty(layout.d, device="cuda")
+    rows = list(T.unbind(0))
+
+    def step():
+        merge_axpy(base, rows, w, _lib.MR_ORDER_SUM_FIRST, False, seg_end, seg_group, out=merged)
+        return _lambda_grad(grads, layout, T, seg_group, G)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = step()
+    for trial in range(3):
+        w.copy_(torch.rand((G, K), generator=g, device="cuda"))
+        grad.copy_(torch.randn(layout.d, generator=g, device="cuda"))
+        graph.replay()
+        got_merged, got_gw = merged.clone(), out.clone()
+        want_gw = step()
+        assert torch.equal(got_merged, merged) and torch.equal(got_gw, want_gw), trial
