@@ -139,6 +139,91 @@ class Evaluator:
         score_topk(queries.hi, queries.lo, table, k, mode, out=(loc_v, loc_i))
         return exchange_packed(local, k, table.group, gathered=table.gather_buffer(queries.shape[0], k))
 
+    def topk_embeddings_streamed(self, user_emb: Union[torch.Tensor, "PreparedQueries"], host_items: torch.Tensor,
+                                 k: Optional[int] = None, id_base: int = 0, n_total: Optional[int] = None, group=None,
+                                 normalize: bool = False, mode: int = MR_SCORE_TF32X3,
+                                 first_rows: int = 32768, max_chunks: int = 12) -> Tuple[torch.Tensor, torch.Tensor]:
+        """`topk_embeddings` for an item table that still lives in HOST memory (what `load_item_embeddings` /
+        `ItemEncoderMixin.encode_items(...).cpu()` hand over): the rows are copied to the GPU in chunks on a copy stream
+        while the previous chunk is being scored, so the transfer hides behind the tensor-core work instead of preceding
+        it.  Chunk sizes ramp up geometrically from `first_rows` (only the first, small copy is exposed); every chunk is
+        split into its TF32 operands, scored into its own sorted list, and the lists are merged (`mr_topk_merge_packed`).
+        Because a (query, item) score does not depend on how the table is cut, the result is bit-identical to the
+        one-table call.  `host_items` = this rank's rows (pinned memory makes the copies asynchronous); `id_base`,
+        `n_total`, `group` as for `ShardedItemTable`."""
+        from .sharded import exchange_packed, topk_merge_packed
+        k = self._max_k if k is None else k
+        if k > MAX_FUSED_TOPK:
+            raise ValueError(f"fused top-k supports k <= {MAX_FUSED_TOPK}")
+        dev = _lib.require_cuda()
+        if host_items.dim() != 2:
+            raise ValueError("item table must be (N, E)")
+        n_local = int(host_items.shape[0])
+        n_total = n_local if n_total is None else int(n_total)
+        if k > n_total:
+            raise RuntimeError(f"selected index k out of range (k={k}, N={n_total})")
+        bf16 = mode == MR_SCORE_BF16
+        queries = user_emb if isinstance(user_emb, PreparedQueries) else PreparedQueries(user_emb, normalize, bf16)
+        Q = queries.shape[0]
+        # chunk plan: geometric ramp, at most max_chunks lists (k * chunks candidates per row must stay mergeable)
+        max_chunks = max(1, min(max_chunks, 8192 // max(k, 1)))
+        bounds, lo, rows = [], 0, max(int(first_rows), 1)
+        while lo < n_local:
+            if len(bounds) == max_chunks - 1:
+                rows = n_local - lo
+            hi = min(n_local, lo + rows)
+            bounds.append((lo, hi))
+            lo, rows = hi, rows * 2
+        C = max(len(bounds), 1)
+        partial = torch.empty((C, 2, Q, k), dtype=torch.int32, device=dev)
+        if not bounds:        # an empty shard: every list is empty
+            partial[:, 0].view(torch.float32).fill_(float("-inf"))
+            partial[:, 1].fill_(-1)
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy = self._copy_stream
+        copy.wait_stream(main)
+        ws = None
+        for c, (a, b) in enumerate(bounds):
+            with torch.cuda.stream(copy):
+                chunk = host_items[a:b].to(device=dev, dtype=torch.float32, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            main.wait_event(ready)
+            chunk.record_stream(main)
+            table = ShardedItemTable(chunk, id_base=id_base + a, n_total=n_total, normalize=normalize, bf16=bf16)
+            table._ws = ws                                            # one scratch for all chunks (grown if needed)
+            if b - a >= k:
+                score_topk(queries.hi, queries.lo, table, k, mode, out=(partial[c, 0].view(torch.float32), partial[c, 1]))
+            else:
+                self._score_small_chunk(queries, table, k, mode, partial[c])
+            ws = table._ws
+        vals, ids = topk_merge_packed(partial, k) if C > 1 else (partial[0, 0].view(torch.float32), partial[0, 1])
+        if group is not None:
+            import torch.distributed as dist
+            if dist.get_world_size(group) > 1:
+                local = torch.stack([vals.contiguous().view(torch.int32), ids.contiguous()])
+                return exchange_packed(local, k, group)
+        return vals, ids
+
+    @staticmethod
+    def _score_small_chunk(queries: "PreparedQueries", table: ShardedItemTable, k: int, mode: int, out: torch.Tensor) -> None:
+        """A chunk with fewer than k rows: its list has only n < k entries; the rest of the (Q, k) plane is marked empty."""
+        n = table.n_local
+        out[0].view(torch.float32).fill_(float("-inf"))
+        out[1].fill_(-1)
+        if n:
+            v, i = score_topk(queries.hi, queries.lo, table, n, mode)
+            out[0].view(torch.float32)[:, :n] = v
+            out[1][:, :n] = i
+
+    def evaluate_embeddings_streamed(self, user_emb, host_items: torch.Tensor, labels: torch.Tensor, metric_prefix: str = "",
+                                     **kw) -> Dict[str, float]:
+        """`evaluate_embeddings` with a host-resident item table (see `topk_embeddings_streamed`)."""
+        _, ids = self.topk_embeddings_streamed(user_emb, host_items, self._max_k, **kw)
+        return self.metrics_from_ids(ids, labels, metric_prefix)
+
     @staticmethod
     def prepare_queries(user_emb: torch.Tensor, normalize: bool = False, mode: int = MR_SCORE_TF32X3) -> PreparedQueries:
         """Split / convert the query embeddings once; pass the result as `user_emb` to `topk_embeddings` /

@@ -42,6 +42,12 @@ def main() -> int:
             for _ in range(2):                                                               # second call reuses the scratch
                 sv, si = ev.topk_embeddings(q, table, k)
                 ok &= bool(torch.equal(si, full_i)) and bool(torch.equal(sv.view(torch.int32), full_v.view(torch.int32)))
+            # host-resident shard streamed in chunks behind the scoring, then the same exchange
+            from mergerec_b200.evaluator import shard_bounds
+            lo_i, hi_i = shard_bounds(N, world, rank)
+            hv, hi_ids = ev.topk_embeddings_streamed(q, torch.from_numpy(items[lo_i:hi_i]), k, id_base=lo_i, n_total=N,
+                                                     group=dist.group.WORLD, first_rows=997)
+            ok &= bool(torch.equal(hi_ids, full_i)) and bool(torch.equal(hv.view(torch.int32), full_v.view(torch.int32)))
             m_sharded = ev.evaluate_embeddings(q, table, tl)
             m_full = ev.evaluate_embeddings(tu, ti, tl)
             ok &= m_sharded == m_full

@@ -460,3 +460,24 @@ def test_topk_merge_sorted_fast_path_unsorted_fallback_and_duplicates():
     di = np.array([[[5, 6, 7]], [[5, 8, 9]]], np.int32)
     v, i = topk_merge(dev(dv), dev(di), 6)
     assert host(i)[0].tolist() == [5, 5, 6, 8, 7, 9] and host(v)[0].tolist() == [3.0, 3.0, 2.0, 1.5, 1.0, 0.5]
+
+
+@pytest.mark.parametrize("kind,Q,N,E,k,first", [("grid", 300, 20011, 64, 50, 1000), ("gauss", 130, 5000, 768, 100, 64),
+                                                 ("grid", 70, 90, 32, 50, 16), ("grid", 40, 3000, 128, 10, 4096)])
+def test_streamed_host_table_equals_one_table(kind, Q, N, E, k, first):
+    """`topk_embeddings_streamed` (host-resident item table copied in growing chunks behind the scoring) gives exactly the
+    one-table result: ids, score bits, metric floats -- including chunks shorter than k and a single-chunk table."""
+    users, items, labels = synth.make_catalog(Q, N, E, kind=kind, seed=29)
+    ev = Evaluator(["NDCG", "RECALL"], [1, 10, k])
+    tu, tl = dev(users), dev(labels)
+    want_v, want_i = ev.topk_embeddings(tu, dev(items), k)
+    for pinned in (False, True):
+        h = torch.from_numpy(items)
+        h = h.pin_memory() if pinned else h
+        v, i = ev.topk_embeddings_streamed(tu, h, k, first_rows=first, max_chunks=7)
+        assert torch.equal(i, want_i) and torch.equal(v.view(torch.int32), want_v.view(torch.int32))
+    assert ev.evaluate_embeddings_streamed(tu, torch.from_numpy(items), tl, first_rows=first) == ev.evaluate_embeddings(tu, dev(items), tl)
+    # a shard of a larger catalog: global ids = id_base + local row
+    v, i = ev.topk_embeddings_streamed(tu, torch.from_numpy(items[N // 2:]), min(k, N - N // 2), id_base=N // 2, n_total=N, first_rows=first)
+    wv, wi = ev.topk_embeddings(tu, ShardedItemTable(dev(items[N // 2:]), id_base=N // 2, n_total=N), min(k, N - N // 2))
+    assert torch.equal(i, wi) and torch.equal(v.view(torch.int32), wv.view(torch.int32))
