@@ -34,8 +34,13 @@ constexpr int kBlockN = 256;   // items per tile (TMEM columns per accumulator s
 // k-block = fp32 elements per pipeline stage and row: BK = 32 -> 128-byte rows (SWIZZLE_128B), BK = 16 -> 64-byte rows
 // (SWIZZLE_64B): half-size stages, more of them in flight (template parameter BK of the kernel)
 constexpr int kUmmaK = 8;      // tf32: 32 bytes of K per tcgen05.mma
-constexpr int kEpiGroups = 1;  // epilogue warp groups (4 warps each); group g drains accumulator stage g
-constexpr int kThreads = 128 + 128 * kEpiGroups;
+// Epilogue warp groups (4 warps each; template parameter EG of the kernel): with EG = 2, group g drains accumulator
+// stage g, i.e. every second tile, with its own per-row candidate buffers and lists.  Every mode runs ONE group by
+// default.  Two groups were measured for the epilogue-bound bf16-compat mode at BASELINE config 5
+// (MR_SCORE_BF16_EPI_GROUPS=2): 140.4 ms against 121.7 ms with one group, identical lists -- each group sees only every
+// second tile, so its per-row threshold rises half as fast, twice as many candidates pass the filter and twice as many
+// lists are sorted and merged; the filter, not the number of warps draining TMEM, is what has to get cheaper.
+constexpr int kMaxEpiGroups = 2;
 constexpr int kCap = 256;      // per-row candidate buffer (keys); power of two, >= 2 * MR_MAX_FUSED_TOPK
 constexpr int kChunk = 16;     // accumulator columns per tcgen05.ld
 constexpr int kAccStages = 2;
@@ -60,9 +65,9 @@ struct Params {
     int QB;       // query blocks = ceil(Q / (128 * CG))
     int S;        // item splits
     int QG;       // query blocks per L2 group
-    u64* cand;    // grid * kEpiGroups * 128 * kCap keys
-    float* out_val;     // (S * kEpiGroups, Q, K)
-    int32_t* out_id;    // (S * kEpiGroups, Q, K)
+    u64* cand;    // grid * EG * 128 * kCap keys
+    float* out_val;     // (S * EG, Q, K)
+    int32_t* out_id;    // (S * EG, Q, K)
     long long* dbg;     // optional timestamps of block 0 (mr_score_topk_debug_buffer), else NULL
     int l2_hint;        // 1: query loads evict_last, item loads evict_first (MR_SCORE_L2HINT, default on)
 };
@@ -376,8 +381,8 @@ __device__ __forceinline__ void warp_write_list(const Params& p, size_t o, const
     }
 }
 
-template <int CG, int BK, bool BF16>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CG, int BK, bool BF16, int EG>
+__global__ void __launch_bounds__(128 + 128 * EG, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_constant__ CUtensorMap map_ulo,
                   const __grid_constant__ CUtensorMap map_ihi, const __grid_constant__ CUtensorMap map_ilo,
                   const Params p) {
@@ -534,7 +539,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
         const int grp = (warp - 4) >> 2;
         const int ew = (warp - 4) & 3;
         const int row = ew * 32 + lane;
-        u64* warp_buf = p.cand + (((size_t)blockIdx.x * kEpiGroups + grp) * kBlockM + ew * 32) * kCap;
+        u64* warp_buf = p.cand + (((size_t)blockIdx.x * EG + grp) * kBlockM + ew * 32) * kCap;
         u64* my_buf = warp_buf + (size_t)lane * kCap;
         const int K = p.K;
         uint32_t it = 0;
@@ -546,7 +551,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
             uint32_t thr = 0;                        // score key of the row's K-th best so far (0: list not full)
             float thr_f = __int_as_float(0x7FC00000);  // same threshold as a float; NaN = "everything passes"
             for (int t = u.t0; t < u.t1; ++t, ++it) {
-                if (kEpiGroups > 1 && (int)(it & 1) != grp) continue;   // two groups: group g drains stage g
+                if (EG > 1 && (int)(it & 1) != grp) continue;   // two groups: group g drains stage g
                 const uint32_t acc = it & 1;
                 if (threadIdx.x == 128) dbg_stamp(p, 2, it, 0);
                 mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1, 4);
@@ -661,7 +666,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                 warp_load_keys(ka, warp_buf + (size_t)L * kCap, na, lane);
                 warp_load_keys(kb, warp_buf + (size_t)(L + 1) * kCap, nb, lane);
                 warp_sort256x2(ka, kb, lane);
-                const size_t list = (size_t)u.split * kEpiGroups + grp;
+                const size_t list = (size_t)u.split * EG + grp;
                 warp_write_list(p, (list * p.Q + qL) * K, ka, K, lane);
                 if (qL + 1 < p.Q) warp_write_list(p, (list * p.Q + qL + 1) * K, kb, K, lane);
                 __syncwarp();
@@ -710,15 +715,16 @@ static bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int E, int
 }
 
 struct Plan {
-    int cg, bk, QB, T, S, QG, grid;
+    int cg, bk, eg, QB, T, S, QG, grid;
     int64_t cand_bytes, part_bytes;
 };
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
-static Plan make_plan(int64_t Q, int64_t N, int K) {
+static Plan make_plan(int64_t Q, int64_t N, int K, bool bf16) {
     Plan pl;
+    pl.eg = (bf16 && env_int("MR_SCORE_BF16_EPI_GROUPS", 1) == 2) ? 2 : 1;
     pl.cg = env_int("MR_SCORE_CTA_GROUP", 2) == 1 ? 1 : 2;
     pl.bk = env_int("MR_SCORE_BK", 32) == 16 ? 16 : 32;
     const int sms = sm_count();
@@ -729,7 +735,7 @@ static Plan make_plan(int64_t Q, int64_t N, int K) {
     // item splits: each unit pays a top-K warm-up (its first tiles pass everything and trigger bursts of row sorts),
     // measured at roughly (8 + K / 5) tile-times; units are executed in waves of `clusters`.  Pick the S that
     // minimises waves * (tiles per unit + warm-up).
-    int smax = 8192 / (kEpiGroups * (K > 0 ? K : 1));  // mr_topk_merge takes at most 8192 candidates per row
+    int smax = 8192 / (pl.eg * (K > 0 ? K : 1));  // mr_topk_merge takes at most 8192 candidates per row
     if (smax > pl.T) smax = pl.T;
     if (smax < 1) smax = 1;
     int s = env_int("MR_SCORE_SPLITS", 0);
@@ -754,20 +760,20 @@ static Plan make_plan(int64_t Q, int64_t N, int K) {
     const int64_t units = (int64_t)pl.QB * pl.S;
     pl.grid = (int)((units < clusters ? units : clusters) * pl.cg);
     if (pl.grid < pl.cg) pl.grid = pl.cg;
-    pl.cand_bytes = (int64_t)sms * kEpiGroups * kBlockM * kCap * 8;
-    pl.part_bytes = (int64_t)pl.S * kEpiGroups * Q * K * 8;
+    pl.cand_bytes = (int64_t)sms * pl.eg * kBlockM * kCap * 8;
+    pl.part_bytes = (int64_t)pl.S * pl.eg * Q * K * 8;
     return pl;
 }
 
-template <int CG, int BK, bool BF16>
+template <int CG, int BK, bool BF16, int EG>
 static int launch(const Plan& pl, const CUtensorMap& muh, const CUtensorMap& mul, const CUtensorMap& mih, const CUtensorMap& mil,
                   const Params& p, cudaStream_t stream) {
     using C = Cfg<CG, BK, BF16>;
-    cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<CG, BK, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<CG, BK, BF16, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("mr_score_topk: shared memory attribute: %s", cudaGetErrorString(e)); return (int)e; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(128 + 128 * EG);
     cfg.dynamicSmemBytes = C::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -777,7 +783,7 @@ static int launch(const Plan& pl, const CUtensorMap& muh, const CUtensorMap& mul
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, score_topk_kernel<CG, BK, BF16>, muh, mul, mih, mil, p);
+    e = cudaLaunchKernelEx(&cfg, score_topk_kernel<CG, BK, BF16, EG>, muh, mul, mih, mil, p);
     if (e != cudaSuccess) { set_error("mr_score_topk: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return MR_OK;
 }
@@ -801,8 +807,10 @@ extern "C" int64_t mr_score_topk_workspace_bytes(int64_t Q, int64_t N, int E, in
         return MR_ERR_INVALID_ARG;
     }
     if (Q == 0) return 0;
-    const st::Plan pl = st::make_plan(Q, N, K);
-    return pl.cand_bytes + pl.part_bytes + 256;
+    // sized for the mode that needs the most scratch (bf16-compat: two epilogue groups), so one query serves every mode
+    const st::Plan pa = st::make_plan(Q, N, K, false), pb = st::make_plan(Q, N, K, true);
+    const int64_t a = pa.cand_bytes + pa.part_bytes, b = pb.cand_bytes + pb.part_bytes;
+    return (a > b ? a : b) + 256;
 }
 
 extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, const float* Ihi, const float* Ilo, int64_t N,
@@ -828,7 +836,7 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
         if (e != cudaSuccess) { set_error("mr_score_topk: memset: %s", cudaGetErrorString(e)); return (int)e; }
         return MR_OK;
     }
-    const st::Plan pl = st::make_plan(Q, N, K);
+    const st::Plan pl = st::make_plan(Q, N, K, bf16);
     const int64_t need = pl.cand_bytes + pl.part_bytes + 256;
     if (!ws || ws_bytes < need) {
         set_error("mr_score_topk: workspace of %lld bytes needed, %lld given", (long long)need, (long long)ws_bytes);
@@ -858,9 +866,10 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     if (!ok) { set_error("mr_score_topk: cuTensorMapEncodeTiled failed (driver without TMA support?)"); return MR_ERR_UNSUPPORTED; }
 
     int rc;
-    if (bf16) rc = pl.cg == 1 ? st::launch<1, 32, true>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 32, true>(pl, muh, mul, mih, mil, p, s);
-    else if (bk == 32) rc = pl.cg == 1 ? st::launch<1, 32, false>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 32, false>(pl, muh, mul, mih, mil, p, s);
-    else rc = pl.cg == 1 ? st::launch<1, 16, false>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 16, false>(pl, muh, mul, mih, mil, p, s);
+    if (bf16 && pl.eg == 2) rc = pl.cg == 1 ? st::launch<1, 32, true, 2>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 32, true, 2>(pl, muh, mul, mih, mil, p, s);
+    else if (bf16) rc = pl.cg == 1 ? st::launch<1, 32, true, 1>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 32, true, 1>(pl, muh, mul, mih, mil, p, s);
+    else if (bk == 32) rc = pl.cg == 1 ? st::launch<1, 32, false, 1>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 32, false, 1>(pl, muh, mul, mih, mil, p, s);
+    else rc = pl.cg == 1 ? st::launch<1, 16, false, 1>(pl, muh, mul, mih, mil, p, s) : st::launch<2, 16, false, 1>(pl, muh, mul, mih, mil, p, s);
     if (rc != MR_OK) return rc;
-    return mr_topk_merge(part_val, part_id, pl.S * st::kEpiGroups, Q, K, K, out_val, out_id, stream);
+    return mr_topk_merge(part_val, part_id, pl.S * pl.eg, Q, K, K, out_val, out_id, stream);
 }

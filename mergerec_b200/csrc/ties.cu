@@ -825,6 +825,17 @@ struct SpecState {     // per model, staged in shared memory
     u64 lo, hi, mid;
 };
 
+// Rare path of the speculative pass, out of line: the key of an in-window element is appended to the thread's private
+// candidate list of model k and the provisional cut decides whether the element survives for now.
+static __device__ __noinline__ float spec_collect(int k, float u, int64_t j, const SpecState* s_st, uint32_t* s_cnt,
+                                           const PassCounters& pc, int64_t gsz, int64_t gtid) {
+    const u64 key = ties_key(__float_as_uint(u) & 0x7FFFFFFFu, j);
+    const uint32_t n = s_cnt[k * kTiesThreads + threadIdx.x];
+    if (n < (uint32_t)pc.cand_cap) pc.cand_keys[((size_t)k * gsz + gtid) * pc.cand_cap + n] = key;
+    s_cnt[k * kTiesThreads + threadIdx.x] = n + 1;
+    return (key >= s_st[k].mid) ? u : 0.0f;
+}
+
 template <int K, int MODE, bool VEC>
 __global__ void __launch_bounds__(kTiesThreads, K <= 8 ? 2 : 1)
 ties_spec_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, const TiesState* __restrict__ st,
@@ -978,28 +989,15 @@ ties_spec_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             float sc[K];
-            bool hit = false;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const float u = __fsub_rn(xs[k][c], bx[c]);
                 const uint32_t t = (__float_as_uint(u) & 0x7FFFFFFFu) - lom[k];
                 below2[k >> 1] += (t >> 31) << (16 * (k & 1));      // magnitude below the bracket: trimmed
-                hit |= t <= span[k];                                  // inside the bracket's magnitude window
                 sc[k] = ((int)t >= 0) ? u : 0.0f;
-            }
-            if (hit) {   // rare (~6 % of the columns at K = 8): collect the in-window keys, the provisional cut decides
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float u = __fsub_rn(xs[k][c], bx[c]);
-                    const uint32_t mag = __float_as_uint(u) & 0x7FFFFFFFu;
-                    if (mag - lom[k] <= span[k]) {
-                        const u64 key = ties_key(mag, j0 + c);
-                        const uint32_t n = s_cnt[k * kTiesThreads + threadIdx.x];
-                        if (n < (uint32_t)pc.cand_cap) pc.cand_keys[((size_t)k * gsz + gtid) * pc.cand_cap + n] = key;
-                        s_cnt[k * kTiesThreads + threadIdx.x] = n + 1;
-                        sc[k] = (key >= s_st[k].mid) ? u : 0.0f;
-                    }
-                }
+                // inside the bracket's magnitude window (0.4 % of the elements, but some lane of a warp hits in one of
+                // nine (model, column) pairs): ONE out-of-line copy of the collection path instead of 32 inlined ones
+                if (t <= span[k]) sc[k] = spec_collect(k, u, j0 + c, s_st, s_cnt, pc, gsz, gtid);
             }
             uint32_t eb;
             ties_elect<K, false>(sc, lo_ok, res[c], eb);
