@@ -359,7 +359,7 @@ class TiesCfg2(LambdaMergeK8):
                     "two-pass pipeline, build only (ties_build_kernel<8, VECTORS, vec4>)": {"ms": ms_build, "GB/s": self.bytes_build / GB / (ms_build * 1e-3), "bytes": self.bytes_build},
                     "lambda-gradient reduction (lambda_grad_kernel, incl. host pointer-table upload)": {"ms": ms_lgrad, "GB/s": lgrad_bytes / GB / (ms_lgrad * 1e-3), "bytes": lgrad_bytes},
                     "lambda merge (merge_kernel)": {"ms": ms_merge, "GB/s": self.bytes_merge / GB / (ms_merge * 1e-3), "bytes": self.bytes_merge},
-                    "fused TIES + lambda merge, That never materialised (merge_ties_lambda: select + fused build)": {"ms": ms_fused, "GB/s": self.bytes_merge / GB / (ms_fused * 1e-3), "bytes": self.bytes_merge},
+                    "fused TIES + lambda merge in one pass, That never materialised (merge_ties_lambda)": {"ms": ms_fused, "GB/s": self.bytes_merge / GB / (ms_fused * 1e-3), "bytes": self.bytes_merge},
                 }}, "ties_spec_kernel")
 
     def extra(self):
@@ -1370,7 +1370,7 @@ class MergeCfg4(TiesCfg2):
                     "task-arithmetic merge from models (merge_kernel, A1)": {"ms": ms_arith, "GB/s": self.bytes_arith / GB / (ms_arith * 1e-3), "bytes": self.bytes_arith},
                     "ties_select (sample + 1 full pass + finish)": {"ms": ms_select, "GB/s": sel_bytes / GB / (ms_select * 1e-3), "bytes": sel_bytes},
                     "task-wise lambda merge of That (merge_kernel, A3)": {"ms": ms_merge, "GB/s": self.bytes_merge / GB / (ms_merge * 1e-3), "bytes": self.bytes_merge},
-                    "fused TIES + lambda merge, That never materialised (merge_ties_lambda: select + fused build)": {"ms": ms_fused, "GB/s": self.bytes_merge / GB / (ms_fused * 1e-3), "bytes": self.bytes_merge},
+                    "fused TIES + lambda merge in one pass, That never materialised (merge_ties_lambda)": {"ms": ms_fused, "GB/s": self.bytes_merge / GB / (ms_fused * 1e-3), "bytes": self.bytes_merge},
                 }}
 
     def extra(self):

@@ -155,7 +155,7 @@ def merge_ties(base_model: FlattenedModel, models: List[FlattenedModel], weights
 def merge_ties_lambda(base_model: FlattenedModel, models: List[FlattenedModel], density: float, w: torch.Tensor,
                       seg_end: Optional[torch.Tensor] = None, seg_group: Optional[torch.Tensor] = None,
                       cut: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                      one_pass: bool = False) -> FlattenedModel:
+                      one_pass: bool = True) -> FlattenedModel:
     """Extension: ``get_ties_vectors`` followed by the (task- or layer-wise) lambda merge in ONE pass that never
     materialises the (K, d) TIES vectors.  Bit-identical to
     ``base + (w[g][:, None] * get_ties_vectors(...)).sum(0)`` evaluated block by block like
@@ -166,9 +166,9 @@ def merge_ties_lambda(base_model: FlattenedModel, models: List[FlattenedModel], 
         out = torch.empty_like(base_model)
     assert w.dtype == torch.float32 and w.is_contiguous() and w.shape[-1] == K
     if cut is None and one_pass:
-        # one pass over the data (select folded into the fused build).  Measured on K = 8 BLaIR-base: 2.6 ms against
-        # 2.1-2.4 ms for select + fused build -- this mode's pass is instruction-bound (1.13 G warp-instructions, 26 % of
-        # the warp samples waiting on instruction fetch), so the two-pass form stays the default here
+        # one pass over the data (select folded into the fused build).  Measured on K = 8 BLaIR-base: 2.3 ms against
+        # 2.46 ms for select + fused build in the same run (`one_pass=False`); this mode's pass is instruction-bound
+        # (1.1 G warp-instructions), not HBM-bound
         select_build(base_model, rows, ties_topk_count(density, base_model.numel()), _lib.MR_TIES_FUSED_MERGE, out, w=w,
                      G=w.numel() // K, seg_end=seg_end, seg_group=seg_group)
         return out
