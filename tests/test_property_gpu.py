@@ -124,11 +124,14 @@ def test_ties_family(K, d, shift, seed, density, quant, specials):
     assert np.array_equal(host(cut).view(np.uint64), ocut), "cut keys"
     assert np.array_equal(host(trim), otrim) and np.array_equal(host(elect), oelect), "masks"
     assert_bit_equal(host(That), oT, "TIES vectors")
+    assert_bit_equal(host(get_ties_vectors(tb, tm, density)), oT, "TIES vectors, one-pass select + build")
     w = [float(x) for x in rng.uniform(0.1, 1.0, size=K)]
     assert_bit_equal(host(merge_ties(tb, tm, w, density)), orc.merge_ties(base, models, w, density), "merge_ties")
     lam = rng.uniform(0.1, 0.5, size=(1, K)).astype(np.float32)
     fused = merge_ties_lambda(tb, tm, density, dev(lam))
     assert_bit_equal(host(fused), orc.lambda_merge(base, oT, lam), "fused TIES + lambda merge")
+    assert_bit_equal(host(merge_ties_lambda(tb, tm, density, dev(lam), one_pass=False)), orc.lambda_merge(base, oT, lam),
+                     "fused TIES + lambda merge, two-pass form")
     assert_bit_equal(host(get_localize_and_stitch_vectors(tb, tm, density)), orc.lns_vectors(base, models, density),
                      "localize-and-stitch vectors")
     # the sharded merger's select (per-slice estimate + windowed radix levels + tie scan) on a single rank
