@@ -598,7 +598,7 @@ class EvalCatalog(Workload):
         self.h_users = _pinned(self.users.cpu())
         self.h_items = _pinned(self.items.cpu())
         self.h_labels = _pinned(self.labels.cpu())
-        self.h2d_bytes = self.h_users.numel() * 4 + self.h_items.numel() * 4 + self.h_labels.numel() * 8
+        self.h2d_bytes = -(-self.h_users.shape[0] // self.world) * self.E * 4 + self.h_items.numel() * 4 + self.h_labels.numel() * 8
         self.d2h_bytes = self.Q * 4          # the rank of each label; the metric floats are finished on the host
 
     def step_e2e(self):
@@ -606,7 +606,8 @@ class EvalCatalog(Workload):
         (`Evaluator.evaluate_embeddings_streamed`): H2D of the queries and labels, then this rank's item rows in
         geometrically growing chunks on a copy stream while the previous chunk is split and scored, merge of the chunk
         lists, exchange, label rank, D2H of the ranks, host finalisation."""
-        users = self.h_users.to(self.device, non_blocking=True)
+        from mergerec_b200.evaluator import replicate_from_host
+        users = replicate_from_host(self.h_users, self.group)      # 1/N of the queries per rank over PCIe, all-gather over NVLink
         labels = self.h_labels.to(self.device, non_blocking=True)
         self.last = self.ev.evaluate_embeddings_streamed(users, self.h_items, labels, id_base=self.lo, n_total=self.N,
                                                          group=self.group, mode=self.mode)

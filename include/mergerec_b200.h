@@ -178,6 +178,11 @@ int mr_topk_merge(const float* vals, const int32_t* ids, int L, int64_t Q, int K
 int mr_topk_merge_packed(const void* packed, int L, int64_t Q, int K_in, int K_out, float* out_val, int32_t* out_id,
                          mr_stream_t stream);
 
+/* HOST helper (no device work): the value CPython's builtin sum() gives for the n doubles of x -- the reference's
+ * `sum(ndcgs) / len(ndcgs)`, evaluator/metrics.py:61, 88.  compensated != 0: Neumaier summation as in CPython >= 3.12
+ * (Python/bltinmodule.c); 0: plain left-to-right addition (older interpreters).  x: host pointer. */
+double mr_float_sum(const double* x, int64_t n, int compensated);
+
 /* rank[q] = position of labels[q] in ids[q, :K], or -1          ref: evaluator/metrics.py:51-59, 79-84 */
 int mr_label_rank(const int32_t* ids, int64_t Q, int K, const int64_t* labels, int32_t* rank, mr_stream_t stream);
 

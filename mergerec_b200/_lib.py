@@ -38,6 +38,7 @@ SIGNATURES = {
     "mr_topk_rows": ([_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp], C.c_int),
     "mr_topk_merge": ([_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp], C.c_int),
     "mr_topk_merge_packed": ([_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp], C.c_int),
+    "mr_float_sum": ([_vp, _i64, _i32], C.c_double),
     "mr_label_rank": ([_vp, _i64, _i32, _vp, _vp, _vp], C.c_int),
     "mr_score_topk_workspace_bytes": ([_i64, _i64, _i32, _i32], _i64),
     "mr_score_topk": ([_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp], C.c_int),

@@ -240,4 +240,6 @@ class Evaluator:
     def metrics_from_ids(self, ids: torch.Tensor, labels: torch.Tensor, metric_prefix: str = "") -> Dict[str, float]:
         """One rank lookup on the GPU (Q int32 back to the host), then every (metric, k) from the same ranks."""
         ranks = label_rank(ids, labels).cpu().numpy()
-        return {metric_prefix + m.name: m.from_ranks(ranks) for m in self._metrics}
+        found = ranks.compress(ranks >= 0)     # compressed once; row order (= the reference's summation order) is kept
+        n = int(ranks.shape[0])
+        return {metric_prefix + m.name: m.from_found(found, n) for m in self._metrics}

@@ -42,6 +42,10 @@ def main() -> int:
             for _ in range(2):                                                               # second call reuses the scratch
                 sv, si = ev.topk_embeddings(q, table, k)
                 ok &= bool(torch.equal(si, full_i)) and bool(torch.equal(sv.view(torch.int32), full_v.view(torch.int32)))
+            # the replicated queries: 1/world per rank over PCIe + one all-gather == a plain copy
+            from mergerec_b200.evaluator import replicate_from_host
+            ok &= bool(torch.equal(replicate_from_host(torch.from_numpy(users), dist.group.WORLD), tu))
+            ok &= bool(torch.equal(replicate_from_host(torch.from_numpy(labels), dist.group.WORLD), tl))
             # host-resident shard streamed in chunks behind the scoring, then the same exchange
             from mergerec_b200.evaluator import shard_bounds
             lo_i, hi_i = shard_bounds(N, world, rank)

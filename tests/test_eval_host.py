@@ -82,6 +82,22 @@ def test_fast_metric_finalisation_equals_the_row_loop():
         got_r, got_n = recall_from_ranks(ranks, k), ndcg_from_ranks(ranks, k)
         assert isinstance(got_r, float) and isinstance(got_n, float)
         assert got_r.hex() == float(want_r).hex() and got_n.hex() == float(want_n).hex()
+        found = ranks[ranks >= 0]              # the compressed form `metrics_from_ids` uses
+        assert Recall(k).from_found(found, n).hex() == float(want_r).hex() and NDCG(k).from_found(found, n).hex() == float(want_n).hex()
+
+
+def test_float_sum_helper_is_the_interpreters_sum():
+    """`mr_float_sum` must return exactly what the running interpreter's builtin `sum()` returns for a list of floats
+    (Neumaier-compensated on CPython >= 3.12): random magnitudes, cancellation, long lists, the NDCG gain values."""
+    from mergerec_b200.evaluator.metrics import _python_float_sum
+    rng = np.random.default_rng(11)
+    t = _gain_table(128)
+    cases = [rng.standard_normal(n) * 10.0 ** rng.integers(-8, 8) for n in (1, 2, 3, 17, 1000, 65536)]
+    cases += [t[rng.integers(0, 100, size=40000)], np.array([1e16, 1.0, -1e16, 1.0]), np.array([0.1] * 1000),
+              rng.standard_normal(5000) * np.exp(rng.uniform(-30, 30, 5000))]
+    for x in cases:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert _python_float_sum(x).hex() == float(sum(x.tolist())).hex()
 
 
 def _free_port():
