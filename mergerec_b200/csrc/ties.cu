@@ -89,6 +89,8 @@ struct PassCounters {
     u64* cand_keys;      // K * n_threads * cand_cap
     int cand_cap;
     int64_t j_off;       // global index of local element 0 (sharded select: keys carry GLOBAL indices); 0 otherwise
+    u64* sample_keys;    // optional, sample passes only: the composite key of every sampled element, (K, sample_ld); the
+    int64_t sample_ld;   // second look at the same sample then reads this contiguous cache instead of striding again
 };
 
 // Shared-memory layout of the pass kernel (dynamic): hist[K][bins] u32 | lo[K] hi[K] u64 | shift[K] i32 |
@@ -221,7 +223,14 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
             const int64_t pos = i >> 1;
             q = pos * stride + (int64_t)((((uint32_t)pos * 2654435761u) >> 8) % (uint32_t)stride);
             q = (q & ~(int64_t)1) + (i & 1);
-            if (q >= nq) continue;   // the last window may be cut short
+            if (q >= nq) {           // the last window may be cut short
+                if (pc.sample_keys)
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) pc.sample_keys[(size_t)k * pc.sample_ld + i * 4 + c] = 0;   // 0 = no element
+                continue;
+            }
         }
         const int64_t j0 = q << 2;
         if (VEC && q < nq_full) {
@@ -243,6 +252,13 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
                     MR_TIES_EDGE(k, m2, j0 + 2);
                     MR_TIES_EDGE(k, m3, j0 + 3);
                 }
+                if (stride > 1 && pc.sample_keys) {
+                    u64* sk = pc.sample_keys + (size_t)k * pc.sample_ld + i * 4;
+                    sk[0] = ties_key(m0, j0 + pc.j_off);
+                    sk[1] = ties_key(m1, j0 + 1 + pc.j_off);
+                    sk[2] = ties_key(m2, j0 + 2 + pc.j_off);
+                    sk[3] = ties_key(m3, j0 + 3 + pc.j_off);
+                }
             }
             visited += 4;
         } else {
@@ -255,8 +271,13 @@ ties_pass_kernel(const float* __restrict__ base, PtrPack<K> models, int64_t d, c
                     bool hit = false;
                     MR_TIES_MAG(k, models.p[k][j0 + c], b, m0);
                     if (hit) MR_TIES_EDGE(k, m0, j0 + c);
+                    if (stride > 1 && pc.sample_keys) pc.sample_keys[(size_t)k * pc.sample_ld + i * 4 + c] = ties_key(m0, j0 + c + pc.j_off);
                 }
             }
+            if (stride > 1 && pc.sample_keys)
+                for (int c = nvalid; c < 4; ++c)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) pc.sample_keys[(size_t)k * pc.sample_ld + i * 4 + c] = 0;
             visited += (uint32_t)nvalid;
         }
     }
@@ -321,6 +342,39 @@ ties_cand_hist_kernel(const TiesState* __restrict__ st, const uint32_t* __restri
         if (v) atomicAdd(&hist[k * kTiesBins + i], v);
     }
     if (above && threadIdx.x == 0 && s_not_above) atomicAdd(&above[k], (u64)0 - (u64)s_not_above);   // two's-complement subtract
+}
+
+// ---- second look at the sparse sample: histogram of the cached keys inside the current bracket ------------------------------
+// Same counters as a sample pass over the data would produce (hist of the keys in [lo, hi], `above` = keys > hi), read
+// from the contiguous key cache the first pass wrote (34 MB at K = 8) instead of striding over the K + 1 vectors again.
+static __global__ void __launch_bounds__(256)
+ties_keys_hist_kernel(const TiesState* __restrict__ st, const u64* __restrict__ keys, int64_t ld, int64_t n,
+                      uint32_t* __restrict__ hist, u64* __restrict__ above) {
+    __shared__ uint32_t s_hist[kTiesBins];
+    __shared__ uint32_t s_above;
+    const int k = blockIdx.y;
+    const TiesState s = st[k];
+    if (s.status != TIES_ST_SEARCH) return;
+    for (int i = threadIdx.x; i < kTiesBins; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_above = 0;
+    __syncthreads();
+    uint32_t ab = 0;
+    const u64* row = keys + (size_t)k * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const u64 key = row[i];
+        if (key == 0) continue;                    // slot without an element (cut-short last window)
+        if (key > s.hi) ++ab;
+        else if (key >= s.lo) atomicAdd(&s_hist[(uint32_t)((key - s.lo) >> s.shift)], 1u);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ab += __shfl_xor_sync(0xffffffffu, ab, off);
+    if ((threadIdx.x & 31) == 0 && ab) atomicAdd(&s_above, ab);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTiesBins; i += blockDim.x) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(&hist[k * kTiesBins + i], v);
+    }
+    if (threadIdx.x == 0 && s_above) atomicAdd(&above[k], (u64)s_above);
 }
 
 // ---- pick: turn a histogram into a narrower bracket ---------------------------------------------------
@@ -1329,6 +1383,8 @@ struct TiesWs {
     uint32_t* cand_cnt;  // K * n_lists
     u64* fin_keys;       // K * final cap
     u64* cand_keys;      // K * n_lists * cand_cap
+    u64* sample_keys;    // K * sample_ld: key cache of the sparse sample (NULL when the "sample" is the whole vector)
+    int64_t sample_ld;
     size_t zero_bytes;   // bytes from hist to the end of fin_cnt
     int n_lists, cand_cap;
     size_t total;
@@ -1394,6 +1450,9 @@ static TiesWs ties_layout(void* ws, int64_t d, int K) {
     L.cand_cnt = reinterpret_cast<uint32_t*>(p + off); off += align256((size_t)K * n_lists * 4);
     L.fin_keys = reinterpret_cast<u64*>(p + off); off += align256((size_t)K * kTiesFinalCap * 8);
     L.cand_keys = reinterpret_cast<u64*>(p + off); off += align256((size_t)K * n_lists * (size_t)cap * 8);
+    L.sample_ld = stride > 1 ? (((n_s + 63) / 64) * 64) : 0;      // n_s = sampled elements = slots the sample pass writes
+    L.sample_keys = stride > 1 ? reinterpret_cast<u64*>(p + off) : nullptr;
+    off += align256((size_t)K * (size_t)L.sample_ld * 8);
     L.total = off;
     return L;
 }
@@ -1401,11 +1460,12 @@ static TiesWs ties_layout(void* ws, int64_t d, int K) {
 template <int K>
 static int ties_launch_pass(const float* base, const float* const* models, int64_t d, const float* w, int64_t stride,
                             int collect /* 0 none, 1 magnitude window (fast path), 2 exact */, const TiesWs& L, cudaStream_t st,
-                            int64_t j_off = 0, bool zero_counters = true) {
+                            int64_t j_off = 0, bool zero_counters = true, bool save_sample_keys = false) {
     PtrPack<K> pack;
     bool vec = host_aligned16(base);
     for (int k = 0; k < K; ++k) { pack.p[k] = models[k]; vec = vec && host_aligned16(models[k]); }
-    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap, j_off};
+    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap, j_off,
+                    (save_sample_keys && stride > 1) ? L.sample_keys : nullptr, L.sample_ld};
     const size_t smem = PassSmem<K>::bytes();
     const int blocks = ties_pass_blocks(K);   // (sample passes too: a smaller grid makes them latency-bound, 70 -> 236 us)
     if (zero_counters) {
@@ -1427,6 +1487,32 @@ static int ties_launch_pass(const float* base, const float* const* models, int64
     }
 #undef MR_PASS
     MR_CUDA_LAUNCH_CHECK("mr_ties_select(pass)");
+    return MR_OK;
+}
+
+// The two looks at the sparse sample that bracket the cut: the first strides over the vectors (and caches every sampled
+// key), the second histograms the cached keys inside the first bracket.  With stride 1 (small vectors) both are passes
+// over the data.
+template <int K>
+static int ties_sparse_brackets(const float* base, const float* const* models, int64_t d, const float* w, int64_t k_cnt,
+                                const TiesWs& L, int32_t* status, cudaStream_t st) {
+    const int64_t stride = ties_sample_stride(d);
+    const int64_t n_s = ties_sample_count(d, stride);
+    int64_t r_hi, r_lo;
+    ties_sample_ranks(d, k_cnt, n_s, &r_hi, &r_lo);
+    int rc = ties_launch_pass<K>(base, models, d, w, stride, 0, L, st, 0, true, true);
+    if (rc != MR_OK) return rc;
+    ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, r_hi, r_lo, 0, status);
+    if (stride > 1 && L.sample_keys) {
+        cudaError_t e = cudaMemsetAsync(L.hist, 0, L.zero_bytes, st);
+        if (e != cudaSuccess) { set_error("mr_ties_select: memset: %s", cudaGetErrorString(e)); return (int)e; }
+        dim3 grid(64, (unsigned)K);
+        ties_keys_hist_kernel<<<grid, 256, 0, st>>>(L.st, L.sample_keys, L.sample_ld, n_s, L.hist, L.above);
+    } else {
+        rc = ties_launch_pass<K>(base, models, d, w, stride, 0, L, st);
+        if (rc != MR_OK) return rc;
+    }
+    ties_pick_kernel<<<K, kTiesBins, 0, st>>>(L.st, L.hist, L.above, r_hi, r_lo, 0, status);
     return MR_OK;
 }
 
@@ -1490,16 +1576,9 @@ extern "C" int mr_ties_select(const float* base, const float* const* models, int
     ties_init_kernel<<<1, 32, 0, st>>>(L.st, K, reinterpret_cast<u64*>(cut), status, k_cnt, d);
     MR_CUDA_LAUNCH_CHECK("mr_ties_select(init)");
     if (k_cnt <= 0 || k_cnt >= d) return MR_OK;
-    const int64_t stride = ties_sample_stride(d);
-    const int64_t n_s = ties_sample_count(d, stride);
-    int64_t r_hi, r_lo;
-    ties_sample_ranks(d, k_cnt, n_s, &r_hi, &r_lo);
     MR_DISPATCH_K(K, {
-        for (int it = 0; it < 2; ++it) {  // two sample passes: 2^63 -> quarter-octave bins -> ~1 % bracket
-            rc = ties_launch_pass<KK>(base, models, d, w, stride, 0, L, st);
-            if (rc != MR_OK) return rc;
-            ties_pick_kernel<<<KK, kTiesBins, 0, st>>>(L.st, L.hist, L.above, r_hi, r_lo, 0, status);
-        }
+        rc = ties_sparse_brackets<KK>(base, models, d, w, k_cnt, L, status, st);   // 2^63 -> quarter-octave bins -> ~1 % bracket
+        if (rc != MR_OK) return rc;
         rc = ties_launch_pass<KK>(base, models, d, w, 1, 1, L, st);
         if (rc != MR_OK) return rc;
     });
@@ -1700,9 +1779,10 @@ extern "C" int mr_ties_select_build(const float* base, const float* const* model
     // error of the sample quantile, i.e. to 1 / sqrt(sample size).
     static const int64_t dense_quads = []() { const char* e = getenv("MR_TIES_SPEC_SAMPLE_QUADS"); return e ? atoll(e) : 4 * kTiesSampleQuads; }();
     MR_DISPATCH_K(K, {
-        for (int it = 0; it < 3; ++it) {
-            const int64_t stride = ties_sample_stride(d, it < 2 ? kTiesSampleQuads : dense_quads);
-            if (it == 2 && stride >= ties_sample_stride(d)) break;     // small vectors: the sparse sample is already everything
+        rc = ties_sparse_brackets<KK>(base, models, d, nullptr, k_cnt, L, status, st);
+        if (rc != MR_OK) return rc;
+        const int64_t stride = ties_sample_stride(d, dense_quads);
+        if (stride < ties_sample_stride(d)) {      // (small vectors: the sparse sample is already everything)
             const int64_t n_s = ties_sample_count(d, stride);
             int64_t r_hi, r_lo;
             ties_sample_ranks(d, k_cnt, n_s, &r_hi, &r_lo);
@@ -1720,7 +1800,7 @@ extern "C" int mr_ties_select_build(const float* base, const float* const* model
     size_t smem = (size_t)K * (sizeof(SpecState) + 12 + (size_t)kTiesThreads * 4) + 32;
     if (!rows_out) smem += (((size_t)G * K * 4 + 15) & ~(size_t)15) + ((seg_end && seg_group) ? ((((size_t)P * 12) + 15) & ~(size_t)15) : 0);
     if (vec) smem = ((smem + 127) & ~(size_t)127) + (size_t)kSpecStages * (K + 1) * 4096 + 64;   // TMA ring + mbarriers
-    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap, 0};
+    PassCounters pc{L.hist, L.above, L.cand_cnt, L.cand_keys, L.cand_cap, 0, nullptr, 0};
     SpecLaunch S{base, models, K, d, L.st, L.mid, reinterpret_cast<const u64*>(cut), status, pc, a, smem, L.n_lists, vec, st};
     int blocks = 0;
     auto launch = rows_out ? ties_spec_launch_vectors : ties_spec_launch_fused;
