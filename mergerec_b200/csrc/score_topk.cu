@@ -70,6 +70,13 @@ struct Params {
     int32_t* out_id;    // (S * EG, Q, K)
     long long* dbg;     // optional timestamps of block 0 (mr_score_topk_debug_buffer), else NULL
     int l2_hint;        // 1: query loads evict_last, item loads evict_first (MR_SCORE_L2HINT, default on)
+    // Pacing of the units that share an item stream (NULL = off): sync[stream * sync_windows + j] counts the units whose
+    // producer has issued the loads of tile window j (sync_w tiles); a producer does not start window j + 2 before every
+    // unit of its stream has issued window j -- or a short timeout has passed: the pacing is a performance hint (it keeps
+    // the units within 2 windows of each other, so an item tile fetched by the first is still in L2 for the last), never
+    // a correctness condition, and can therefore not deadlock.
+    int32_t* sync;
+    int sync_w, sync_windows, sync_lead;
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------------
@@ -229,6 +236,8 @@ __device__ __forceinline__ void dbg_stamp(const Params& p, int role, uint32_t ti
 // ---- static unit schedule (identical in every role) ---------------------------------------------------------------
 struct Unit {
     int qb, split, t0, t1;
+    int stream;    // index of the item stream this unit walks = (query group, split): its units share every item tile
+    int members;   // units on that stream (query blocks of the group)
 };
 __device__ __forceinline__ bool get_unit(const Params& p, int u, Unit& out) {
     if (u >= p.QB * p.S) return false;
@@ -240,6 +249,8 @@ __device__ __forceinline__ bool get_unit(const Params& p, int u, Unit& out) {
     out.qb = qg0 + (r - out.split * qgn);
     out.t0 = (int)(((int64_t)out.split * p.T) / p.S);
     out.t1 = (int)(((int64_t)(out.split + 1) * p.T) / p.S);
+    out.stream = g * p.S + out.split;
+    out.members = qgn;
     return true;
 }
 
@@ -445,12 +456,32 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
         if (lane == 0) {
             uint32_t kiter = 0;
             Unit u;
-            const uint64_t pol_q = l2_policy_evict_last(), pol_i = l2_policy_evict_first();
+            // l2_hint: 1 = queries evict_last / items evict_first (default); 2..4 = experiment modes (MR_SCORE_L2HINT)
+            const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
+            uint64_t pol_q = pol_last, pol_i = pol_first;
+            if (p.l2_hint == 3) { pol_q = pol_first; pol_i = pol_last; }
+            if (p.l2_hint == 4) { pol_q = pol_last; pol_i = pol_last; }
             const bool hint = p.l2_hint != 0;
+            const bool hint_items = p.l2_hint != 2;          // 2: queries evict_last, items default policy
             for (int ui = cluster_id; get_unit(p, ui, u); ui += num_clusters) {
                 const int qrow = (u.qb * CG + (int)rank) * kBlockM;
+                int32_t* pace = p.sync ? p.sync + (size_t)u.stream * p.sync_windows : nullptr;
                 for (int t = u.t0; t < u.t1; ++t) {
                     const int nrow = t * kBlockN + (int)rank * C::kBRows;
+                    if (pace && u.members > 1) {
+                        const int r = t - u.t0;
+                        if (r > 0 && r % p.sync_w == 0) {
+                            const int j = r / p.sync_w;                     // window j starts; window j - 1 is issued
+                            if (leader) atomicAdd(&pace[j - 1], 1);
+                            if (j >= p.sync_lead) {
+                                const long long t_start = clock64();
+                                while (*reinterpret_cast<volatile int32_t*>(&pace[j - p.sync_lead]) < u.members) {
+                                    if (clock64() - t_start > 60000) break;    // ~40 us: give up, never block
+                                    __nanosleep(200);
+                                }
+                            }
+                        }
+                    }
                     dbg_stamp(p, 0, (uint32_t)(t - u.t0), 0);
 #pragma unroll 1
                     for (int kb = 0; kb < p.KB; ++kb, ++kiter) {
@@ -465,10 +496,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                         const int kc = kb * C::kElemsPerBlock;
                         if (hint) {
                             tma_load_2d_hint<CG>(sbase, &map_uhi, full, kc, qrow, pol_q);
-                            tma_load_2d_hint<CG>(sbase + (BF16 ? 1 : 2) * kABytes, &map_ihi, full, kc, nrow, pol_i);
+                            if (hint_items) tma_load_2d_hint<CG>(sbase + (BF16 ? 1 : 2) * kABytes, &map_ihi, full, kc, nrow, pol_i);
+                            else tma_load_2d<CG>(sbase + (BF16 ? 1 : 2) * kABytes, &map_ihi, full, kc, nrow);
                             if (x3) {
                                 tma_load_2d_hint<CG>(sbase + kABytes, &map_ulo, full, kc, qrow, pol_q);
-                                tma_load_2d_hint<CG>(sbase + 2 * kABytes + C::kBBytes, &map_ilo, full, kc, nrow, pol_i);
+                                if (hint_items) tma_load_2d_hint<CG>(sbase + 2 * kABytes + C::kBBytes, &map_ilo, full, kc, nrow, pol_i);
+                                else tma_load_2d<CG>(sbase + 2 * kABytes + C::kBBytes, &map_ilo, full, kc, nrow);
                             }
                         } else {
                             tma_load_2d<CG>(sbase, &map_uhi, full, kc, qrow);
@@ -716,7 +749,8 @@ static bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int E, int
 
 struct Plan {
     int cg, bk, eg, QB, T, S, QG, grid;
-    int64_t cand_bytes, part_bytes;
+    int64_t cand_bytes, part_bytes, sync_bytes;
+    int sync_w, sync_windows;
 };
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -762,6 +796,12 @@ static Plan make_plan(int64_t Q, int64_t N, int K, bool bf16) {
     if (pl.grid < pl.cg) pl.grid = pl.cg;
     pl.cand_bytes = (int64_t)sms * pl.eg * kBlockM * kCap * 8;
     pl.part_bytes = (int64_t)pl.S * pl.eg * Q * K * 8;
+    // pacing counters: (query groups x splits) streams x windows of sync_w tiles
+    pl.sync_w = env_int("MR_SCORE_PACE_TILES", 1);
+    if (pl.sync_w < 1) pl.sync_w = 0;
+    const int groups = (pl.QB + pl.QG - 1) / pl.QG;
+    pl.sync_windows = pl.sync_w ? ((pl.T + pl.S - 1) / pl.S + pl.sync_w - 1) / pl.sync_w + 2 : 0;
+    pl.sync_bytes = pl.sync_w ? (((int64_t)groups * pl.S * pl.sync_windows * 4 + 255) & ~(int64_t)255) : 0;
     return pl;
 }
 
@@ -809,7 +849,7 @@ extern "C" int64_t mr_score_topk_workspace_bytes(int64_t Q, int64_t N, int E, in
     if (Q == 0) return 0;
     // sized for the mode that needs the most scratch (bf16-compat: two epilogue groups), so one query serves every mode
     const st::Plan pa = st::make_plan(Q, N, K, false), pb = st::make_plan(Q, N, K, true);
-    const int64_t a = pa.cand_bytes + pa.part_bytes, b = pb.cand_bytes + pb.part_bytes;
+    const int64_t a = pa.cand_bytes + pa.part_bytes + pa.sync_bytes, b = pb.cand_bytes + pb.part_bytes + pb.sync_bytes;
     return (a > b ? a : b) + 256;
 }
 
@@ -837,7 +877,7 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
         return MR_OK;
     }
     const st::Plan pl = st::make_plan(Q, N, K, bf16);
-    const int64_t need = pl.cand_bytes + pl.part_bytes + 256;
+    const int64_t need = pl.cand_bytes + pl.part_bytes + pl.sync_bytes + 256;
     if (!ws || ws_bytes < need) {
         set_error("mr_score_topk: workspace of %lld bytes needed, %lld given", (long long)need, (long long)ws_bytes);
         return MR_ERR_WORKSPACE;
@@ -852,6 +892,14 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     p.cand = reinterpret_cast<mr::u64*>(w);
     p.dbg = g_score_dbg;
     p.l2_hint = st::env_int("MR_SCORE_L2HINT", 1);
+    p.sync = nullptr; p.sync_w = pl.sync_w; p.sync_windows = pl.sync_windows;
+    p.sync_lead = st::env_int("MR_SCORE_PACE_LEAD", 2);
+    if (p.sync_lead < 1) p.sync_lead = 1;
+    if (pl.sync_bytes) {
+        p.sync = reinterpret_cast<int32_t*>(w + pl.cand_bytes + pl.part_bytes);
+        cudaError_t e = cudaMemsetAsync(p.sync, 0, (size_t)pl.sync_bytes, s);
+        if (e != cudaSuccess) { set_error("mr_score_topk: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     float* part_val = reinterpret_cast<float*>(w + pl.cand_bytes);
     int32_t* part_id = reinterpret_cast<int32_t*>(w + pl.cand_bytes + pl.part_bytes / 2);
     p.out_val = part_val;
