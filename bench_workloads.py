@@ -623,15 +623,21 @@ class EvalCatalog(Workload):
         passes = 3 if self.mode == 0 else 1
         local_flops = 2.0 * self.Q * self.table.n_local * self.E
         ach = passes * local_flops / (ms * 1e-3) / 1e12
-        # a launch of a few ms runs at boost clocks (burst peak); one of hundreds of ms sits at the 1 kW power cap like
-        # a back-to-back cuBLAS loop (sustained peak).  Both TF32 peaks are measured here with cuBLAS; the figures
-        # derived from MEASURED_PEAKS.json's bf16 numbers (/ 2) are listed beside them.
+        # There is no TF32 entry in MEASURED_PEAKS.json, so the denominator is the LARGEST dense-TF32 rate this run can
+        # vouch for: cuBLAS TF32 GEMMs measured here (burst = best of 10; sustained = back to back at the 1 kW power cap)
+        # and the bf16 peaks of MEASURED_PEAKS.json halved.  (Rounds 1-2 switched between burst and sustained by launch
+        # length; since the item-stream pacing this kernel draws less DRAM power than cuBLAS and overtook the sustained
+        # figures, so the conservative choice is the maximum.)  All four fractions are listed below.
         tf32 = measure_tf32_peak(self.device)
-        sustained = ms > 100.0
-        peak = tf32["tf32_tflops_sustained"] if sustained else tf32["tf32_tflops"]
+        cands = {"cuBLAS TF32 GEMM 8192^3 measured in this run, burst (best of 10)": tf32["tf32_tflops"],
+                 "cuBLAS TF32 GEMM 8192^3 measured in this run, sustained (back to back for ~2 s)": tf32["tf32_tflops_sustained"],
+                 "MEASURED_PEAKS.json bf16 burst / 2": peaks["bf16_tflops"] / 2,
+                 "MEASURED_PEAKS.json bf16 sustained / 2": peaks["bf16_tflops_sustained"] / 2}
+        peak_name = max(cands, key=cands.get)
+        peak = cands[peak_name]
         roof = {"bound": "tensor", "kernel": "mr::st::score_topk_kernel<2, 32> (tcgen05.mma kind::tf32, cta_group::2) + list merge",
                 "achieved": ach, "peak": peak,
-                "peak_source": "cuBLAS TF32 GEMM 8192^3 measured in this run (" + ("sustained, back to back for ~2 s" if sustained else "burst, best of 10") + ")",
+                "peak_source": "largest of the four dense-TF32 candidates: " + peak_name,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms_per_launch": ms,
                 "tensor_passes": passes, "logical_tflops": local_flops / (ms * 1e-3) / 1e12,
                 "algorithmic_flops_per_launch": passes * local_flops,

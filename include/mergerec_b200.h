@@ -282,13 +282,19 @@ int mr_normalize_rows(const float* x, int64_t rows, int E, float* out, mr_stream
  * inter-balancing weights of pcb.py:44-53.  clamp_lo / clamp_hi (dev, K floats) are the int(d*0.01)-th and
  * int(d*0.99 - 1)-th smallest |tau_k| (pcb.py:17-27; obtained with mr_ties_select on the magnitudes);
  * q_index = int(d * (1 - density)) is the ascending rank of the lower clamp of the balancing weights, found here
- * exactly: dense = 1 runs three full histogram passes; dense = 0 runs them on a 1/32 sample, then two windowed passes
- * over everything around the sample's quantile, and reports per model in status (dev int32 K) 1 = exact result,
- * 0 = the window missed (call again with dense = 1).  task_out (K rows, ldo) / thr_out (K x {q, max}) are optional
- * diagnostics.  exp / tanh are CUDA's: values agree with torch's CPU kernels to ~1 ulp (floating-point contract). */
-int64_t mr_pcb_workspace_bytes(int K);
+ * exactly.  flags = 0: fast search -- a 1/32 sample (one pass, keys cached) brackets the quantile between two order
+ * statistics of the sample, then ONE pass over everything counts what lies below that window and collects the keys
+ * inside it; MR_PCB_DENSE: three full histogram passes instead.  The divisions by per-model ranges and per-column sums
+ * use a prepared reciprocal with two FMA corrections (correctly rounded while clamps and divisors lie in
+ * [2^-60, 2^60]); MR_PCB_IEEE compiles every division as an IEEE divide instead.  status (dev int32 K) per model:
+ * 1 = exact result, 0 = the fast search's window missed (call again with MR_PCB_DENSE), 2 = operands outside the fast
+ * divisions' range (call again with MR_PCB_IEEE).  task_out (K rows, ldo) / thr_out (K x {q, max}) are optional
+ * diagnostics.  exp / tanh are CUDA's: values agree with torch's CPU kernels to ~1 ulp (floating-point contract).
+ * ws: dev scratch of mr_pcb_workspace_bytes(d, K) bytes (sample keys, per-warp candidate lists, histograms). */
+enum { MR_PCB_DENSE = 1, MR_PCB_IEEE = 2 };
+int64_t mr_pcb_workspace_bytes(int64_t d, int K);
 int mr_pcb_vectors(const float* base, const float* const* models, int K, int64_t d, const float* clamp_lo,
-                   const float* clamp_hi, int64_t q_index, int dense, int32_t* status, float* out, int64_t ldo,
+                   const float* clamp_hi, int64_t q_index, int flags, int32_t* status, float* out, int64_t ldo,
                    float* task_out, float* thr_out, void* ws, int64_t ws_bytes, mr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -32,39 +32,78 @@ def _magnitude_of(cut: torch.Tensor) -> torch.Tensor:
 
 
 def get_pcb_vectors(base_model: FlattenedModel, models: List[FlattenedModel], density: float = 0.2,
-                    return_diagnostics: bool = False, force_dense: bool = False, **__):
+                    return_diagnostics: bool = False, force_dense: bool = False, force_ieee: bool = False, **__):
     lib = _lib.load()
     rows = as_rows(models)
     K, d = len(rows), base_model.numel()
     dev = base_model.device
     i_lo, i_hi = int(d * 0.01), int(d * (1 - 0.01) - 1)          # pcb.py:20-21 with min_ratio = max_ratio = 0.01
     i_hi = i_hi if i_hi >= 0 else d + i_hi                       # sorted_x[-1] for tiny d, like the reference's indexing
-    if i_lo == 0:
-        # d < 100: sorted_x[0] is the row minimum of |tau| (pcb.py:20); the order-statistic select answers "keep
-        # everything" for k = d with cut 0 rather than the d-th largest magnitude, so take the minimum directly
-        lo = torch.stack([(r - base_model).abs().min() for r in rows]).to(torch.float32).contiguous()
-    else:
-        lo = _magnitude_of(select_kth_largest(base_model, rows, d - i_lo)).contiguous()
-    hi = _magnitude_of(select_kth_largest(base_model, rows, d - i_hi)).contiguous()
+    def clamps(defer: bool):
+        """1 % / 99 % magnitude clamps (exact order statistics of |tau_k|) and the deferred select statuses."""
+        sts = []
+        if i_lo == 0:
+            # d < 100: sorted_x[0] is the row minimum of |tau| (pcb.py:20); the order-statistic select answers "keep
+            # everything" for k = d with cut 0 rather than the d-th largest magnitude, so take the minimum directly
+            lo_ = torch.stack([(r - base_model).abs().min() for r in rows]).to(torch.float32).contiguous()
+        else:
+            c = select_kth_largest(base_model, rows, d - i_lo, defer_status=defer)
+            if defer:
+                c, st_ = c
+                sts.append(st_)
+            lo_ = _magnitude_of(c).contiguous()
+        c = select_kth_largest(base_model, rows, d - i_hi, defer_status=defer)
+        if defer:
+            c, st_ = c
+            sts.append(st_)
+        return lo_, _magnitude_of(c).contiguous(), sts
+
     q_index = int(d * (1 - density))                             # pcb.py:53: min_ratio = 1 - density, max_ratio = 0
     out = alloc_rows(K, d, dev)
     ldo = max(out.stride(0), d)
     task = alloc_rows(K, d, dev) if return_diagnostics else None
     thr = torch.empty((K, 2), dtype=torch.float32, device=dev) if return_diagnostics else None
-    ws_bytes = int(lib.mr_pcb_workspace_bytes(K))
+    ws_bytes = int(lib.mr_pcb_workspace_bytes(d, K))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     status = torch.zeros(K, dtype=torch.int32, device=dev)
-    for dense in ((1,) if force_dense else (0, 1)):
-        # fast path: dense radix passes on a 1/32 sample, then two windowed passes over everything; a window that misses
-        # the wanted rank is reported in `status` and the three dense passes over the whole vector run instead
-        rc = lib.mr_pcb_vectors(_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(lo), _lib.dptr(hi),
-                                q_index, dense, _lib.dptr(status), _lib.dptr(out), ldo, _lib.dptr(task), _lib.dptr(thr),
+
+    def run(lo_, hi_, flags: int):
+        rc = lib.mr_pcb_vectors(_lib.dptr(base_model, torch.float32), _lib.ptr_array(rows), K, d, _lib.dptr(lo_), _lib.dptr(hi_),
+                                q_index, flags, _lib.dptr(status), _lib.dptr(out), ldo, _lib.dptr(task), _lib.dptr(thr),
                                 _lib.dptr(ws), ws_bytes, _lib.stream_handle())
         _lib.check(rc, "mr_pcb_vectors")
-        if bool((status.cpu() == 1).all()):
+
+    # Common case, one host synchronisation for the whole call: both magnitude selects run deferred (sampled bracket),
+    # then the fast quantile search (sample, one windowed pass over everything) and the build; the three status words
+    # are read together.  A select whose bracket missed is redone on its exact path; a quantile window that missed the
+    # wanted rank (status 0) is redone with the three dense radix passes over the whole vector; clamps or ranges outside
+    # [2^-60, 2^60] (status 2: the prepared-reciprocal divisions are not valid there) are redone with IEEE divides.
+    flags = _lib.MR_PCB_DENSE if force_dense else 0
+    if force_ieee:
+        flags |= _lib.MR_PCB_IEEE
+    lo, hi, sel_status = clamps(defer=True)
+    run(lo, hi, flags)
+    got = torch.cat(sel_status + [status]).cpu()
+    n_sel = sum(int(s.numel()) for s in sel_status)
+    if bool((got[:n_sel] != 1).any()):
+        lo, hi, _ = clamps(defer=False)
+        run(lo, hi, flags)
+        got = torch.cat([got[:n_sel], status.cpu()])
+    for _ in range(2):          # at most: window missed -> dense, then range -> IEEE (or the other way round)
+        st_ = got[n_sel:]
+        if bool((st_ == 1).all()):
             break
+        if bool((st_ == 0).any()):
+            if flags & _lib.MR_PCB_DENSE:
+                raise _lib.MergeRecLibraryError("PCB quantile search failed")
+            flags |= _lib.MR_PCB_DENSE
+        if bool((st_ == 2).any()):
+            flags |= _lib.MR_PCB_IEEE
+        run(lo, hi, flags)
+        got = torch.cat([got[:n_sel], status.cpu()])
     else:
-        raise _lib.MergeRecLibraryError("PCB quantile search failed")
+        if bool((got[n_sel:] != 1).any()):
+            raise _lib.MergeRecLibraryError(f"PCB vectors failed with status {got[n_sel:].tolist()}")
     if return_diagnostics:
         return out, task, thr, lo, hi
     return out

@@ -130,3 +130,36 @@ def test_fast_and_dense_quantile_paths_agree():
         a, _, ta, *_ = get_pcb_vectors(tb, tm, density=dens, return_diagnostics=True)
         b, _, tb2, *_ = get_pcb_vectors(tb, tm, density=dens, return_diagnostics=True, force_dense=True)
         assert torch.equal(ta, tb2) and torch.equal(a[:, :d], b[:, :d]), dens
+
+
+def test_prepared_reciprocal_divisions_equal_ieee_divides():
+    """The kernels divide by per-model ranges and per-column sums with a prepared reciprocal and two FMA corrections
+    (csrc/pcb.cu: pcb_div_by); MR_PCB_IEEE compiles the same kernels with IEEE divides.  Both must agree bit for bit --
+    balancing weights, thresholds and vectors -- on the fast and on the dense search, also for unaligned rows."""
+    K, d = 5, 600_011
+    base, models = synth.make_flat(d, K, seed=41)
+    tb, tm = dev(base), [dev(m) for m in models]
+    for force_dense in (False, True):
+        a = get_pcb_vectors(tb, tm, density=0.2, return_diagnostics=True, force_dense=force_dense)
+        b = get_pcb_vectors(tb, tm, density=0.2, return_diagnostics=True, force_dense=force_dense, force_ieee=True)
+        for x, y in zip(a[:3], b[:3]):
+            assert torch.equal(x[..., :d].view(torch.int32) if x.dim() == 2 and x.shape[1] >= d else x.view(torch.int32),
+                               y[..., :d].view(torch.int32) if y.dim() == 2 and y.shape[1] >= d else y.view(torch.int32))
+    # unaligned pointers take the scalar-load instantiation
+    ub, um = dev(np.concatenate([[0], base]).astype(np.float32))[1:], [dev(np.concatenate([[0], m]).astype(np.float32))[1:] for m in models]
+    a = get_pcb_vectors(ub, um, density=0.2)
+    b = get_pcb_vectors(tb, tm, density=0.2)
+    assert torch.equal(a[:, :d], b[:, :d])
+
+
+def test_degenerate_ranges_fall_back_to_ieee_divides():
+    """A clamp range outside [2^-60, 2^60] is reported by the kernels (status 2) and the call reruns with IEEE divides:
+    tiny updates (|tau| ~ 1e-25) give the same vectors as the forced-IEEE path and stay finite."""
+    K, d = 3, 200_003
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal(d).astype(np.float32) * np.float32(1e-20)
+    models = [(base + rng.standard_normal(d).astype(np.float32) * np.float32(1e-25)).astype(np.float32) for _ in range(K)]
+    tb, tm = dev(base), [dev(m) for m in models]
+    a = get_pcb_vectors(tb, tm, density=0.2)
+    b = get_pcb_vectors(tb, tm, density=0.2, force_ieee=True)
+    assert torch.equal(a[:, :d].view(torch.int32), b[:, :d].view(torch.int32))
