@@ -7,8 +7,9 @@ A "step" is one pass of the hot path over one batch of synthetic input (random-i
 architecture; there is no network for checkpoints).  `value` is the whole-job throughput with inputs already
 in HBM; `e2e` is the same metric through the public API with HOST buffers (pinned) and the host<->device
 copies inside the timed region.  `roofline` times the dominant kernel alone with CUDA events;
-`cpu_baseline` times the CPU oracle (a port of the reference's algorithm, oracle/) on the box's host cores.
-`--impl reference` runs only that CPU arm.  See DESIGN.md section "Measurement".
+`cpu_baseline` times the UNMODIFIED reference packages (baseline/_ref, copied there by baseline/install_ref.py) on the
+box's host cores, with the oracle port (oracle/) beside it; where baseline/_ref is absent only the port runs and the
+line says `kind: "port"`.  `--impl reference` runs only that CPU arm.  See DESIGN.md section "Measurement".
 """
 from __future__ import annotations
 

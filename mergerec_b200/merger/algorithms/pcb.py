@@ -5,8 +5,9 @@
 * the 1 % / 99 % clamp of ``|tau_k|`` (``_clamp(torch.abs(task_vectors), 0.01, 0.01)``, pcb.py:17-27,42) are the
   ``d - int(d*0.01)``-th and ``d - int(d*0.99 - 1)``-th LARGEST magnitudes -- found with the TIES selection kernels;
 * the lower clamp of the balancing weights (``_clamp(task_pcb, 1 - density, 0)``, pcb.py:53) is the
-  ``int(d*(1-density))``-th smallest of values that only exist on the fly -- ``mr_pcb_vectors`` finds it with three
-  histogram passes and never materialises a (K, d) temporary.
+  ``int(d*(1-density))``-th smallest of values that only exist on the fly -- ``mr_pcb_vectors`` finds it exactly with a
+  sampled key window and ONE pass over the data (three dense histogram passes as the fallback) and never materialises a
+  (K, d) temporary.
 
 Floating-point contract: torch's CPU ``exp`` / ``tanh`` and CUDA's differ in the last bit, so the vectors agree with the
 reference to ~1e-6 of the row scale except in columns holding an element whose balancing weight lies within a few ulp

@@ -18,5 +18,6 @@ for _ in range(reps):
     out = get_pcb_vectors(base, models, 0.2)
 e1.record(); e1.synchronize()
 print("get_pcb_vectors ms", e0.elapsed_time(e1) / reps, "checksum", int(out.view(torch.int32).to(torch.int64).sum().item()), flush=True)
-out2 = get_pcb_vectors(base, models, 0.2, force_ieee=True)
-print("prepared-reciprocal divisions == IEEE divides, bit for bit:", bool(torch.equal(out.view(torch.int32), out2.view(torch.int32))), flush=True)
+if len(sys.argv) <= 2:
+    out2 = get_pcb_vectors(base, models, 0.2, force_ieee=True)
+    print("prepared-reciprocal divisions == IEEE divides, bit for bit:", bool(torch.equal(out.view(torch.int32), out2.view(torch.int32))), flush=True)
