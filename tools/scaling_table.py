@@ -9,7 +9,7 @@ for n in (1, 2, 4, 8):
 t1 = rows[0][1]["ms_per_step"]
 m1 = rows[0][1]["merger"]["ms_per_step"]
 print("# BASELINE config 5 (evaluator, item table sharded over N GPUs, one NCCL all-gather + merge) and the nested merger line")
-print("# `python bench.py --gpus N --steps 20 --warmup 5` (torch.distributed.run for N > 1); CUDA events, max over ranks")
+print("# `python bench.py --gpus N ` (N = 1: --steps 20 --warmup 5; N > 1: torch.distributed.run, --steps 10 --warmup 3); CUDA events, max over ranks")
 print(f"{'N':>2} {'ms/step':>9} {'scores/s':>11} {'speed-up':>8} {'eff.':>6} {'e2e ms':>8} {'kernel ms':>10} {'gather+merge':>12} {'host ms':>8} {'sm MHz':>7}  checksum(topk_ids, score bits)")
 for n, b in rows:
     st = b["stage_ms"]
