@@ -77,6 +77,7 @@ struct Params {
     // a correctness condition, and can therefore not deadlock.
     int32_t* sync;
     int sync_w, sync_windows, sync_lead;
+    int sync_giveup;    // windows after which a unit stops waiting if a member of its stream has not even started (0 = never)
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------------
@@ -466,6 +467,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
             for (int ui = cluster_id; get_unit(p, ui, u); ui += num_clusters) {
                 const int qrow = (u.qb * CG + (int)rank) * kBlockM;
                 int32_t* pace = p.sync ? p.sync + (size_t)u.stream * p.sync_windows : nullptr;
+                // A stream whose units are spread over two waves of CTA pairs (QG * S does not fill a wave exactly, e.g.
+                // 18 x 4 of 74 at BASELINE config 4) has members that start a whole unit later: a unit that still finds a
+                // member absent `sync_giveup` windows into its own walk stops waiting for good instead of paying the
+                // timeout at every window.
+                bool peers = true;
                 for (int t = u.t0; t < u.t1; ++t) {
                     const int nrow = t * kBlockN + (int)rank * C::kBRows;
                     if (pace && u.members > 1) {
@@ -473,7 +479,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_uhi, const __grid_cons
                         if (r > 0 && r % p.sync_w == 0) {
                             const int j = r / p.sync_w;                     // window j starts; window j - 1 is issued
                             if (leader) atomicAdd(&pace[j - 1], 1);
-                            if (j >= p.sync_lead) {
+                            if (peers && p.sync_giveup > 0 && j == p.sync_lead + p.sync_giveup &&
+                                *reinterpret_cast<volatile int32_t*>(&pace[0]) < u.members)
+                                peers = false;
+                            if (j >= p.sync_lead && peers) {
                                 const long long t_start = clock64();
                                 while (*reinterpret_cast<volatile int32_t*>(&pace[j - p.sync_lead]) < u.members) {
                                     if (clock64() - t_start > 60000) break;    // ~40 us: give up, never block
@@ -895,6 +904,7 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     p.sync = nullptr; p.sync_w = pl.sync_w; p.sync_windows = pl.sync_windows;
     p.sync_lead = st::env_int("MR_SCORE_PACE_LEAD", 2);
     if (p.sync_lead < 1) p.sync_lead = 1;
+    p.sync_giveup = st::env_int("MR_SCORE_PACE_GIVEUP", 8);
     if (pl.sync_bytes) {
         p.sync = reinterpret_cast<int32_t*>(w + pl.cand_bytes + pl.part_bytes);
         cudaError_t e = cudaMemsetAsync(p.sync, 0, (size_t)pl.sync_bytes, s);
