@@ -77,6 +77,7 @@ struct Params {
     // a correctness condition, and can therefore not deadlock.
     int32_t* sync;
     int sync_w, sync_windows, sync_lead;
+    int wave;           // CTA pairs (clusters) in the grid = units that run at the same time
     int sync_giveup;    // windows after which a unit stops waiting if a member of its stream has not even started (0 = never)
 };
 
@@ -241,17 +242,43 @@ struct Unit {
     int members;   // units on that stream (query blocks of the group)
 };
 __device__ __forceinline__ bool get_unit(const Params& p, int u, Unit& out) {
-    if (u >= p.QB * p.S) return false;
-    const int per_group = p.QG * p.S;
-    const int g = u / per_group, r = u - g * per_group;
-    const int qg0 = g * p.QG;
-    const int qgn = (p.QB - qg0) < p.QG ? (p.QB - qg0) : p.QG;
-    out.split = r / qgn;
-    out.qb = qg0 + (r - out.split * qgn);
+    const int U = p.QB * p.S;
+    if (u >= U) return false;
+    if (p.QG == 0) {
+        // wave-aligned order (default): units are numbered query-block-major, u = qb * S + split, and wave w of the
+        // grid's CTA pairs runs units [w * wave, (w + 1) * wave) -- so the pairs running at the same time walk exactly S
+        // item streams, each shared by the units of that wave with the same split (wave / S of them, +- 1 when S does not
+        // divide the wave), whatever S is.
+        // Inside a wave the pairs are handed out split-major (pairs 0 .. m_0 - 1 walk stream 0, the next m_1 stream 1,
+        // ...), so neighbouring SMs share a stream -- with S = 2 this is the 37 + 37 arrangement the numbers above were
+        // measured with.
+        const int w = u / p.wave;
+        const int lo = w * p.wave, hi = (lo + p.wave) < U ? (lo + p.wave) : U;
+        int r = u - lo, sp = 0, m = 0;
+        for (; sp < p.S; ++sp) {
+            m = (hi + p.S - 1 - sp) / p.S - (lo + p.S - 1 - sp) / p.S;   // number of v in [lo, hi) with v % S == sp
+            if (r < m) break;
+            r -= m;
+        }
+        const int first = lo + (sp - lo % p.S + p.S) % p.S;               // first v >= lo with v % S == sp
+        const int v = first + r * p.S;
+        out.split = sp;
+        out.qb = v / p.S;
+        out.stream = w * p.S + sp;
+        out.members = m;
+    } else {
+        // explicit query groups (MR_SCORE_QGROUP): group g = QG query blocks x S splits, split-major inside the group
+        const int per_group = p.QG * p.S;
+        const int g = u / per_group, r = u - g * per_group;
+        const int qg0 = g * p.QG;
+        const int qgn = (p.QB - qg0) < p.QG ? (p.QB - qg0) : p.QG;
+        out.split = r / qgn;
+        out.qb = qg0 + (r - out.split * qgn);
+        out.stream = g * p.S + out.split;
+        out.members = qgn;
+    }
     out.t0 = (int)(((int64_t)out.split * p.T) / p.S);
     out.t1 = (int)(((int64_t)(out.split + 1) * p.T) / p.S);
-    out.stream = g * p.S + out.split;
-    out.members = qgn;
     return true;
 }
 
@@ -795,11 +822,12 @@ static Plan make_plan(int64_t Q, int64_t N, int K, bool bf16) {
     }
     if (s > smax) s = smax;
     pl.S = s;
-    // query blocks per L2 group: one wave of CTA pairs = QG query blocks x S item splits, so that the pairs running at
-    // the same time walk only S item streams and clusters / S query blocks (measured at BASELINE config 5 with the L2
-    // eviction hints: QG = 37, S = 2 -> 443 ms; 16 x 2 -> 447; 18 x 4 -> 466; 8 x 9 -> 481; 74 x 2 -> 548)
-    pl.QG = env_int("MR_SCORE_QGROUP", clusters / pl.S);
-    if (pl.QG < 1) pl.QG = 1;
+    // One wave of CTA pairs walks only S item streams (get_unit's wave-aligned order), so an item tile is shared by
+    // wave / S query blocks and the query operands of a wave fit L2 next to the item streams (measured at BASELINE
+    // config 5 with the L2 eviction hints, as explicit groups QG x S: 37 x 2 -> 443 ms; 16 x 2 -> 447; 18 x 4 -> 466;
+    // 8 x 9 -> 481; 74 x 2 -> 548).  MR_SCORE_QGROUP = explicit query groups of that many blocks (experiments).
+    pl.QG = env_int("MR_SCORE_QGROUP", 0);
+    if (pl.QG < 0) pl.QG = 0;
     const int64_t units = (int64_t)pl.QB * pl.S;
     pl.grid = (int)((units < clusters ? units : clusters) * pl.cg);
     if (pl.grid < pl.cg) pl.grid = pl.cg;
@@ -808,7 +836,8 @@ static Plan make_plan(int64_t Q, int64_t N, int K, bool bf16) {
     // pacing counters: (query groups x splits) streams x windows of sync_w tiles
     pl.sync_w = env_int("MR_SCORE_PACE_TILES", 1);
     if (pl.sync_w < 1) pl.sync_w = 0;
-    const int groups = (pl.QB + pl.QG - 1) / pl.QG;
+    const int wave = pl.grid / pl.cg;
+    const int groups = pl.QG ? (pl.QB + pl.QG - 1) / pl.QG : (int)((units + wave - 1) / wave);   // streams = groups x S
     pl.sync_windows = pl.sync_w ? ((pl.T + pl.S - 1) / pl.S + pl.sync_w - 1) / pl.sync_w + 2 : 0;
     pl.sync_bytes = pl.sync_w ? (((int64_t)groups * pl.S * pl.sync_windows * 4 + 255) & ~(int64_t)255) : 0;
     return pl;
@@ -897,7 +926,7 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     const int bk = bf16 ? 32 : pl.bk;                 // bf16 rows are 64 elements = 128 bytes: the BK = 32 geometry
     const int kelems = bf16 ? 64 : bk;
     p.KB = (E + kelems - 1) / kelems;
-    p.T = pl.T; p.QB = pl.QB; p.S = pl.S; p.QG = pl.QG;
+    p.T = pl.T; p.QB = pl.QB; p.S = pl.S; p.QG = pl.QG; p.wave = pl.grid / pl.cg;
     p.cand = reinterpret_cast<mr::u64*>(w);
     p.dbg = g_score_dbg;
     p.l2_hint = st::env_int("MR_SCORE_L2HINT", 1);
