@@ -208,6 +208,15 @@ int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, const float* Ih
                   int K, int32_t id_base, int mode, float* out_val, int32_t* out_id, void* ws, int64_t ws_bytes,
                   mr_stream_t stream);
 
+/* Host-only view of the kernel's static schedule for a problem shape (no CUDA call; tests/test_schedule.py).  A unit =
+ * (block of 256 queries, contiguous range of 256-item tiles); the grid's CTA pairs run the units in waves of `wave`,
+ * unit u on pair u % wave.  plan_out (8 int32): query blocks, item tiles, item splits S, wave, CTAs per pair, item
+ * streams (each with its pacing counters), pacing windows per stream, tiles per window.  units_out (optional, 6 int32
+ * per unit, at most max_units of them): query block, split, first tile, end tile, stream, units sharing that stream.
+ * Returns the number of units (or an argument error < 0). */
+int64_t mr_score_topk_schedule(int64_t Q, int64_t N, int K, int mode, int32_t* plan_out, int32_t* units_out,
+                               int64_t max_units);
+
 /* Diagnostics: when dev_buf != NULL, later mr_score_topk launches of this thread make block 0 record clock64()
  * stamps per tile (3 roles x 64 tiles x 4 slots of int64: tools/score_sweep.py prints them).  NULL switches it off. */
 int mr_score_topk_debug_buffer(void* dev_buf, int64_t bytes);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "mr_score_topk_workspace_bytes": ([_i64, _i64, _i32, _i32], _i64),
     "mr_score_topk": ([_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "mr_score_topk_debug_buffer": ([_vp, _i64], C.c_int),
+    "mr_score_topk_schedule": ([_i64, _i64, _i32, _i32, _vp, _vp, _i64], _i64),
     "mr_to_bf16": ([_vp, _i64, _vp, _vp], C.c_int),
     "mr_split_tf32": ([_vp, _i64, _vp, _vp, _vp], C.c_int),
     "mr_scores_fp32": ([_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp], C.c_int),

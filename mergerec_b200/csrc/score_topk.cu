@@ -241,7 +241,7 @@ struct Unit {
     int stream;    // index of the item stream this unit walks = (query group, split): its units share every item tile
     int members;   // units on that stream (query blocks of the group)
 };
-__device__ __forceinline__ bool get_unit(const Params& p, int u, Unit& out) {
+__host__ __device__ __forceinline__ bool get_unit(const Params& p, int u, Unit& out) {
     const int U = p.QB * p.S;
     if (u >= U) return false;
     if (p.QG == 0) {
@@ -876,6 +876,32 @@ extern "C" int mr_score_topk_debug_buffer(void* dev_buf, int64_t bytes) {
                "mr_score_topk_debug_buffer: need %d bytes", 4 * st::kDbgTiles * st::kDbgSlots * 8);
     g_score_dbg = reinterpret_cast<long long*>(dev_buf);
     return MR_OK;
+}
+
+// Host-only view of the static schedule (no CUDA call: the plan and get_unit are plain arithmetic).
+extern "C" int64_t mr_score_topk_schedule(int64_t Q, int64_t N, int K, int mode, int32_t* plan_out, int32_t* units_out,
+                                          int64_t max_units) {
+    using namespace mr;
+    if (Q < 1 || N < 1 || K < 1 || K > MR_MAX_FUSED_TOPK || !plan_out) {
+        set_error("mr_score_topk_schedule: need Q, N >= 1, 1 <= K <= %d and plan_out", MR_MAX_FUSED_TOPK);
+        return MR_ERR_INVALID_ARG;
+    }
+    const st::Plan pl = st::make_plan(Q, N, K, mode == MR_SCORE_BF16);
+    st::Params p{};
+    p.T = pl.T; p.QB = pl.QB; p.S = pl.S; p.QG = pl.QG; p.wave = pl.grid / pl.cg;
+    const int64_t U = (int64_t)pl.QB * pl.S;
+    const int groups = pl.QG ? (pl.QB + pl.QG - 1) / pl.QG : (int)((U + p.wave - 1) / p.wave);
+    const int32_t plan[8] = {pl.QB, pl.T, pl.S, p.wave, pl.cg, groups * pl.S, pl.sync_windows, pl.sync_w};
+    for (int i = 0; i < 8; ++i) plan_out[i] = plan[i];
+    if (units_out) {
+        for (int64_t u = 0; u < U && u < max_units; ++u) {
+            st::Unit un;
+            st::get_unit(p, (int)u, un);
+            int32_t* o = units_out + u * 6;
+            o[0] = un.qb; o[1] = un.split; o[2] = un.t0; o[3] = un.t1; o[4] = un.stream; o[5] = un.members;
+        }
+    }
+    return U;
 }
 
 extern "C" int64_t mr_score_topk_workspace_bytes(int64_t Q, int64_t N, int E, int K) {
