@@ -71,9 +71,9 @@ struct Params {
     long long* dbg;     // optional timestamps of block 0 (mr_score_topk_debug_buffer), else NULL
     int l2_hint;        // 1: query loads evict_last, item loads evict_first (MR_SCORE_L2HINT, default on)
     // Pacing of the units that share an item stream (NULL = off): sync[stream * sync_windows + j] counts the units whose
-    // producer has issued the loads of tile window j (sync_w tiles); a producer does not start window j + 2 before every
-    // unit of its stream has issued window j -- or a short timeout has passed: the pacing is a performance hint (it keeps
-    // the units within 2 windows of each other, so an item tile fetched by the first is still in L2 for the last), never
+    // producer has issued the loads of tile window j (sync_w tiles); a producer does not start window j + sync_lead
+    // before every unit of its stream has issued window j -- or a short timeout has passed: the pacing is a performance hint
+    // (it keeps the units within sync_lead windows of each other, so an item tile fetched by the first is still in L2 for the last), never
     // a correctness condition, and can therefore not deadlock.
     int32_t* sync;
     int sync_w, sync_windows, sync_lead;
@@ -957,7 +957,7 @@ extern "C" int mr_score_topk(const float* Uhi, const float* Ulo, int64_t Q, cons
     p.dbg = g_score_dbg;
     p.l2_hint = st::env_int("MR_SCORE_L2HINT", 1);
     p.sync = nullptr; p.sync_w = pl.sync_w; p.sync_windows = pl.sync_windows;
-    p.sync_lead = st::env_int("MR_SCORE_PACE_LEAD", 2);
+    p.sync_lead = st::env_int("MR_SCORE_PACE_LEAD", 1);   // lead 1 / 2 / 3 at config 5: 376.5 / 379.6 / 381.2 ms
     if (p.sync_lead < 1) p.sync_lead = 1;
     p.sync_giveup = st::env_int("MR_SCORE_PACE_GIVEUP", 8);
     if (pl.sync_bytes) {
