@@ -29,7 +29,7 @@ constexpr int kPcbThreads = 256;
 constexpr int kPcbWarps = kPcbThreads / 32;
 constexpr int kPcbBins = 2048;
 constexpr int kPcbSlots = 2;        // sample order statistics searched at once: window start, window end
-constexpr int64_t kPcbStride = 32;  // sample of the fast path: columns 0, 32, 64, ...
+constexpr int64_t kPcbStride = 32;  // sample of the fast path: 1 / 32 of the columns (pcb_sample_column)
 
 struct PcbState {     // one per (slot, model); the window search uses the slot-0 entries
     uint32_t prefix;  // key bits decided so far
@@ -139,7 +139,19 @@ __device__ __forceinline__ int pcb_load_quad(const float* __restrict__ base, con
     return nvalid;
 }
 
-// Radix pass over the columns 0, stride, 2 stride, ... -- pass 0: bins = key >> 21 (+ row maxima); pass 1:
+// The 1 / stride sample of the fast path: one quad of 4 adjacent columns out of every block of 4 * stride columns, at a
+// hashed position inside its block.  Adjacent columns share a 32-byte DRAM sector (a pick of 4 costs what a pick of 1
+// costs), and the hashed position keeps the sample from locking onto a fixed column residue of the weight matrices (a
+// plain stride of 32 would only ever see columns = 0 mod 32 of a 768- or 1024-wide row -- e.g. never, or always, an outlier
+// dimension of a transformer -- and a biased sample costs the fallback to the dense search).  Only whole blocks are sampled.
+__host__ __device__ __forceinline__ int64_t pcb_sample_count(int64_t d, int64_t stride) { return 4 * (d / (4 * stride)); }
+__device__ __forceinline__ int64_t pcb_sample_column(int64_t i, int64_t stride) {
+    const int64_t c = i >> 2;
+    const uint32_t h = ((uint32_t)c * 2654435761u) >> 16;
+    return c * (4 * stride) + 4 * (int64_t)(h % (uint32_t)stride) + (i & 3);
+}
+
+// Radix pass over the columns (stride = 1) or over the sample (stride > 1) -- pass 0: bins = key >> 21 (+ row maxima); pass 1:
 // (key >> 10) & 2047 inside prefix; pass 2: key & 1023 inside prefix.  stride = 1: the dense search (all three passes);
 // stride > 1: the fast path's only pass over the sample (pass 0), which also caches the keys in skeys (K, n_s).
 template <int K>
@@ -159,14 +171,14 @@ pcb_hist_kernel(const float* __restrict__ base, PtrPack<K> m, int64_t d, int64_t
     for (int k = 0; k < K; ++k) mx[k] = 0;
     const int64_t tail0 = d & ~(int64_t)31;
     const int64_t span = (int64_t)gridDim.x * blockDim.x;
-    const int64_t n_vis = (d + stride - 1) / stride;
+    const int64_t n_vis = stride == 1 ? d : pcb_sample_count(d, stride);
     const int64_t rounds = (n_vis + span - 1) / span;  // every lane runs every round (the match below is warp-wide)
     auto sweep = [&](auto safe_tag) {
     constexpr bool SAFE = decltype(safe_tag)::value;
     for (int64_t it = 0; it < rounds; ++it) {
         const int64_t i = it * span + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const int64_t j = i * stride;
-        const bool live = j < d;
+        const bool live = i < n_vis;
+        const int64_t j = !live ? 0 : (stride == 1 ? i : pcb_sample_column(i, stride));
         float x[K], tau[K], A[K], task[K];
         const float b = live ? ldg_stream1(base + j) : 0.f;
 #pragma unroll
@@ -563,7 +575,7 @@ struct PcbWs {
 };
 static PcbWs pcb_layout(int64_t d, int K) {
     PcbWs L;
-    L.n_s = (d + kPcbStride - 1) / kPcbStride;
+    L.n_s = pcb_sample_count(d, kPcbStride);
     // sampling error of an order statistic of the sample: sigma <= sqrt(n_s) / 2 ranks; the window spans +-R = 6 sigma
     // + 16 sample ranks, i.e. about 2 R * stride elements of the full vector -- provisioned four times over
     const int64_t r_max = (int64_t)(3.0 * sqrt((double)L.n_s)) + 16;
