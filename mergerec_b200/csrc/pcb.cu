@@ -61,9 +61,11 @@ __device__ __forceinline__ float pcb_unkey(uint32_t k) {
 // residual is exact in an FMA) is faithful; a second correction of a faithful quotient with a correctly rounded
 // reciprocal is the correctly rounded quotient (Markstein's division theorem) -- five FMA-pipe instructions, no MUFU, no
 // branch, and x = +0 gives +0.  The kernels are compiled twice: SAFE = true uses these sequences and is valid while every
-// divisor and every clamp lies in [2^-60, 2^60] (no residual can underflow; numerators never exceed their divisors by
-// more than that); pcb_status_kernel checks exactly this on the device and reports status 2 otherwise, upon which the
-// caller reruns with MR_PCB_IEEE (SAFE = false: __fdiv_rn everywhere).
+// divisor and every upper clamp lies in [2^-60, 2^60] (numerators never exceed their divisors by more than that, and a
+// residual can only underflow for a numerator below ~2^-100, where a last-bit difference from IEEE is 20 orders of
+// magnitude under every tolerance of this floating-point path); pcb_status_kernel checks exactly this on the device and
+// reports status 2 otherwise, upon which the caller reruns with MR_PCB_IEEE (SAFE = false: __fdiv_rn everywhere).
+// tests/test_division_sequences.py checks the sequence exhaustively over the mantissas of x on the CPU.
 template <bool SAFE>
 __device__ __forceinline__ float pcb_div_by(float x, float y, float r) {
     if (!SAFE) return __fdiv_rn(x, y);
